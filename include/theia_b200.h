@@ -1,0 +1,175 @@
+/* theia_b200 -- C ABI of the B200-native Theia distillation hot path.
+ *
+ * Plain C: device pointers are `void*` / typed pointers into CUDA memory that the CALLER owns
+ * (PyTorch allocates every tensor, workspace included); every entry point takes an explicit
+ * `cudaStream_t` (passed as void*), never synchronises, never allocates on the hot path, and
+ * returns 0 on success or a non-zero error code (`theia_last_error()` gives the text).
+ *
+ * The reference (bdaiinstitute/theia) has no native layer; the entry points below replace the
+ * PyTorch / transformers library calls its Python makes on this path.  Each one cites the
+ * reference call site it replaces (paths relative to /root/reference, or `hf:` =
+ * site-packages/transformers 5.5.0).
+ */
+#ifndef THEIA_B200_H
+#define THEIA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THEIA_OK 0
+#define THEIA_ERR_ARG 1
+#define THEIA_ERR_CUDA 2
+#define THEIA_ERR_UNSUPPORTED 3
+
+const char* theia_last_error(void);
+int theia_version(void);
+/* Number of kernels this library has launched since load (all streams, this process). */
+long long theia_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * tcgen05 GEMM / implicit-GEMM convolution.   D[M,N] (+)= A[M,K] * B[N,K]^T , bf16 in, fp32
+ * accumulate in TMEM, fused epilogue.  Replaces: nn.Linear (hf:models/vit/modeling_vit.py:216-230,
+ * 262, 290, 305; src/theia/models/adapter_heads.py:313-314,325-326), nn.Conv2d(3,D,16,16)
+ * (hf:modeling_vit.py:151,166), nn.Conv2d 3x3 / nn.ConvTranspose2d (adapter_heads.py:282-288,
+ * 304-327) and their autograd dgrad / wgrad.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  THEIA_OP_K2D = 0,    /* operand stored [rows][K]  (K contiguous), 2-D                           */
+  THEIA_OP_MN2D = 1,   /* operand stored [K][rows]  (rows contiguous), 2-D  (wgrad operands)       */
+  THEIA_OP_CONV_K = 2, /* A only: NHWC activation gathered per tap, K = ntaps * C                  */
+  THEIA_OP_CONV_MN = 3 /* B only: NHWC activation gathered for ONE tap (= z index), K = pixels     */
+};
+
+enum {
+  THEIA_EPI_GELU = 1 << 1,      /* out2 = bf16(v) (pre-activation), v = gelu(v)                     */
+  THEIA_EPI_RELU = 1 << 2,      /* v = max(v, 0)                                                    */
+  THEIA_EPI_RESID = 1 << 3,     /* v += aux[m,n]        (aux may alias out: accumulate)             */
+  THEIA_EPI_OUT_F32 = 1 << 4,   /* store fp32 instead of bf16                                       */
+  THEIA_EPI_ATOMIC = 1 << 5,    /* fp32 atomicAdd into out (split-K wgrad)                          */
+  THEIA_EPI_MUL_DGELU = 1 << 6, /* v *= gelu'(aux[m,n])                                             */
+  THEIA_EPI_MUL_RELUMASK = 1 << 7, /* v = aux[m,n] > 0 ? v : 0                                      */
+  THEIA_EPI_POSCLS = 1 << 8,    /* token t = m % tokens: t==0 ? cls[n]+pos[0,n] : v + pos[t,n]      */
+  THEIA_EPI_STATS = 1 << 9      /* per-image sum / sum-of-squares of the stored values -> stats     */
+};
+
+typedef struct theia_conv_geom {
+  /* the NHWC tensor gathered by a CONV_* operand: element strides, extents */
+  int C, H, W, B;
+  long long stride_w, stride_h, stride_b; /* in elements; channel stride is 1 */
+  int ntaps;                              /* CONV_K: taps folded into K.  CONV_MN: number of z slices */
+  int dh[9], dw[9];                       /* input pixel = output pixel + (dh, dw); OOB reads are zero */
+  int tile_w, tile_h;                     /* CONV_K: M-tile = tile_h x tile_w output pixels (=128)   */
+  int out_h, out_w;                       /* valid output extent (rows with h>=out_h or w>=out_w are not stored) */
+  /* output row of pixel (b,h,w) = b*out_img_rows + out_row_off + (h*sy+py)*out_wpitch + (w*sx+px) */
+  int out_img_rows, out_row_off, out_wpitch, sy, sx, py, px;
+} theia_conv_geom;
+
+typedef struct theia_gemm_desc {
+  int M, N, K;      /* CONV_K: M = B * tiles_per_image * 128 virtual rows, K = ntaps*C          */
+  int a_mode, b_mode;
+  const void* A;    /* bf16 */
+  long long lda;    /* elements between consecutive rows of the stored 2-D operand              */
+  const void* B;    /* bf16 */
+  long long ldb;
+  theia_conv_geom conv; /* used when a_mode == CONV_K or b_mode == CONV_MN */
+  int epi;          /* THEIA_EPI_* flags */
+  void* out;        /* bf16 (default) or fp32 */
+  long long ldo;
+  void* out2;       /* GELU: pre-activation, bf16, same shape as out */
+  const float* bias;/* [N] or NULL */
+  const void* aux;  /* bf16, indexed like out */
+  const float* pos; /* POSCLS: [tokens, N] */
+  const float* cls; /* POSCLS: [N] */
+  int tokens;       /* POSCLS: tokens per image */
+  float* stats;     /* STATS: [images][2] */
+  int rows_per_image; /* STATS (non-conv A): rows of M per image */
+  int splits;       /* split-K factor (>=1); requires ATOMIC when > 1 */
+  int batch_z;      /* z slices (CONV_MN taps); out advances by out_z_stride elements per z */
+  long long out_z_stride;
+  int bn;           /* N tile: 0 = auto, else 128 / 192 / 256 */
+} theia_gemm_desc;
+
+int theia_gemm(const theia_gemm_desc* d, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * HBM-bound fused kernels (bf16 I/O, fp32 statistics).
+ * ------------------------------------------------------------------------------------------ */
+/* nn.LayerNorm(D) rows (hf:modeling_vit.py:325-326,333,340,455).  y = (x-mean)*rstd*gamma+beta */
+int theia_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                        int M, int D, float eps, void* stream);
+/* dx = LN'(dy) (+ dadd); dgamma/dbeta are ACCUMULATED (+=) */
+int theia_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                        const void* dadd, void* dx, float* dgamma, float* dbeta, int M, int D, void* stream);
+/* nn.LayerNorm([C,H,W]) per image, NHWC storage, n = H*W*C (adapter_heads.py:306-324).  stats[b] =
+ * {sum, sumsq} produced by the GEMM epilogue (THEIA_EPI_STATS). gamma/beta are the HWC-permuted affine. */
+int theia_ln3d_apply(const void* x, const float* stats, const float* gamma_hwc, const float* beta_hwc, void* y,
+                     int B, int n, float eps, void* stream);
+/* red: scratch [B][2]; dgamma/dbeta (HWC) ACCUMULATED; relu_mask: also apply the producer's ReLU mask (x>0) */
+int theia_ln3d_bwd(const void* dy, const void* x, const float* stats, const float* gamma_hwc, float* red, void* dx,
+                   float* dgamma_hwc, float* dbeta_hwc, int B, int n, float eps, int relu_mask, void* stream);
+/* Loss terms of one teacher (src/theia/models/rvfm.py:153-176): acc scratch [B][5]; out3 = {mse, cos, l1} */
+int theia_loss_fwd(const float* pred, const void* target, int target_is_bf16, float* acc, float* out3, int B, int n,
+                   void* stream);
+/* dpred (bf16 or fp32) = coef3[0]*d(mse)/dp + coef3[1]*d(cos)/dp + coef3[2]*d(l1)/dp ; coef3 lives on the device */
+int theia_loss_bwd(const float* pred, const void* target, int target_is_bf16, const float* acc, const float* coef3,
+                   void* dpred, int dpred_is_f32, int B, int n, void* stream);
+/* DeiT image processor without resize (backbones.py:337-339): uint8 HWC/CHW 224x224 -> bf16 patch rows
+ * [B*197, 768] (row b*197 is the zero CLS slot; column = c*256 + i*16 + j) */
+int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_rescale,
+                     int do_normalize, const float* mean3, const float* std3, void* stream);
+/* attention (hf:modeling_vit.py:171-196,232-246): qkv [B*N,3*H*64] bf16 -> out [B*N,H*64]; lse [B,H,N] */
+int theia_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream);
+int theia_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N,
+                        int H, void* stream);
+/* parameter packing helpers */
+int theia_gather4(const void* in, void* out, int in_is_f32, int out_is_f32, int n0, int n1, int n2, int n3,
+                  long long s0, long long s1, long long s2, long long s3, long long base, void* stream);
+int theia_cast_bf16(const float* in, void* out, long long n, void* stream);
+int theia_transpose_cast_bf16(const float* in, void* out, int R, int C, void* stream);
+/* out[n] += sum_m x[m,n] (rows with m % skip_mod == 0 skipped when skip_mod > 0) */
+int theia_colsum(const void* x, float* out, int M, int N, long long ld, int skip_mod, void* stream);
+/* out[j] = sum_b x[b*n + j] */
+int theia_batchsum(const void* x, float* out, int B, int n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-path model: replaces RobotVisionFM.forward / autograd backward
+ * (src/theia/models/rvfm.py:115-136; src/theia/scripts/train/train_rvfm.py:116,125).
+ * ------------------------------------------------------------------------------------------ */
+#define THEIA_MAX_TEACHERS 8
+typedef struct theia_model_config {
+  int hidden, heads, layers, image, patch, max_batch;
+  float ln_eps;
+  int num_teachers;
+  const char* teacher_names[THEIA_MAX_TEACHERS];
+  int teacher_c[THEIA_MAX_TEACHERS];
+  int teacher_hw[THEIA_MAX_TEACHERS]; /* target H (= W) */
+} theia_model_config;
+typedef struct theia_model theia_model;
+
+int theia_model_create(const theia_model_config* cfg, theia_model** out);
+void theia_model_destroy(theia_model* m);
+long long theia_model_param_floats(const theia_model* m);    /* size of the flat fp32 parameter buffer */
+long long theia_model_workspace_bytes(const theia_model* m);
+int theia_model_num_params(const theia_model* m);
+/* state_dict key, shape and element offset (in the flat buffer) of parameter i */
+int theia_model_param_info(const theia_model* m, int i, char* name, int name_cap, long long* dims4, int* ndim,
+                           long long* offset);
+int theia_model_bind(theia_model* m, float* master, float* grads, void* workspace);
+int theia_model_pack(theia_model* m, void* stream);
+int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channels_first, int do_rescale,
+                        int do_normalize, const float* mean3, const float* std3, int run_heads, float* const* preds,
+                        void* tokens_bf16_out, void* stream);
+int theia_model_backward(theia_model* m, const void* const* dpreds, void* stream);
+
+/* debug knobs for bring-up (descriptor field overrides); key 0 clears all */
+int theia_debug_set(int key, long long value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THEIA_B200_H */

@@ -1,0 +1,713 @@
+// HBM-bound kernels of the distillation step: row LayerNorm (fwd/bwd), per-image LayerNorm over
+// [C,H,W] used by the lconv heads (apply / bwd), fused loss reduction + gradient, image
+// pre-processing into patch rows, parameter packing, column reductions.
+// All are warp-shuffle reductions with 16-byte vector accesses; fp32 statistics, bf16 I/O.
+#include "common.cuh"
+#include "host_util.h"
+#include "theia_b200.h"
+
+namespace theia {
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x, f[1] = a.y, f[2] = b.x, f[3] = b.y, f[4] = c.x, f[5] = c.y, f[6] = d.x, f[7] = d.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
+}
+
+// ============================================================================================
+// Row LayerNorm.  One warp per row, D <= 1024, D % 8 == 0.  Two-pass statistics in registers.
+// ============================================================================================
+constexpr int LN_MAXC = 4;  // chunks of 8 per lane: D <= 32*8*4 = 1024
+
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            int M, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nch = D >> 3;
+  const bf16* xr = x + static_cast<long long>(warp) * D;
+  float v[LN_MAXC][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      load8(xr + ch * 8, v[c]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[c][e];
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[c][e] - mean;
+        ss += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+  bf16* yr = y + static_cast<long long>(warp) * D;
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      float g[8], b[8], o[8];
+      load8f(gamma + ch * 8, g);
+      load8f(beta + ch * 8, b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (v[c][e] - mean) * rstd * g[e] + b[e];
+      store8(yr + ch * 8, o);
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[warp] = mean;
+    if (rstd_out) rstd_out[warp] = rstd;
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  optional + dadd (residual grad).
+// dgamma/dbeta: per-lane register partials over the rows a warp visits, block-reduced, atomics.
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean_in,
+                                                            const float* __restrict__ rstd_in,
+                                                            const bf16* __restrict__ dadd, bf16* __restrict__ dx,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int M, int D) {
+  extern __shared__ float red[];  // [2][D]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int nch = D >> 3;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float ag[LN_MAXC][8], ab[LN_MAXC][8], gm[LN_MAXC][8];
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c) {
+    const int ch = lane + 32 * c;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ag[c][e] = 0.f, ab[c][e] = 0.f, gm[c][e] = 0.f;
+    if (ch < nch) load8f(gamma + ch * 8, gm[c]);
+  }
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < M; row += warps_total) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const long long base = static_cast<long long>(row) * D;
+    float g[LN_MAXC][8], xh[LN_MAXC][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        float d[8], xv[8];
+        load8(dy + base + ch * 8, d);
+        load8(x + base + ch * 8, xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[c][e] = (xv[e] - mean) * rstd;
+          g[c][e] = d[e] * gm[c][e];
+          s1 += g[c][e];
+          s2 += g[c][e] * xh[c][e];
+          ag[c][e] += d[e] * xh[c][e];
+          ab[c][e] += d[e];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int c = 0; c < LN_MAXC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = rstd * (g[c][e] - s1 - xh[c][e] * s2);
+        if (dadd) {
+          float a[8];
+          load8(dadd + base + ch * 8, a);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += a[e];
+        }
+        store8(dx + base + ch * 8, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < LN_MAXC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&red[ch * 8 + e], ag[c][e]);
+        atomicAdd(&red[D + ch * 8 + e], ab[c][e]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[D + i]);
+  }
+}
+
+// ============================================================================================
+// LayerNorm over [C,H,W] per image (lconv heads), NHWC storage: n = H*W*C elements per image.
+// Statistics (sum, sumsq) come from the producing GEMM's epilogue.
+// ============================================================================================
+__global__ void __launch_bounds__(256) ln3d_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         bf16* __restrict__ y, int n, long long total, float eps) {
+  const long long i8 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i8 >= total) return;
+  const int b = static_cast<int>(i8 / n);
+  const int j = static_cast<int>(i8 - static_cast<long long>(b) * n);
+  const float mean = stats[2 * b] / n;
+  const float var = fmaxf(stats[2 * b + 1] / n - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  float v[8], g[8], bb[8], o[8];
+  load8(x + i8, v);
+  load8f(gamma + j, g);
+  load8f(beta + j, bb);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * g[e] + bb[e];
+  store8(y + i8, o);
+}
+
+// pass 1: per-image sums of g = dy*gamma and g*xhat (-> red[b][2]); dgamma/dbeta over the batch.
+// grid (chunks, image groups); block 256 threads x 8 elements.
+constexpr int LN3D_GROUP = 16;
+__global__ void __launch_bounds__(256) ln3d_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                              const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma, float* __restrict__ red,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              int n, int B, float eps) {
+  __shared__ float sred[LN3D_GROUP][2];
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const bool act = j < n;
+  const int b0 = blockIdx.y * LN3D_GROUP;
+  if (threadIdx.x < LN3D_GROUP * 2) (&sred[0][0])[threadIdx.x] = 0.f;
+  __syncthreads();
+  float g8[8], ag[8], ab[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) ag[e] = 0.f, ab[e] = 0.f, g8[e] = 0.f;
+  if (act) load8f(gamma + j, g8);
+  const int lane = threadIdx.x & 31;
+  for (int bi = 0; bi < LN3D_GROUP; ++bi) {
+    const int b = b0 + bi;
+    if (b >= B) break;
+    float s1 = 0.f, s2 = 0.f;
+    if (act) {
+      const float mean = stats[2 * b] / n;
+      const float var = fmaxf(stats[2 * b + 1] / n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float d[8], xv[8];
+      const long long off = static_cast<long long>(b) * n + j;
+      load8(dy + off, d);
+      load8(x + off, xv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (xv[e] - mean) * rstd;
+        const float g = d[e] * g8[e];
+        s1 += g;
+        s2 += g * xh;
+        ag[e] += d[e] * xh;
+        ab[e] += d[e];
+      }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      atomicAdd(&sred[bi][0], s1);
+      atomicAdd(&sred[bi][1], s2);
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(dgamma + j + e, ag[e]);
+      atomicAdd(dbeta + j + e, ab[e]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < LN3D_GROUP * 2) {
+    const int bi = threadIdx.x >> 1;
+    if (b0 + bi < B) atomicAdd(red + 2 * (b0 + bi) + (threadIdx.x & 1), sred[bi][threadIdx.x & 1]);
+  }
+}
+
+// pass 2: dx = rstd * (g - mean(g) - xhat*mean(g*xhat)); optional ReLU mask of the producer
+// (x is the post-ReLU conv output, so x > 0 <=> pre-activation > 0).
+__global__ void __launch_bounds__(256) ln3d_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                             const float* __restrict__ stats,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ red, bf16* __restrict__ dx,
+                                                             int n, long long total, float eps, int relu_mask) {
+  const long long i8 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i8 >= total) return;
+  const int b = static_cast<int>(i8 / n);
+  const int j = static_cast<int>(i8 - static_cast<long long>(b) * n);
+  const float mean = stats[2 * b] / n;
+  const float var = fmaxf(stats[2 * b + 1] / n - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const float c1 = red[2 * b] / n, c2 = red[2 * b + 1] / n;
+  float d[8], xv[8], g8[8], o[8];
+  load8(dy + i8, d);
+  load8(x + i8, xv);
+  load8f(gamma + j, g8);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float xh = (xv[e] - mean) * rstd;
+    float r = rstd * (d[e] * g8[e] - c1 - xh * c2);
+    if (relu_mask && !(xv[e] > 0.f)) r = 0.f;
+    o[e] = r;
+  }
+  store8(dx + i8, o);
+}
+
+// ============================================================================================
+// Loss (rvfm.py:153-176).  pred fp32 [B,n], target fp32 or bf16 [B,n].
+//   acc[b][5] = { sum d^2, sum smoothl1(d), sum p^2, sum t^2, sum p*t }
+// ============================================================================================
+template <typename TT>
+__device__ __forceinline__ void load_t4(const TT* p, float (&f)[4]);
+template <>
+__device__ __forceinline__ void load_t4<float>(const float* p, float (&f)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w;
+}
+template <>
+__device__ __forceinline__ void load_t4<bf16>(const bf16* p, float (&f)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  f[0] = a.x, f[1] = a.y, f[2] = b.x, f[3] = b.y;
+}
+
+template <typename TT>
+__global__ void __launch_bounds__(256) loss_reduce_kernel(const float* __restrict__ pred, const TT* __restrict__ tgt,
+                                                          float* __restrict__ acc, int n, int chunk) {
+  __shared__ float sh[5][8];
+  const int b = blockIdx.y;
+  const long long base = static_cast<long long>(b) * n;
+  const int j0 = blockIdx.x * chunk;
+  const int j1 = min(n, j0 + chunk);
+  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = j0 + threadIdx.x * 4; j < j1; j += blockDim.x * 4) {
+    float p[4], t[4];
+    load_t4<float>(pred + base + j, p);
+    load_t4<TT>(tgt + base + j, t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d = p[e] - t[e];
+      const float ad = fabsf(d);
+      s[0] += d * d;
+      s[1] += ad < 1.f ? 0.5f * d * d : ad - 0.5f;
+      s[2] += p[e] * p[e];
+      s[3] += t[e] * t[e];
+      s[4] += p[e] * t[e];
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    s[k] = warp_sum(s[k]);
+    if (lane == 0) sh[k][w] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[threadIdx.x][i];
+    atomicAdd(acc + b * 5 + threadIdx.x, t);
+  }
+}
+
+// out[3] = {mse, cos, l1} of one teacher (unweighted means, as nn.MSELoss / CosineEmbeddingLoss /
+// SmoothL1Loss return them).  One block.
+__global__ void loss_finalize_kernel(const float* __restrict__ acc, float* __restrict__ out, int B, int n) {
+  __shared__ float sh[3][32];
+  float m = 0.f, c = 0.f, l = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* a = acc + b * 5;
+    m += a[0];
+    l += a[1];
+    const float pn = fmaxf(sqrtf(a[2]), 1e-12f), tn = fmaxf(sqrtf(a[3]), 1e-12f);
+    // F.normalize then CosineEmbeddingLoss (eps 1e-8 on the unit vectors)
+    const float pp = a[2] / (pn * pn), tt = a[3] / (tn * tn);
+    const float cosv = (a[4] / (pn * tn)) / sqrtf((pp + 1e-8f) * (tt + 1e-8f));
+    c += 1.f - cosv;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  m = warp_sum(m), c = warp_sum(c), l = warp_sum(l);
+  if (lane == 0) sh[0][w] = m, sh[1][w] = c, sh[2][w] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M_ = 0.f, C_ = 0.f, L_ = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) M_ += sh[0][i], C_ += sh[1][i], L_ += sh[2][i];
+    const double cnt = static_cast<double>(B) * n;
+    out[0] = static_cast<float>(M_ / cnt);
+    out[1] = C_ / B;
+    out[2] = static_cast<float>(L_ / cnt);
+  }
+}
+
+// dpred = gm*2d/(B n) + gl*clamp(d,-1,1)/(B n) + gc/B * d(1-cos_b)/dp ; g* = upstream grad * weight,
+// read from device memory (coef[3] = {g_mse*w, g_cos*w, g_l1*w}) so no host sync is needed.
+template <typename TT, typename TO>
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ pred, const TT* __restrict__ tgt,
+                                                        const float* __restrict__ acc, const float* __restrict__ coef,
+                                                        TO* __restrict__ dpred, int n, int B) {
+  const int b = blockIdx.y;
+  const long long base = static_cast<long long>(b) * n;
+  const float* a = acc + b * 5;
+  const float pn = fmaxf(sqrtf(a[2]), 1e-12f), tn = fmaxf(sqrtf(a[3]), 1e-12f);
+  const float inv_cnt = 1.f / (static_cast<float>(B) * static_cast<float>(n));
+  const float km = coef[0] * 2.f * inv_cnt;
+  const float kl = coef[2] * inv_cnt;
+  const float kc = coef[1] / B;
+  // cos = pt/(pn tn):  dcos/dp = t/(pn tn) - pt p/(pn^3 tn);  loss term is (1 - cos)
+  const float ct = -kc / (pn * tn);
+  const float cp = kc * a[4] / (pn * pn * pn * tn);
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j >= n) return;
+  float p[4], t[4], o[4];
+  load_t4<float>(pred + base + j, p);
+  load_t4<TT>(tgt + base + j, t);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float d = p[e] - t[e];
+    o[e] = km * d + kl * fminf(fmaxf(d, -1.f), 1.f) + ct * t[e] + cp * p[e];
+  }
+  if constexpr (sizeof(TO) == 4) {
+    *reinterpret_cast<float4*>(dpred + base + j) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+    uint2 u;
+    u.x = pack_bf16x2(o[0], o[1]);
+    u.y = pack_bf16x2(o[2], o[3]);
+    *reinterpret_cast<uint2*>(dpred + base + j) = u;
+  }
+}
+
+// ============================================================================================
+// Image pre-processing (DeiT processor without resize): uint8 -> normalised bf16 patch rows.
+// out[b*197 + 0][:] = 0 (CLS slot), out[b*197 + 1 + p][c*256 + i*16 + j] = norm(img[b, py*16+i, px*16+j, c])
+// ============================================================================================
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int B,
+                                                         int chw, float s0, float s1, float s2, float o0, float o1,
+                                                         float o2) {
+  // one thread per 8 consecutive k of one patch row
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * 197 * 96;
+  if (t >= total) return;
+  const int k8 = static_cast<int>(t % 96);
+  const long long row = t / 96;
+  const int tok = static_cast<int>(row % 197);
+  const int b = static_cast<int>(row / 197);
+  float o[8];
+  if (tok == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  } else {
+    const int p = tok - 1, py = p / 14, px = p % 14;
+    const int k = k8 * 8;
+    const int c = k >> 8, i = (k >> 4) & 15, j = k & 15;
+    const int yy = py * 16 + i, xx = px * 16 + j;
+    const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const float of = c == 0 ? o0 : (c == 1 ? o1 : o2);
+    if (chw) {
+      const uint8_t* src = img + ((static_cast<long long>(b) * 3 + c) * 224 + yy) * 224 + xx;
+      const uint2 u = *reinterpret_cast<const uint2*>(src);  // xx % 8 == 0
+      const uint8_t* q = reinterpret_cast<const uint8_t*>(&u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (static_cast<float>(q[e]) - of) * sc;
+    } else {
+      const uint8_t* src = img + ((static_cast<long long>(b) * 224 + yy) * 224 + xx) * 3 + c;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (static_cast<float>(src[e * 3]) - of) * sc;
+    }
+  }
+  store8(out + row * 768 + k8 * 8, o);
+}
+
+// ============================================================================================
+// Generic strided gather (parameter packing / gradient unpacking).
+//   out[((a*n1 + b)*n2 + c)*n3 + d] = in[base + a*s0 + b*s1 + c*s2 + d*s3]
+// ============================================================================================
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) gather4_kernel(const TI* __restrict__ in, TO* __restrict__ out, int n0, int n1,
+                                                      int n2, int n3, long long s0, long long s1, long long s2,
+                                                      long long s3, long long base) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n0) * n1 * n2 * n3;
+  if (t >= total) return;
+  long long r = t;
+  const int d = static_cast<int>(r % n3);
+  r /= n3;
+  const int c = static_cast<int>(r % n2);
+  r /= n2;
+  const int b = static_cast<int>(r % n1);
+  const int a = static_cast<int>(r / n1);
+  const float v = static_cast<float>(in[base + a * s0 + b * s1 + c * s2 + d * s3]);
+  out[t] = static_cast<TO>(v);
+}
+
+// tiled transpose-cast: out[c][r] = (bf16) in[r][c]   (fp32 [R,Cc] -> bf16 [Cc,R])
+__global__ void transpose_cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? in[static_cast<long long>(r) * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) out[static_cast<long long>(c) * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 f = *reinterpret_cast<const float4*>(in + i);
+    uint2 u;
+    u.x = pack_bf16x2(f.x, f.y);
+    u.y = pack_bf16x2(f.z, f.w);
+    *reinterpret_cast<uint2*>(out + i) = u;
+  } else {
+    for (long long k = i; k < n; ++k) out[k] = __float2bfloat16_rn(in[k]);
+  }
+}
+
+// ============================================================================================
+// Column sum of a bf16 [M,N] matrix into fp32 out[N] (+=): bias gradients.
+// rows with (m % skip_mod == 0) are skipped when skip_mod > 0 (CLS rows for the patch bias).
+// period > 0: out has `period*N` entries and row m adds into out[(m % period)*N + n] (pos-emb grad).
+// ============================================================================================
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int M, int N,
+                                                     long long ld, int skip_mod, int rows_per_block) {
+  __shared__ float sh[8][256];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = (blockIdx.x * 32 + tx) * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float a[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = 0.f;
+  if (n < N) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      if (skip_mod > 0 && (r % skip_mod) == 0) continue;
+      float v[8];
+      load8(x + static_cast<long long>(r) * ld + n, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sh[ty][tx * 8 + e] = a[e];
+  __syncthreads();
+  const int col = threadIdx.x;  // 256 columns per block
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += sh[i][col];
+  const int gn = blockIdx.x * 256 + col;
+  if (gn < N) atomicAdd(out + gn, s);
+}
+
+// out[j] (=) sum_b x[b*n + j] : batch reduction (pos-emb / cls gradients), x bf16, out fp32
+__global__ void __launch_bounds__(256) batchsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int B, int n) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (j >= n) return;
+  float a[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float v[8];
+    load8(x + static_cast<long long>(b) * n + j, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += v[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) out[j + e] = a[e];
+}
+
+}  // namespace theia
+
+using namespace theia;
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" int theia_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                   float* rstd, int M, int D, float eps, void* stream) {
+  if (D % 8 != 0 || D > 1024) return set_error(THEIA_ERR_ARG, "layernorm: D %% 8 == 0 and D <= 1024 required");
+  if (M <= 0) return THEIA_OK;
+  const int wpb = 8;
+  layernorm_fwd_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, S(stream)>>>(
+      static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y), mean, rstd, M, D, eps);
+  THEIA_CHECK_LAUNCH("layernorm_fwd");
+  return THEIA_OK;
+}
+
+extern "C" int theia_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                                   const float* rstd, const void* dadd, void* dx, float* dgamma, float* dbeta, int M,
+                                   int D, void* stream) {
+  if (D % 8 != 0 || D > 1024) return set_error(THEIA_ERR_ARG, "layernorm: D %% 8 == 0 and D <= 1024 required");
+  if (M <= 0) return THEIA_OK;
+  int grid = num_sms() * 2;
+  if (grid > (M + 7) / 8) grid = (M + 7) / 8;
+  layernorm_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), S(stream)>>>(
+      static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd, static_cast<const bf16*>(dadd),
+      static_cast<bf16*>(dx), dgamma, dbeta, M, D);
+  THEIA_CHECK_LAUNCH("layernorm_bwd");
+  return THEIA_OK;
+}
+
+extern "C" int theia_ln3d_apply(const void* x, const float* stats, const float* gamma_hwc, const float* beta_hwc,
+                                void* y, int B, int n, float eps, void* stream) {
+  if (n % 8 != 0) return set_error(THEIA_ERR_ARG, "ln3d: n %% 8 != 0");
+  const long long total = static_cast<long long>(B) * n;
+  const long long thr = total / 8;
+  ln3d_apply_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, S(stream)>>>(
+      static_cast<const bf16*>(x), stats, gamma_hwc, beta_hwc, static_cast<bf16*>(y), n, total, eps);
+  THEIA_CHECK_LAUNCH("ln3d_apply");
+  return THEIA_OK;
+}
+
+extern "C" int theia_ln3d_bwd(const void* dy, const void* x, const float* stats, const float* gamma_hwc, float* red,
+                              void* dx, float* dgamma_hwc, float* dbeta_hwc, int B, int n, float eps, int relu_mask,
+                              void* stream) {
+  if (n % 8 != 0) return set_error(THEIA_ERR_ARG, "ln3d: n %% 8 != 0");
+  cudaError_t e = cudaMemsetAsync(red, 0, sizeof(float) * 2 * B, S(stream));
+  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  dim3 g1((n / 8 + 255) / 256, (B + LN3D_GROUP - 1) / LN3D_GROUP);
+  ln3d_bwd_reduce_kernel<<<g1, 256, 0, S(stream)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats,
+                                                    gamma_hwc, red, dgamma_hwc, dbeta_hwc, n, B, eps);
+  THEIA_CHECK_LAUNCH("ln3d_bwd_reduce");
+  const long long total = static_cast<long long>(B) * n;
+  ln3d_bwd_apply_kernel<<<static_cast<unsigned>((total / 8 + 255) / 256), 256, 0, S(stream)>>>(
+      static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, gamma_hwc, red, static_cast<bf16*>(dx), n,
+      total, eps, relu_mask);
+  THEIA_CHECK_LAUNCH("ln3d_bwd_apply");
+  return THEIA_OK;
+}
+
+extern "C" int theia_loss_fwd(const float* pred, const void* target, int target_is_bf16, float* acc, float* out3,
+                              int B, int n, void* stream) {
+  if (n % 4 != 0) return set_error(THEIA_ERR_ARG, "loss: n %% 4 != 0");
+  cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * 5 * B, S(stream));
+  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  const int chunk = 16384;
+  dim3 g((n + chunk - 1) / chunk, B);
+  if (target_is_bf16)
+    loss_reduce_kernel<bf16><<<g, 256, 0, S(stream)>>>(pred, static_cast<const bf16*>(target), acc, n, chunk);
+  else
+    loss_reduce_kernel<float><<<g, 256, 0, S(stream)>>>(pred, static_cast<const float*>(target), acc, n, chunk);
+  THEIA_CHECK_LAUNCH("loss_reduce");
+  loss_finalize_kernel<<<1, 256, 0, S(stream)>>>(acc, out3, B, n);
+  THEIA_CHECK_LAUNCH("loss_finalize");
+  return THEIA_OK;
+}
+
+extern "C" int theia_loss_bwd(const float* pred, const void* target, int target_is_bf16, const float* acc,
+                              const float* coef3, void* dpred, int dpred_is_f32, int B, int n, void* stream) {
+  if (n % 4 != 0) return set_error(THEIA_ERR_ARG, "loss: n %% 4 != 0");
+  dim3 g((n / 4 + 255) / 256, B);
+  const bf16* tb = static_cast<const bf16*>(target);
+  const float* tf = static_cast<const float*>(target);
+  if (target_is_bf16 && dpred_is_f32)
+    loss_grad_kernel<bf16, float><<<g, 256, 0, S(stream)>>>(pred, tb, acc, coef3, static_cast<float*>(dpred), n, B);
+  else if (target_is_bf16)
+    loss_grad_kernel<bf16, bf16><<<g, 256, 0, S(stream)>>>(pred, tb, acc, coef3, static_cast<bf16*>(dpred), n, B);
+  else if (dpred_is_f32)
+    loss_grad_kernel<float, float><<<g, 256, 0, S(stream)>>>(pred, tf, acc, coef3, static_cast<float*>(dpred), n, B);
+  else
+    loss_grad_kernel<float, bf16><<<g, 256, 0, S(stream)>>>(pred, tf, acc, coef3, static_cast<bf16*>(dpred), n, B);
+  THEIA_CHECK_LAUNCH("loss_grad");
+  return THEIA_OK;
+}
+
+extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_rescale,
+                                int do_normalize, const float* mean3, const float* std3, void* stream) {
+  // out = (x - off) * scale  per channel
+  float sc[3], of[3];
+  for (int c = 0; c < 3; ++c) {
+    if (do_normalize) {
+      const float m = do_rescale ? mean3[c] * 255.f : mean3[c];
+      const float s = do_rescale ? std3[c] * 255.f : std3[c];
+      of[c] = m;
+      sc[c] = 1.f / s;
+    } else {
+      of[c] = 0.f;
+      sc[c] = do_rescale ? (1.f / 255.f) : 1.f;
+    }
+  }
+  const long long total = static_cast<long long>(B) * 197 * 96;
+  preprocess_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, S(stream)>>>(
+      images, static_cast<bf16*>(patches), B, channels_first, sc[0], sc[1], sc[2], of[0], of[1], of[2]);
+  THEIA_CHECK_LAUNCH("preprocess");
+  return THEIA_OK;
+}
+
+extern "C" int theia_gather4(const void* in, void* out, int in_is_f32, int out_is_f32, int n0, int n1, int n2, int n3,
+                             long long s0, long long s1, long long s2, long long s3, long long base, void* stream) {
+  const long long total = static_cast<long long>(n0) * n1 * n2 * n3;
+  if (total == 0) return THEIA_OK;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (in_is_f32 && !out_is_f32)
+    gather4_kernel<float, bf16><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(in), static_cast<bf16*>(out), n0,
+                                                             n1, n2, n3, s0, s1, s2, s3, base);
+  else if (in_is_f32 && out_is_f32)
+    gather4_kernel<float, float><<<grid, 256, 0, S(stream)>>>(static_cast<const float*>(in), static_cast<float*>(out),
+                                                              n0, n1, n2, n3, s0, s1, s2, s3, base);
+  else
+    return set_error(THEIA_ERR_UNSUPPORTED, "gather4: unsupported dtype combination");
+  THEIA_CHECK_LAUNCH("gather4");
+  return THEIA_OK;
+}
+
+extern "C" int theia_cast_bf16(const float* in, void* out, long long n, void* stream) {
+  if (n <= 0) return THEIA_OK;
+  cast_kernel<<<static_cast<unsigned>((n / 4 + 256) / 256), 256, 0, S(stream)>>>(in, static_cast<bf16*>(out), n);
+  THEIA_CHECK_LAUNCH("cast");
+  return THEIA_OK;
+}
+
+extern "C" int theia_transpose_cast_bf16(const float* in, void* out, int R, int C, void* stream) {
+  dim3 g((C + 31) / 32, (R + 31) / 32), b(32, 8);
+  transpose_cast_kernel<<<g, b, 0, S(stream)>>>(in, static_cast<bf16*>(out), R, C);
+  THEIA_CHECK_LAUNCH("transpose_cast");
+  return THEIA_OK;
+}
+
+extern "C" int theia_colsum(const void* x, float* out, int M, int N, long long ld, int skip_mod, void* stream) {
+  if (N % 8 != 0) return set_error(THEIA_ERR_ARG, "colsum: N %% 8 != 0");
+  const int rows_per_block = 512;
+  dim3 g((N + 255) / 256, (M + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<<<g, 256, 0, S(stream)>>>(static_cast<const bf16*>(x), out, M, N, ld, skip_mod, rows_per_block);
+  THEIA_CHECK_LAUNCH("colsum");
+  return THEIA_OK;
+}
+
+extern "C" int theia_batchsum(const void* x, float* out, int B, int n, void* stream) {
+  if (n % 8 != 0) return set_error(THEIA_ERR_ARG, "batchsum: n %% 8 != 0");
+  batchsum_kernel<<<(n / 8 + 255) / 256, 256, 0, S(stream)>>>(static_cast<const bf16*>(x), out, B, n);
+  THEIA_CHECK_LAUNCH("batchsum");
+  return THEIA_OK;
+}

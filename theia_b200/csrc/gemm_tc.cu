@@ -1,0 +1,520 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[M,N] (+)= A[M,K] * B[N,K]^T      bf16 operands, fp32 accumulation in TMEM
+//
+// One persistent, warp-specialised kernel:
+//   warp 0   TMA producer   (cp.async.bulk.tensor 2-D / 4-D, 128-byte swizzle, OOB zero fill
+//                            = the convolution padding)
+//   warp 1   MMA issuer     (one thread, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue      (tcgen05.ld -> registers -> swizzled smem transpose -> coalesced
+//                            global stores with the fused epilogue)
+// Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring
+// (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Operand modes (include/theia_b200.h): K-major 2-D, MN-major 2-D (wgrad), K-major NHWC
+// gather with the taps folded into K (forward / dgrad convolutions), MN-major NHWC gather of
+// one tap (convolution wgrad, tap = z slice).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "host_util.h"
+#include "theia_b200.h"
+
+namespace theia {
+
+struct GemmK {
+  int M, N;
+  int num_kb, kb_per_split, splits, batch_z;
+  int m_tiles, n_tiles, total_items;
+  int a_mode, b_mode;
+  int cchunks;  // CONV_K: 64-channel chunks per tap
+  int dh[9], dw[9];
+  int tile_w, tile_h, tiles_per_img;
+  int kb_per_img, rows_per_kb;  // CONV_MN
+  int conv_out;                 // output rows follow the conv geometry
+  int out_h, out_w, out_img_rows, out_row_off, out_wpitch, sy, sx, py, px;
+  int epi;
+  void* out;
+  long long ldo;
+  void* out2;
+  const float* bias;
+  const bf16* aux;
+  const float* pos;
+  const float* cls;
+  int tokens;
+  float* stats;
+  long long out_z_stride;
+  uint32_t idesc;
+  uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int STAGING_BYTES = 4 * 32 * 32 * 4;
+constexpr int SMEM_LIMIT = 232448;  // 227 KB
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_LIMIT - STAGING_BYTES - 1024 - 256) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
+};
+
+struct Item {
+  int m_blk, n_blk, z, kb0, kb1;
+};
+
+__device__ __forceinline__ Item decode_item(const GemmK& p, int item) {
+  Item it;
+  it.n_blk = item % p.n_tiles;
+  int t = item / p.n_tiles;
+  it.m_blk = t % p.m_tiles;
+  t /= p.m_tiles;
+  it.z = t % p.batch_z;
+  const int s = t / p.batch_z;
+  it.kb0 = s * p.kb_per_split;
+  it.kb1 = min(p.num_kb, it.kb0 + p.kb_per_split);
+  return it;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmK p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* staging_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + STAGING_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        const int m0 = it.m_blk * BM, n0 = it.n_blk * BN;
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          // ---- A ----
+          if (p.a_mode == THEIA_OP_K2D) {
+            tma_load_2d(&tmA, sa, &full[stage], kb * BK, m0);
+          } else if (p.a_mode == THEIA_OP_MN2D) {
+            tma_load_2d(&tmA, sa, &full[stage], m0, kb * BK);
+            tma_load_2d(&tmA, sa + 8192, &full[stage], m0 + 64, kb * BK);
+          } else {  // CONV_K
+            const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+            const int b = it.m_blk / p.tiles_per_img, ht = it.m_blk - b * p.tiles_per_img;
+            tma_load_4d(&tmA, sa, &full[stage], cc * 64, p.dw[tap], ht * p.tile_h + p.dh[tap], b);
+          }
+          // ---- B ----
+          if (p.b_mode == THEIA_OP_K2D) {
+            tma_load_2d(&tmB, sb, &full[stage], kb * BK, n0);
+          } else if (p.b_mode == THEIA_OP_MN2D) {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(&tmB, sb + i * 8192, &full[stage], n0 + 64 * i, kb * BK);
+          } else {  // CONV_MN: tap = z
+            const int b = kb / p.kb_per_img, hb = kb - b * p.kb_per_img;
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_4d(&tmB, sb + i * 8192, &full[stage], n0 + 64 * i, p.dw[it.z],
+                          hb * p.rows_per_kb + p.dh[it.z], b);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
+            const uint64_t db = make_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
+            tc_mma_bf16(d_tmem, da, db, p.idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tfull[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue ==============================
+    const int wq = warp - 4;  // TMEM lane quarter == warp % 4
+    float* stg = staging_all + wq * (32 * 32);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int epi = p.epi;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const Item it = decode_item(p, item);
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      float st_s = 0.f, st_ss = 0.f;
+      int img = 0;
+      if (p.conv_out) img = it.m_blk / p.tiles_per_img;
+      constexpr int NCHUNK = BN / 32;
+#pragma unroll 1
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int nbase = it.n_blk * BN + ch * 32;
+        if (nbase >= p.N) {  // nothing to store; still release the accumulator below
+          if (ch == NCHUNK - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          continue;
+        }
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == NCHUNK - 1) {  // all TMEM reads of this accumulator are done
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        // phase 1: row-per-thread -> swizzled staging (conflict-free float4 stores)
+        {
+          float4* row = reinterpret_cast<float4*>(stg + lane * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 f;
+            f.x = __uint_as_float(v[4 * j + 0]);
+            f.y = __uint_as_float(v[4 * j + 1]);
+            f.z = __uint_as_float(v[4 * j + 2]);
+            f.w = __uint_as_float(v[4 * j + 3]);
+            row[j ^ (lane & 7)] = f;
+          }
+        }
+        __syncwarp();
+        // phase 2: 4 rows x 128 B per warp instruction, coalesced global access
+        const int c = lane & 7;
+        const int n = nbase + c * 4;
+        const bool ncol_ok = n < p.N;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && ncol_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3);  // row within the warp's 32-row slab
+          const int r = wq * 32 + rr;          // row within the tile
+          float4 f = reinterpret_cast<const float4*>(stg + rr * 32)[c ^ (rr & 7)];
+          long long orow;
+          bool ok = ncol_ok;
+          int m = it.m_blk * BM + r;
+          if (p.conv_out) {
+            const int ht = it.m_blk - img * p.tiles_per_img;
+            const int hh = r / p.tile_w, ww = r - hh * p.tile_w;
+            const int h = ht * p.tile_h + hh;
+            ok = ok && (h < p.out_h) && (ww < p.out_w);
+            orow = static_cast<long long>(img) * p.out_img_rows + p.out_row_off +
+                   static_cast<long long>(h * p.sy + p.py) * p.out_wpitch + (ww * p.sx + p.px);
+          } else {
+            ok = ok && (m < p.M);
+            orow = m;
+          }
+          if (!ok) continue;
+          const long long off = orow * p.ldo + n;
+          float x0 = f.x + bias4.x, x1 = f.y + bias4.y, x2 = f.z + bias4.z, x3 = f.w + bias4.w;
+          if (epi & THEIA_EPI_POSCLS) {
+            const int t = m % p.tokens;
+            const float4 ps = *reinterpret_cast<const float4*>(p.pos + static_cast<long long>(t) * p.N + n);
+            if (t == 0) {
+              const float4 cl = *reinterpret_cast<const float4*>(p.cls + n);
+              x0 = cl.x + ps.x, x1 = cl.y + ps.y, x2 = cl.z + ps.z, x3 = cl.w + ps.w;
+            } else {
+              x0 += ps.x, x1 += ps.y, x2 += ps.z, x3 += ps.w;
+            }
+          }
+          if (epi & THEIA_EPI_GELU) {
+            uint2 pre;
+            pre.x = pack_bf16x2(x0, x1);
+            pre.y = pack_bf16x2(x2, x3);
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + off) = pre;
+            x0 = gelu_exact(x0), x1 = gelu_exact(x1), x2 = gelu_exact(x2), x3 = gelu_exact(x3);
+          }
+          if (epi & THEIA_EPI_RELU) {
+            x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f), x2 = fmaxf(x2, 0.f), x3 = fmaxf(x3, 0.f);
+          }
+          if (epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK)) {
+            const uint2 a = *reinterpret_cast<const uint2*>(p.aux + off);
+            const float2 a01 = unpack_bf16x2(a.x), a23 = unpack_bf16x2(a.y);
+            if (epi & THEIA_EPI_MUL_DGELU) {
+              x0 *= gelu_grad(a01.x), x1 *= gelu_grad(a01.y), x2 *= gelu_grad(a23.x), x3 *= gelu_grad(a23.y);
+            } else if (epi & THEIA_EPI_MUL_RELUMASK) {
+              x0 = a01.x > 0.f ? x0 : 0.f, x1 = a01.y > 0.f ? x1 : 0.f;
+              x2 = a23.x > 0.f ? x2 : 0.f, x3 = a23.y > 0.f ? x3 : 0.f;
+            } else {
+              x0 += a01.x, x1 += a01.y, x2 += a23.x, x3 += a23.y;
+            }
+          }
+          if (epi & THEIA_EPI_ATOMIC) {
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(it.z) * p.out_z_stride + off;
+            atomicAdd(o + 0, x0);
+            atomicAdd(o + 1, x1);
+            atomicAdd(o + 2, x2);
+            atomicAdd(o + 3, x3);
+          } else if (epi & THEIA_EPI_OUT_F32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(x0, x1, x2, x3);
+          } else {
+            uint2 o;
+            o.x = pack_bf16x2(x0, x1);
+            o.y = pack_bf16x2(x2, x3);
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + off) = o;
+            if (epi & THEIA_EPI_STATS) {
+              const float2 q01 = unpack_bf16x2(o.x), q23 = unpack_bf16x2(o.y);
+              st_s += (q01.x + q01.y) + (q23.x + q23.y);
+              st_ss += (q01.x * q01.x + q01.y * q01.y) + (q23.x * q23.x + q23.y * q23.y);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (epi & THEIA_EPI_STATS) {
+        st_s = warp_sum(st_s);
+        st_ss = warp_sum(st_ss);
+        if (lane == 0) {
+          atomicAdd(p.stats + 2 * img, st_s);
+          atomicAdd(p.stats + 2 * img + 1, st_ss);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static long long g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                     uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {pitch_elems * 2};
+  uint32_t box[2] = {box_inner, box_outer};
+  return encode_tensor_map(tm, ptr, 2, dims, strides, box);
+}
+
+template <int BN>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
+    attr_done = true;
+  }
+  int grid = k.total_items < num_sms() ? k.total_items : num_sms();
+  gemm_tc_kernel<BN><<<grid, 256, C::SMEM_BYTES, stream>>>(tmA, tmB, k);
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+  return THEIA_OK;
+}
+
+}  // namespace theia
+
+using namespace theia;
+
+extern "C" int theia_debug_set(int key, long long value) {
+  if (key == 0) {
+    for (auto& v : g_dbg) v = 0;
+    return 0;
+  }
+  if (key < 0 || key >= 8) return THEIA_ERR_ARG;
+  g_dbg[key] = value;
+  return 0;
+}
+
+extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d || !d->A || !d->B || !d->out) return set_error(THEIA_ERR_ARG, "theia_gemm: null pointer");
+  if (d->N % 8 != 0) return set_error(THEIA_ERR_ARG, "theia_gemm: N must be a multiple of 8 (got %d)", d->N);
+  if (d->ldo % 4 != 0) return set_error(THEIA_ERR_ARG, "theia_gemm: ldo must be a multiple of 4");
+  int bn = d->bn;
+  if (bn == 0) {
+    if (d->N % 256 == 0) bn = 256;
+    else if (d->N % 192 == 0) bn = 192;
+    else if (d->N % 128 == 0) bn = 128;
+    else bn = d->N > 192 ? 256 : (d->N > 128 ? 192 : 128);
+  }
+  if (bn != 128 && bn != 192 && bn != 256) return set_error(THEIA_ERR_ARG, "theia_gemm: bn must be 128/192/256");
+
+  GemmK k;
+  memset(&k, 0, sizeof(k));
+  k.M = d->M;
+  k.N = d->N;
+  k.a_mode = d->a_mode;
+  k.b_mode = d->b_mode;
+  k.epi = d->epi;
+  k.out = d->out;
+  k.ldo = d->ldo;
+  k.out2 = d->out2;
+  k.bias = d->bias;
+  k.aux = static_cast<const bf16*>(d->aux);
+  k.pos = d->pos;
+  k.cls = d->cls;
+  k.tokens = d->tokens > 0 ? d->tokens : 1;
+  k.stats = d->stats;
+  k.out_z_stride = d->out_z_stride;
+  k.batch_z = d->batch_z > 0 ? d->batch_z : 1;
+  k.splits = d->splits > 0 ? d->splits : 1;
+  if (k.splits > 1 && !(d->epi & THEIA_EPI_ATOMIC)) return set_error(THEIA_ERR_ARG, "split-K needs EPI_ATOMIC");
+  if ((d->epi & THEIA_EPI_GELU) && !d->out2) return set_error(THEIA_ERR_ARG, "EPI_GELU needs out2");
+  if ((d->epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK)) && !d->aux)
+    return set_error(THEIA_ERR_ARG, "epilogue needs aux");
+  if ((d->epi & THEIA_EPI_POSCLS) && (!d->pos || !d->cls)) return set_error(THEIA_ERR_ARG, "POSCLS needs pos/cls");
+  if ((d->epi & THEIA_EPI_STATS) && (!d->stats || d->a_mode != THEIA_OP_CONV_K))
+    return set_error(THEIA_ERR_ARG, "STATS needs stats and a CONV_K A operand");
+
+  const theia_conv_geom& g = d->conv;
+  CUtensorMap tmA, tmB;
+  int rc;
+  const int a_mn = (d->a_mode == THEIA_OP_MN2D);
+  const int b_mn = (d->b_mode == THEIA_OP_MN2D || d->b_mode == THEIA_OP_CONV_MN);
+
+  // ---- A ----
+  if (d->a_mode == THEIA_OP_K2D) {
+    rc = encode_2d(&tmA, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, 64, BM);
+  } else if (d->a_mode == THEIA_OP_MN2D) {
+    rc = encode_2d(&tmA, d->A, (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, 64, 64);
+  } else if (d->a_mode == THEIA_OP_CONV_K) {
+    if (g.tile_w * g.tile_h != BM || g.C % 64 != 0 || g.ntaps < 1 || g.ntaps > 9)
+      return set_error(THEIA_ERR_ARG, "CONV_K: tile must be 128 pixels, C %% 64 == 0");
+    uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    uint64_t strides[3] = {(uint64_t)g.stride_w * 2, (uint64_t)g.stride_h * 2, (uint64_t)g.stride_b * 2};
+    uint32_t box[4] = {64, (uint32_t)g.tile_w, (uint32_t)g.tile_h, 1};
+    rc = encode_tensor_map(&tmA, d->A, 4, dims, strides, box);
+    k.cchunks = g.C / 64;
+    k.tile_w = g.tile_w;
+    k.tile_h = g.tile_h;
+    k.tiles_per_img = (g.out_h + g.tile_h - 1) / g.tile_h;
+    k.conv_out = 1;
+    k.out_h = g.out_h, k.out_w = g.out_w, k.out_img_rows = g.out_img_rows, k.out_row_off = g.out_row_off;
+    k.out_wpitch = g.out_wpitch, k.sy = g.sy > 0 ? g.sy : 1, k.sx = g.sx > 0 ? g.sx : 1, k.py = g.py, k.px = g.px;
+    if (d->M != g.B * k.tiles_per_img * BM) return set_error(THEIA_ERR_ARG, "CONV_K: M != B*tiles*128");
+    if (d->K != g.ntaps * g.C) return set_error(THEIA_ERR_ARG, "CONV_K: K != ntaps*C");
+  } else {
+    return set_error(THEIA_ERR_ARG, "bad a_mode");
+  }
+  if (rc) return rc;
+  // ---- B ----
+  if (d->b_mode == THEIA_OP_K2D) {
+    rc = encode_2d(&tmB, d->B, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, 64, bn);
+  } else if (d->b_mode == THEIA_OP_MN2D) {
+    rc = encode_2d(&tmB, d->B, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, 64);
+  } else if (d->b_mode == THEIA_OP_CONV_MN) {
+    // pixel grid = out_h x tile_w (the dY grid); the gathered tensor (conv.H x conv.W) may be
+    // smaller (14x14 tokens under the 16x16 grid of the pad convolution)
+    if (g.tile_w < 1 || 64 % g.tile_w != 0 || (g.out_h * g.tile_w) % 64 != 0)
+      return set_error(THEIA_ERR_ARG, "CONV_MN: needs tile_w dividing 64 and out_h*tile_w %% 64 == 0");
+    if (d->K != g.B * g.out_h * g.tile_w) return set_error(THEIA_ERR_ARG, "CONV_MN: K != B*out_h*tile_w");
+    uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
+    uint64_t strides[3] = {(uint64_t)g.stride_w * 2, (uint64_t)g.stride_h * 2, (uint64_t)g.stride_b * 2};
+    uint32_t box[4] = {64, (uint32_t)g.tile_w, (uint32_t)(64 / g.tile_w), 1};
+    rc = encode_tensor_map(&tmB, d->B, 4, dims, strides, box);
+    k.rows_per_kb = 64 / g.tile_w;
+    k.kb_per_img = (g.out_h * g.tile_w) / 64;
+    if (k.batch_z != g.ntaps) return set_error(THEIA_ERR_ARG, "CONV_MN: batch_z must equal ntaps");
+  } else {
+    return set_error(THEIA_ERR_ARG, "bad b_mode");
+  }
+  if (rc) return rc;
+  for (int i = 0; i < 9; ++i) k.dh[i] = g.dh[i], k.dw[i] = g.dw[i];
+
+  k.num_kb = (d->K + BK - 1) / BK;
+  if (k.splits > k.num_kb) k.splits = k.num_kb;
+  k.kb_per_split = (k.num_kb + k.splits - 1) / k.splits;
+  k.splits = (k.num_kb + k.kb_per_split - 1) / k.kb_per_split;  // no empty split
+  k.m_tiles = (d->M + BM - 1) / BM;
+  k.n_tiles = (d->N + bn - 1) / bn;
+  k.total_items = k.m_tiles * k.n_tiles * k.batch_z * k.splits;
+  k.idesc = make_idesc_bf16(BM, bn, a_mn, b_mn);
+  k.a_lbo = a_mn ? 8192 : 16;
+  k.a_sbo = 1024;
+  k.a_kstep = a_mn ? 2048 : 32;
+  k.b_lbo = b_mn ? 8192 : 16;
+  k.b_sbo = 1024;
+  k.b_kstep = b_mn ? 2048 : 32;
+  // bring-up overrides
+  if (g_dbg[1]) k.a_lbo = (uint32_t)g_dbg[1];
+  if (g_dbg[2]) k.a_sbo = (uint32_t)g_dbg[2];
+  if (g_dbg[3]) k.b_lbo = (uint32_t)g_dbg[3];
+  if (g_dbg[4]) k.b_sbo = (uint32_t)g_dbg[4];
+  if (g_dbg[5]) k.a_kstep = (uint32_t)g_dbg[5];
+  if (g_dbg[6]) k.b_kstep = (uint32_t)g_dbg[6];
+
+  if (bn == 128) return launch<128>(tmA, tmB, k, stream);
+  if (bn == 192) return launch<192>(tmA, tmB, k, stream);
+  return launch<256>(tmA, tmB, k, stream);
+}

@@ -1,0 +1,26 @@
+// Host-side helpers shared by the .cu files: error text, launch counter, SM count, TMA
+// tensor-map encoding through the driver entry point (no link-time libcuda dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace theia {
+
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+int num_sms();
+// rank-D bf16 tensor map, 128-byte swizzle, zero OOB fill. dims[0] is the contiguous dim,
+// strides_bytes has rank-1 entries (dims 1..rank-1).
+int encode_tensor_map(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box);
+
+#define THEIA_CHECK_LAUNCH(what)                                                                   \
+  do {                                                                                             \
+    theia::count_launch();                                                                         \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess) return theia::set_error(THEIA_ERR_CUDA, what ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+}  // namespace theia

@@ -1,0 +1,628 @@
+// Orchestration of the distillation step: student ViT forward -> lconv translator heads
+// (forward), and the full backward, as a fixed sequence of kernel launches on one stream.
+// The context owns NO device memory: the caller binds a flat fp32 parameter buffer, a flat
+// fp32 gradient buffer of the same layout and one workspace; this file carves the workspace.
+//
+// Mirrors: src/theia/models/rvfm.py:115-136 (forward), hf:models/vit/modeling_vit.py:100-458
+// (ViTModel), src/theia/models/adapter_heads.py:279-359 (LightConvAdapterHead, 16x16 targets),
+// and their autograd graphs (train_rvfm.py:125).
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "host_util.h"
+#include "theia_b200.h"
+
+namespace theia {
+
+struct PInfo {
+  std::string name;
+  int ndim;
+  long long dims[4];
+  long long off;    // element offset in the flat fp32 buffers
+  long long numel;
+};
+
+struct LayerP {
+  int ln1w, ln1b, qw, kw, vw, qb, kb, vb, ow, ob, ln2w, ln2b, f1w, f1b, f2w, f2b;
+};
+struct HeadP {
+  int padw, padb, g0, b0, c1w, c1b, g1, b1, c2w, c2b, g2, b2, lw, lb;
+  int ct;
+};
+
+// bf16 packed weights (offsets in elements of the bf16 pack buffer)
+struct LayerW {
+  long long wqkv, wqkvT, wo, woT, w1, w1T, w2, w2T;
+};
+struct HeadW {
+  long long padF, padD, c1F, c1D, c2F, c2D, l, lT;
+  long long gb[3][2];  // fp32 pack: gamma/beta HWC for the three LNs (offsets in floats)
+};
+
+struct LayerA {
+  long long ln1, qkv, attn, xmid, ln2, h, a;  // bf16 element offsets
+  long long mean1, rstd1, mean2, rstd2, lse;  // fp32 element offsets
+};
+struct HeadA {
+  long long padout, ln0, c1, ln1, c2, ln2;  // bf16
+  long long stats;                          // fp32 [3][B][2]
+};
+
+}  // namespace theia
+
+using namespace theia;
+
+struct theia_model {
+  theia_model_config cfg;
+  int D, H, L, T, Bmax;
+  std::vector<PInfo> params;
+  long long n_params_total;  // floats in the flat buffer
+  int cls, pos, pew, peb, lnfw, lnfb;
+  std::vector<LayerP> lp;
+  std::vector<HeadP> hp;
+  // bound buffers
+  float* master = nullptr;
+  float* grads = nullptr;
+  uint8_t* ws = nullptr;
+  // workspace carving (byte offsets)
+  long long ws_bytes = 0;
+  long long o_packbf = 0, o_packf32 = 0, o_actbf = 0, o_actf32 = 0;
+  long long n_packbf = 0, n_packf32 = 0, n_actbf = 0, n_actf32 = 0;
+  long long wpe;
+  std::vector<LayerW> lw;
+  std::vector<HeadW> hw;
+  // activations
+  long long patches, tokens, meanf, rstdf;
+  std::vector<long long> x;  // L+1
+  std::vector<LayerA> la;
+  std::vector<HeadA> ha;
+  // backward scratch
+  long long dtok, dx0, dx1, dln, dqkv, dh, dattn, dA0, dA1;  // bf16
+  long long red, wscratch, gbscratch;                         // fp32
+  int last_B = 0;
+};
+
+namespace {
+
+long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+int add_param(theia_model* m, const std::string& name, std::initializer_list<long long> dims) {
+  PInfo p;
+  p.name = name;
+  p.ndim = static_cast<int>(dims.size());
+  p.numel = 1;
+  int i = 0;
+  for (long long d : dims) {
+    p.dims[i++] = d;
+    p.numel *= d;
+  }
+  for (; i < 4; ++i) p.dims[i] = 1;
+  p.off = m->n_params_total;
+  m->n_params_total = align_up(m->n_params_total + p.numel, 64);
+  m->params.push_back(p);
+  return static_cast<int>(m->params.size()) - 1;
+}
+
+std::string legit(const char* t) {
+  std::string s(t);
+  for (auto& c : s)
+    if (c == '.') c = '_';
+  return s;
+}
+
+struct Carver {
+  long long n = 0;
+  long long take(long long elems, long long align_elems) {
+    n = align_up(n, align_elems);
+    const long long o = n;
+    n += elems;
+    return o;
+  }
+};
+
+}  // namespace
+
+extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** out) {
+  if (!cfg || !out) return set_error(THEIA_ERR_ARG, "model_create: null");
+  if (cfg->hidden % 64 != 0 || cfg->heads * 64 != cfg->hidden)
+    return set_error(THEIA_ERR_UNSUPPORTED, "hidden must be heads*64");
+  if (cfg->image != 224 || cfg->patch != 16) return set_error(THEIA_ERR_UNSUPPORTED, "only 224/16 ViT geometry");
+  if (cfg->num_teachers < 0 || cfg->num_teachers > THEIA_MAX_TEACHERS) return set_error(THEIA_ERR_ARG, "num_teachers");
+  for (int t = 0; t < cfg->num_teachers; ++t) {
+    if (cfg->teacher_hw[t] != 16)
+      return set_error(THEIA_ERR_UNSUPPORTED, "teacher %s: only 16x16 targets are built so far (got %d)",
+                       cfg->teacher_names[t], cfg->teacher_hw[t]);
+    if (cfg->teacher_c[t] % 8 != 0) return set_error(THEIA_ERR_UNSUPPORTED, "teacher channels %% 8 != 0");
+  }
+  theia_model* m = new theia_model();
+  m->cfg = *cfg;
+  const int D = m->D = cfg->hidden;
+  m->H = cfg->heads;
+  const int L = m->L = cfg->layers;
+  const int T = m->T = cfg->num_teachers;
+  const int B = m->Bmax = cfg->max_batch;
+  m->n_params_total = 0;
+  const std::string e = "backbone.model.embeddings.";
+  m->cls = add_param(m, e + "cls_token", {1, 1, D});
+  m->pos = add_param(m, e + "position_embeddings", {1, 197, D});
+  m->pew = add_param(m, e + "patch_embeddings.projection.weight", {D, 3, 16, 16});
+  m->peb = add_param(m, e + "patch_embeddings.projection.bias", {D});
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "backbone.model.encoder.layer." + std::to_string(l) + ".";
+    LayerP q;
+    q.ln1w = add_param(m, p + "layernorm_before.weight", {D});
+    q.ln1b = add_param(m, p + "layernorm_before.bias", {D});
+    q.qw = add_param(m, p + "attention.attention.query.weight", {D, D});
+    q.kw = add_param(m, p + "attention.attention.key.weight", {D, D});
+    q.vw = add_param(m, p + "attention.attention.value.weight", {D, D});
+    q.qb = add_param(m, p + "attention.attention.query.bias", {D});
+    q.kb = add_param(m, p + "attention.attention.key.bias", {D});
+    q.vb = add_param(m, p + "attention.attention.value.bias", {D});
+    q.ow = add_param(m, p + "attention.output.dense.weight", {D, D});
+    q.ob = add_param(m, p + "attention.output.dense.bias", {D});
+    q.ln2w = add_param(m, p + "layernorm_after.weight", {D});
+    q.ln2b = add_param(m, p + "layernorm_after.bias", {D});
+    q.f1w = add_param(m, p + "intermediate.dense.weight", {4 * D, D});
+    q.f1b = add_param(m, p + "intermediate.dense.bias", {4 * D});
+    q.f2w = add_param(m, p + "output.dense.weight", {D, 4 * D});
+    q.f2b = add_param(m, p + "output.dense.bias", {D});
+    m->lp.push_back(q);
+  }
+  m->lnfw = add_param(m, "backbone.model.layernorm.weight", {D});
+  m->lnfb = add_param(m, "backbone.model.layernorm.bias", {D});
+  const int C = D;
+  for (int t = 0; t < T; ++t) {
+    const std::string p = "translator.translator_heads." + legit(cfg->teacher_names[t]) + ".";
+    HeadP q;
+    q.ct = cfg->teacher_c[t];
+    q.padw = add_param(m, p + "pad.1.weight", {C, C, 3, 3});
+    q.padb = add_param(m, p + "pad.1.bias", {C});
+    q.g0 = add_param(m, p + "adapter.0.weight", {C, 16, 16});
+    q.b0 = add_param(m, p + "adapter.0.bias", {C, 16, 16});
+    q.c1w = add_param(m, p + "adapter.1.weight", {C, C, 3, 3});
+    q.c1b = add_param(m, p + "adapter.1.bias", {C});
+    q.g1 = add_param(m, p + "adapter.3.weight", {C, 16, 16});
+    q.b1 = add_param(m, p + "adapter.3.bias", {C, 16, 16});
+    q.c2w = add_param(m, p + "adapter.4.weight", {C, C, 3, 3});
+    q.c2b = add_param(m, p + "adapter.4.bias", {C});
+    q.g2 = add_param(m, p + "adapter.6.weight", {C, 16, 16});
+    q.b2 = add_param(m, p + "adapter.6.bias", {C, 16, 16});
+    q.lw = add_param(m, p + "adapter.8.weight", {q.ct, C});
+    q.lb = add_param(m, p + "adapter.8.bias", {q.ct});
+    m->hp.push_back(q);
+  }
+
+  // ---- workspace carving ----
+  const long long M = static_cast<long long>(B) * 197, P = static_cast<long long>(B) * 256;
+  Carver pb, pf, ab, af;
+  const long long AL = 128;  // 256-byte alignment for bf16, 512 for fp32: fine for TMA (16 B) and vectors
+  m->wpe = pb.take(static_cast<long long>(D) * 768, AL);
+  for (int l = 0; l < L; ++l) {
+    LayerW w;
+    const long long DD = static_cast<long long>(D) * D;
+    w.wqkv = pb.take(3 * DD, AL);
+    w.wqkvT = pb.take(3 * DD, AL);
+    w.wo = pb.take(DD, AL);
+    w.woT = pb.take(DD, AL);
+    w.w1 = pb.take(4 * DD, AL);
+    w.w1T = pb.take(4 * DD, AL);
+    w.w2 = pb.take(4 * DD, AL);
+    w.w2T = pb.take(4 * DD, AL);
+    m->lw.push_back(w);
+  }
+  for (int t = 0; t < T; ++t) {
+    HeadW w;
+    const long long W9 = 9LL * C * C;
+    w.padF = pb.take(W9, AL);
+    w.padD = pb.take(W9, AL);
+    w.c1F = pb.take(W9, AL);
+    w.c1D = pb.take(W9, AL);
+    w.c2F = pb.take(W9, AL);
+    w.c2D = pb.take(W9, AL);
+    w.l = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
+    w.lT = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j) w.gb[i][j] = pf.take(256LL * C, AL);
+    m->hw.push_back(w);
+  }
+  m->patches = ab.take(M * 768, AL);
+  m->x.resize(L + 1);
+  for (int l = 0; l <= L; ++l) m->x[l] = ab.take(M * D, AL);
+  for (int l = 0; l < L; ++l) {
+    LayerA a;
+    a.ln1 = ab.take(M * D, AL);
+    a.qkv = ab.take(M * 3 * D, AL);
+    a.attn = ab.take(M * D, AL);
+    a.xmid = ab.take(M * D, AL);
+    a.ln2 = ab.take(M * D, AL);
+    a.h = ab.take(M * 4 * D, AL);
+    a.a = ab.take(M * 4 * D, AL);
+    a.mean1 = af.take(M, AL);
+    a.rstd1 = af.take(M, AL);
+    a.mean2 = af.take(M, AL);
+    a.rstd2 = af.take(M, AL);
+    a.lse = af.take(static_cast<long long>(B) * m->H * 197, AL);
+    m->la.push_back(a);
+  }
+  m->tokens = ab.take(M * D, AL);
+  m->meanf = af.take(M, AL);
+  m->rstdf = af.take(M, AL);
+  for (int t = 0; t < T; ++t) {
+    HeadA a;
+    a.padout = ab.take(P * C, AL);
+    a.ln0 = ab.take(P * C, AL);
+    a.c1 = ab.take(P * C, AL);
+    a.ln1 = ab.take(P * C, AL);
+    a.c2 = ab.take(P * C, AL);
+    a.ln2 = ab.take(P * C, AL);
+    a.stats = af.take(3LL * B * 2, AL);
+    m->ha.push_back(a);
+  }
+  m->dtok = ab.take(M * D, AL);
+  m->dx0 = ab.take(M * D, AL);
+  m->dx1 = ab.take(M * D, AL);
+  m->dln = ab.take(M * D, AL);
+  m->dqkv = ab.take(M * 3 * D, AL);
+  m->dh = ab.take(M * 4 * D, AL);
+  m->dattn = ab.take(M * D, AL);
+  m->dA0 = ab.take(P * C, AL);
+  m->dA1 = ab.take(P * C, AL);
+  m->red = af.take(2LL * B, AL);
+  m->wscratch = af.take(9LL * C * C, AL);
+  m->gbscratch = af.take(2LL * 256 * C, AL);
+  m->n_packbf = pb.n, m->n_packf32 = pf.n, m->n_actbf = ab.n, m->n_actf32 = af.n;
+  long long o = 0;
+  m->o_packbf = o;
+  o = align_up(o + m->n_packbf * 2, 1024);
+  m->o_packf32 = o;
+  o = align_up(o + m->n_packf32 * 4, 1024);
+  m->o_actbf = o;
+  o = align_up(o + m->n_actbf * 2, 1024);
+  m->o_actf32 = o;
+  o = align_up(o + m->n_actf32 * 4, 1024);
+  m->ws_bytes = o;
+  *out = m;
+  return THEIA_OK;
+}
+
+extern "C" void theia_model_destroy(theia_model* m) { delete m; }
+extern "C" long long theia_model_param_floats(const theia_model* m) { return m->n_params_total; }
+extern "C" long long theia_model_workspace_bytes(const theia_model* m) { return m->ws_bytes; }
+extern "C" int theia_model_num_params(const theia_model* m) { return static_cast<int>(m->params.size()); }
+extern "C" int theia_model_param_info(const theia_model* m, int i, char* name, int name_cap, long long* dims4,
+                                      int* ndim, long long* offset) {
+  if (i < 0 || i >= static_cast<int>(m->params.size())) return set_error(THEIA_ERR_ARG, "param index");
+  const PInfo& p = m->params[i];
+  snprintf(name, name_cap, "%s", p.name.c_str());
+  for (int k = 0; k < 4; ++k) dims4[k] = p.dims[k];
+  *ndim = p.ndim;
+  *offset = p.off;
+  return THEIA_OK;
+}
+extern "C" int theia_model_bind(theia_model* m, float* master, float* grads, void* workspace) {
+  if (!master || !workspace) return set_error(THEIA_ERR_ARG, "bind: null");
+  m->master = master;
+  m->grads = grads;
+  m->ws = static_cast<uint8_t*>(workspace);
+  return THEIA_OK;
+}
+
+namespace {
+
+struct Ctx {
+  theia_model* m;
+  cudaStream_t s;
+  bf16* PB(long long off) const { return reinterpret_cast<bf16*>(m->ws + m->o_packbf) + off; }
+  float* PF(long long off) const { return reinterpret_cast<float*>(m->ws + m->o_packf32) + off; }
+  bf16* AB(long long off) const { return reinterpret_cast<bf16*>(m->ws + m->o_actbf) + off; }
+  float* AF(long long off) const { return reinterpret_cast<float*>(m->ws + m->o_actf32) + off; }
+  float* W(int pi) const { return m->master + m->params[pi].off; }
+  float* G(int pi) const { return m->grads + m->params[pi].off; }
+};
+
+#define TRY(x)            \
+  do {                    \
+    int rc__ = (x);       \
+    if (rc__) return rc__; \
+  } while (0)
+
+theia_gemm_desc gemm_base(int M, int N, int K) {
+  theia_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = M, d.N = N, d.K = K;
+  d.a_mode = THEIA_OP_K2D;
+  d.b_mode = THEIA_OP_K2D;
+  d.splits = 1;
+  d.batch_z = 1;
+  return d;
+}
+
+// y[M,N] = x[M,K] * w[N,K]^T (+bias) with epilogue flags
+int linear(const Ctx& c, const bf16* x, const bf16* w, const float* bias, void* out, int M, int N, int K, int epi,
+           const void* aux = nullptr, void* out2 = nullptr) {
+  theia_gemm_desc d = gemm_base(M, N, K);
+  d.A = x, d.lda = K, d.B = w, d.ldb = K;
+  d.out = out, d.ldo = N, d.bias = bias, d.epi = epi, d.aux = aux, d.out2 = out2;
+  return theia_gemm(&d, c.s);
+}
+
+int pick_splits(int tiles, int num_kb) {
+  int s = (2 * num_sms() + tiles - 1) / tiles;
+  const int maxs = num_kb / 8 > 0 ? num_kb / 8 : 1;
+  if (s > maxs) s = maxs;
+  if (s < 1) s = 1;
+  return s;
+}
+
+// dW[Nout,Kin] += dY[Mtok,Nout]^T * X[Mtok,Kin]   (fp32 atomics, split-K over tokens)
+int wgrad(const Ctx& c, const bf16* dy, const bf16* x, float* dw, int Mtok, int Nout, int Kin) {
+  theia_gemm_desc d = gemm_base(Nout, Kin, Mtok);
+  d.a_mode = THEIA_OP_MN2D, d.b_mode = THEIA_OP_MN2D;
+  d.A = dy, d.lda = Nout, d.B = x, d.ldb = Kin;
+  d.out = dw, d.ldo = Kin, d.epi = THEIA_EPI_ATOMIC;
+  const int bn = (Kin % 256 == 0) ? 256 : (Kin % 192 == 0 ? 192 : (Kin > 192 ? 256 : (Kin > 128 ? 192 : 128)));
+  d.bn = bn;
+  const int tiles = ((Nout + 127) / 128) * ((Kin + bn - 1) / bn);
+  d.splits = pick_splits(tiles, (Mtok + 63) / 64);
+  return theia_gemm(&d, c.s);
+}
+
+void conv_geom_16(theia_conv_geom& g, int C, int Hin, int B, long long sw, long long sh, long long sb, int shift0) {
+  memset(&g, 0, sizeof(g));
+  g.C = C, g.H = Hin, g.W = Hin, g.B = B;
+  g.stride_w = sw, g.stride_h = sh, g.stride_b = sb;
+  g.ntaps = 9;
+  for (int t = 0; t < 9; ++t) g.dh[t] = t / 3 + shift0, g.dw[t] = t % 3 + shift0;
+  g.tile_w = 16, g.tile_h = 8;
+  g.out_h = 16, g.out_w = 16, g.out_img_rows = 256, g.out_row_off = 0, g.out_wpitch = 16;
+  g.sy = g.sx = 1, g.py = g.px = 0;
+}
+
+// stride-1 3x3 conv as implicit GEMM over an NHWC tensor; weights packed [Cout][tap][Cin]
+int conv3x3(const Ctx& c, const bf16* x, const theia_conv_geom& g, const bf16* w, const float* bias, void* out,
+            long long ldo, int Cout, int epi, float* stats, const void* aux) {
+  const int tiles_per_img = (g.out_h + g.tile_h - 1) / g.tile_h;
+  theia_gemm_desc d = gemm_base(g.B * tiles_per_img * 128, Cout, 9 * g.C);
+  d.a_mode = THEIA_OP_CONV_K;
+  d.A = x, d.B = w, d.ldb = 9LL * g.C;
+  d.conv = g;
+  d.out = out, d.ldo = ldo, d.bias = bias, d.epi = epi, d.stats = stats, d.aux = aux;
+  return theia_gemm(&d, c.s);
+}
+
+// conv wgrad: ws[tap][Cout][Cin] += dY[pix,Cout]^T * X[pix + tap shift, Cin]
+int conv_wgrad(const Ctx& c, const bf16* dy, const bf16* x, const theia_conv_geom& g, float* wsout, int Cout) {
+  const int P = g.B * 256;
+  theia_gemm_desc d = gemm_base(Cout, g.C, P);
+  d.a_mode = THEIA_OP_MN2D, d.b_mode = THEIA_OP_CONV_MN;
+  d.A = dy, d.lda = Cout, d.B = x;
+  d.conv = g;
+  d.out = wsout, d.ldo = g.C, d.epi = THEIA_EPI_ATOMIC;
+  d.batch_z = 9, d.out_z_stride = static_cast<long long>(Cout) * g.C;
+  const int bn = (g.C % 256 == 0) ? 256 : (g.C % 192 == 0 ? 192 : 128);
+  d.bn = bn;
+  const int tiles = 9 * ((Cout + 127) / 128) * ((g.C + bn - 1) / bn);
+  d.splits = pick_splits(tiles, P / 64);
+  return theia_gemm(&d, c.s);
+}
+
+int zero_f32(const Ctx& c, float* p, long long n) {
+  cudaError_t e = cudaMemsetAsync(p, 0, n * sizeof(float), c.s);
+  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace
+
+// fp32 master -> bf16 / permuted operand copies.  Call after every optimizer step.
+extern "C" int theia_model_pack(theia_model* m, void* stream) {
+  if (!m->master || !m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  const int D = m->D, C = m->D;
+  TRY(theia_cast_bf16(c.W(m->pew), c.PB(m->wpe), 768LL * D, c.s));
+  for (int l = 0; l < m->L; ++l) {
+    const LayerP& p = m->lp[l];
+    const LayerW& w = m->lw[l];
+    TRY(theia_cast_bf16(c.W(p.qw), c.PB(w.wqkv), 3LL * D * D, c.s));  // q,k,v are adjacent in the flat buffer
+    TRY(theia_transpose_cast_bf16(c.W(p.qw), c.PB(w.wqkvT), 3 * D, D, c.s));
+    TRY(theia_cast_bf16(c.W(p.ow), c.PB(w.wo), 1LL * D * D, c.s));
+    TRY(theia_transpose_cast_bf16(c.W(p.ow), c.PB(w.woT), D, D, c.s));
+    TRY(theia_cast_bf16(c.W(p.f1w), c.PB(w.w1), 4LL * D * D, c.s));
+    TRY(theia_transpose_cast_bf16(c.W(p.f1w), c.PB(w.w1T), 4 * D, D, c.s));
+    TRY(theia_cast_bf16(c.W(p.f2w), c.PB(w.w2), 4LL * D * D, c.s));
+    TRY(theia_transpose_cast_bf16(c.W(p.f2w), c.PB(w.w2T), D, 4 * D, c.s));
+  }
+  for (int t = 0; t < m->T; ++t) {
+    const HeadP& p = m->hp[t];
+    const HeadW& w = m->hw[t];
+    const long long C9 = 9LL * C;
+    // ConvTranspose2d weight [Cin][Cout][3][3]: fwd pack F[co][tap2][ci] = Wt[ci][co][8-tap2]
+    TRY(theia_gather4(c.W(p.padw), c.PB(w.padF), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
+    // dgrad pack D[ci][tap][co] = Wt[ci][co][tap]
+    TRY(theia_gather4(c.W(p.padw), c.PB(w.padD), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
+    // Conv2d weight [Cout][Cin][3][3]: fwd F[co][tap][ci]; dgrad D[ci][tap2][co] = W[co][ci][8-tap2]
+    TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1F), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
+    TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1D), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
+    TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2F), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
+    TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2D), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
+    TRY(theia_cast_bf16(c.W(p.lw), c.PB(w.l), 1LL * p.ct * C, c.s));
+    TRY(theia_transpose_cast_bf16(c.W(p.lw), c.PB(w.lT), p.ct, C, c.s));
+    // LN affine [C][16][16] -> [16*16][C]
+    const int gbp[3][2] = {{p.g0, p.b0}, {p.g1, p.b1}, {p.g2, p.b2}};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j)
+        TRY(theia_gather4(c.W(gbp[i][j]), c.PF(w.gb[i][j]), 1, 1, 1, 1, 256, C, 0, 0, 1, 256, 0, c.s));
+  }
+  return THEIA_OK;
+}
+
+// images uint8 [B,224,224,3] (or [B,3,224,224]) -> tokens (bf16, workspace) and, when
+// run_heads, preds[t] fp32 [B,256,C_t] (caller-owned).  tokens_f32 (optional) receives the
+// final-LayerNorm output [B,197,D] in fp32 for forward_feature().
+extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channels_first, int do_rescale,
+                                   int do_normalize, const float* mean3, const float* std3, int run_heads,
+                                   float* const* preds, void* tokens_bf16_out, void* stream) {
+  if (!m->master || !m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
+  if (B < 1 || B > m->Bmax) return set_error(THEIA_ERR_ARG, "batch %d outside [1,%d]", B, m->Bmax);
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  const int D = m->D, C = m->D, H = m->H, L = m->L;
+  const int M = B * 197, P = B * 256;
+  m->last_B = B;
+  TRY(theia_preprocess(images, c.AB(m->patches), B, channels_first, do_rescale, do_normalize, mean3, std3, c.s));
+  {  // patch embedding + CLS + position embeddings (hf:modeling_vit.py:100-128,153-168)
+    theia_gemm_desc d = gemm_base(M, D, 768);
+    d.A = c.AB(m->patches), d.lda = 768, d.B = c.PB(m->wpe), d.ldb = 768;
+    d.out = c.AB(m->x[0]), d.ldo = D, d.bias = c.W(m->peb);
+    d.epi = THEIA_EPI_POSCLS, d.pos = c.W(m->pos), d.cls = c.W(m->cls), d.tokens = 197;
+    TRY(theia_gemm(&d, c.s));
+  }
+  for (int l = 0; l < L; ++l) {  // hf:modeling_vit.py:328-346
+    const LayerP& p = m->lp[l];
+    const LayerW& w = m->lw[l];
+    const LayerA& a = m->la[l];
+    TRY(theia_layernorm_fwd(c.AB(m->x[l]), c.W(p.ln1w), c.W(p.ln1b), c.AB(a.ln1), c.AF(a.mean1), c.AF(a.rstd1), M, D,
+                            m->cfg.ln_eps, c.s));
+    TRY(linear(c, c.AB(a.ln1), c.PB(w.wqkv), c.W(p.qb), c.AB(a.qkv), M, 3 * D, D, 0));
+    TRY(theia_attention_fwd(c.AB(a.qkv), c.AB(a.attn), c.AF(a.lse), B, 197, H, c.s));
+    TRY(linear(c, c.AB(a.attn), c.PB(w.wo), c.W(p.ob), c.AB(a.xmid), M, D, D, THEIA_EPI_RESID, c.AB(m->x[l])));
+    TRY(theia_layernorm_fwd(c.AB(a.xmid), c.W(p.ln2w), c.W(p.ln2b), c.AB(a.ln2), c.AF(a.mean2), c.AF(a.rstd2), M, D,
+                            m->cfg.ln_eps, c.s));
+    TRY(linear(c, c.AB(a.ln2), c.PB(w.w1), c.W(p.f1b), c.AB(a.a), M, 4 * D, D, THEIA_EPI_GELU, nullptr, c.AB(a.h)));
+    TRY(linear(c, c.AB(a.a), c.PB(w.w2), c.W(p.f2b), c.AB(m->x[l + 1]), M, D, 4 * D, THEIA_EPI_RESID, c.AB(a.xmid)));
+  }
+  TRY(theia_layernorm_fwd(c.AB(m->x[L]), c.W(m->lnfw), c.W(m->lnfb), c.AB(m->tokens), c.AF(m->meanf), c.AF(m->rstdf), M,
+                          D, m->cfg.ln_eps, c.s));
+  if (tokens_bf16_out) {
+    cudaError_t e = cudaMemcpyAsync(tokens_bf16_out, c.AB(m->tokens), sizeof(bf16) * M * D, cudaMemcpyDeviceToDevice, c.s);
+    if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memcpy: %s", cudaGetErrorString(e));
+  }
+  if (!run_heads) return THEIA_OK;
+  for (int t = 0; t < m->T; ++t) {  // adapter_heads.py:352-359
+    if (!preds || !preds[t]) continue;
+    const HeadP& p = m->hp[t];
+    const HeadW& w = m->hw[t];
+    const HeadA& a = m->ha[t];
+    float* st0 = c.AF(a.stats);
+    float* st1 = st0 + 2 * B;
+    float* st2 = st1 + 2 * B;
+    TRY(zero_f32(c, st0, 6LL * B));
+    theia_conv_geom g;
+    // pad: ConvTranspose2d(3x3, s1) 14 -> 16 over the spatial tokens (CLS skipped by the base offset)
+    conv_geom_16(g, C, 14, B, D, 14LL * D, 197LL * D, -2);
+    TRY(conv3x3(c, c.AB(m->tokens) + D, g, c.PB(w.padF), c.W(p.padb), c.AB(a.padout), C, C, THEIA_EPI_STATS, st0, nullptr));
+    TRY(theia_ln3d_apply(c.AB(a.padout), st0, c.PF(w.gb[0][0]), c.PF(w.gb[0][1]), c.AB(a.ln0), B, 256 * C, 1e-5f, c.s));
+    conv_geom_16(g, C, 16, B, C, 16LL * C, 256LL * C, -1);
+    TRY(conv3x3(c, c.AB(a.ln0), g, c.PB(w.c1F), c.W(p.c1b), c.AB(a.c1), C, C, THEIA_EPI_RELU | THEIA_EPI_STATS, st1, nullptr));
+    TRY(theia_ln3d_apply(c.AB(a.c1), st1, c.PF(w.gb[1][0]), c.PF(w.gb[1][1]), c.AB(a.ln1), B, 256 * C, 1e-5f, c.s));
+    TRY(conv3x3(c, c.AB(a.ln1), g, c.PB(w.c2F), c.W(p.c2b), c.AB(a.c2), C, C, THEIA_EPI_RELU | THEIA_EPI_STATS, st2, nullptr));
+    TRY(theia_ln3d_apply(c.AB(a.c2), st2, c.PF(w.gb[2][0]), c.PF(w.gb[2][1]), c.AB(a.ln2), B, 256 * C, 1e-5f, c.s));
+    TRY(linear(c, c.AB(a.ln2), c.PB(w.l), c.W(p.lb), preds[t], P, p.ct, C, THEIA_EPI_OUT_F32));
+  }
+  return THEIA_OK;
+}
+
+// Backward of theia_model_forward for the batch of the last forward call.
+// dpreds[t]: bf16 [B,256,C_t] gradient w.r.t. preds[t] (NULL = head not used this step).
+// Writes every parameter gradient into the bound flat `grads` buffer (overwrites).
+extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, void* stream) {
+  if (!m->master || !m->ws || !m->grads) return set_error(THEIA_ERR_ARG, "model not bound (grads)");
+  Ctx c{m, static_cast<cudaStream_t>(stream)};
+  const int B = m->last_B;
+  if (B < 1) return set_error(THEIA_ERR_ARG, "backward before forward");
+  const int D = m->D, C = m->D, H = m->H, L = m->L;
+  const int M = B * 197, P = B * 256;
+  TRY(zero_f32(c, m->grads, m->n_params_total));
+  cudaError_t e = cudaMemsetAsync(c.AB(m->dtok), 0, sizeof(bf16) * M * D, c.s);
+  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+  bf16* dA0 = c.AB(m->dA0);
+  bf16* dA1 = c.AB(m->dA1);
+  float* wsc = c.AF(m->wscratch);
+  float* gbs = c.AF(m->gbscratch);
+  float* red = c.AF(m->red);
+  for (int t = 0; t < m->T; ++t) {
+    if (!dpreds || !dpreds[t]) continue;
+    const HeadP& p = m->hp[t];
+    const HeadW& w = m->hw[t];
+    const HeadA& a = m->ha[t];
+    const bf16* dp = static_cast<const bf16*>(dpreds[t]);
+    float* st0 = c.AF(a.stats);
+    float* st1 = st0 + 2 * B;
+    float* st2 = st1 + 2 * B;
+    // Linear(C -> C_t)
+    TRY(wgrad(c, dp, c.AB(a.ln2), c.G(p.lw), P, p.ct, C));
+    TRY(theia_colsum(dp, c.G(p.lb), P, p.ct, p.ct, 0, c.s));
+    TRY(linear(c, dp, c.PB(w.lT), nullptr, dA0, P, C, p.ct, 0));
+    theia_conv_geom g;
+    const int gbp[3][2] = {{p.g0, p.b0}, {p.g1, p.b1}, {p.g2, p.b2}};
+    const bf16* lnin[3] = {c.AB(a.padout), c.AB(a.c1), c.AB(a.c2)};
+    float* sts[3] = {st0, st1, st2};
+    const bf16* convin[3] = {nullptr, c.AB(a.ln0), c.AB(a.ln1)};
+    const int convw[3] = {p.padw, p.c1w, p.c2w};
+    const int convb[3] = {p.padb, p.c1b, p.c2b};
+    const long long convD[3] = {w.padD, w.c1D, w.c2D};
+    for (int i = 2; i >= 0; --i) {
+      // LayerNorm([C,16,16]) backward (+ ReLU mask of the conv that produced its input)
+      TRY(zero_f32(c, gbs, 2LL * 256 * C));
+      TRY(theia_ln3d_bwd(dA0, lnin[i], sts[i], c.PF(w.gb[i][0]), red, dA1, gbs, gbs + 256 * C, B, 256 * C, 1e-5f,
+                         i > 0 ? 1 : 0, c.s));
+      TRY(theia_gather4(gbs, c.G(gbp[i][0]), 1, 1, 1, C, 16, 16, 0, 1, 16LL * C, C, 0, c.s));
+      TRY(theia_gather4(gbs + 256 * C, c.G(gbp[i][1]), 1, 1, 1, C, 16, 16, 0, 1, 16LL * C, C, 0, c.s));
+      // conv i backward: dA1 = gradient of its (pre-activation) output
+      TRY(theia_colsum(dA1, c.G(convb[i]), P, C, C, 0, c.s));
+      TRY(zero_f32(c, wsc, 9LL * C * C));
+      if (i > 0) {
+        conv_geom_16(g, C, 16, B, C, 16LL * C, 256LL * C, -1);
+        TRY(conv_wgrad(c, dA1, convin[i], g, wsc, C));
+        // grad W[co][ci][tap] = ws[tap][co][ci]
+        TRY(theia_gather4(wsc, c.G(convw[i]), 1, 1, C, C, 9, 1, C, 1, 1LL * C * C, 0, 0, c.s));
+        TRY(conv3x3(c, dA1, g, c.PB(convD[i]), nullptr, dA0, C, C, 0, nullptr, nullptr));
+      } else {
+        conv_geom_16(g, C, 14, B, D, 14LL * D, 197LL * D, -2);
+        TRY(conv_wgrad(c, dA1, c.AB(m->tokens) + D, g, wsc, C));
+        // grad Wt[ci][co][t] = ws[8-t][co][ci]
+        TRY(theia_gather4(wsc, c.G(convw[i]), 1, 1, C, C, 9, 1, 1, C, -1LL * C * C, 0, 8LL * C * C, c.s));
+        // dgrad onto the 14x14 token grid, accumulated over heads
+        conv_geom_16(g, C, 16, B, C, 16LL * C, 256LL * C, 0);
+        g.out_h = 14, g.out_w = 14, g.out_img_rows = 197, g.out_row_off = 1, g.out_wpitch = 14;
+        TRY(conv3x3(c, dA1, g, c.PB(convD[i]), nullptr, c.AB(m->dtok), D, C, THEIA_EPI_RESID, nullptr, c.AB(m->dtok)));
+      }
+    }
+  }
+  // final LayerNorm
+  bf16* dx = c.AB(m->dx0);
+  bf16* dx2 = c.AB(m->dx1);
+  TRY(theia_layernorm_bwd(c.AB(m->dtok), c.AB(m->x[L]), c.W(m->lnfw), c.AF(m->meanf), c.AF(m->rstdf), nullptr, dx,
+                          c.G(m->lnfw), c.G(m->lnfb), M, D, c.s));
+  for (int l = L - 1; l >= 0; --l) {
+    const LayerP& p = m->lp[l];
+    const LayerW& w = m->lw[l];
+    const LayerA& a = m->la[l];
+    // MLP
+    TRY(wgrad(c, dx, c.AB(a.a), c.G(p.f2w), M, D, 4 * D));
+    TRY(theia_colsum(dx, c.G(p.f2b), M, D, D, 0, c.s));
+    TRY(linear(c, dx, c.PB(w.w2T), nullptr, c.AB(m->dh), M, 4 * D, D, THEIA_EPI_MUL_DGELU, c.AB(a.h)));
+    TRY(wgrad(c, c.AB(m->dh), c.AB(a.ln2), c.G(p.f1w), M, 4 * D, D));
+    TRY(theia_colsum(c.AB(m->dh), c.G(p.f1b), M, 4 * D, 4 * D, 0, c.s));
+    TRY(linear(c, c.AB(m->dh), c.PB(w.w1T), nullptr, c.AB(m->dln), M, D, 4 * D, 0));
+    TRY(theia_layernorm_bwd(c.AB(m->dln), c.AB(a.xmid), c.W(p.ln2w), c.AF(a.mean2), c.AF(a.rstd2), dx, dx2,
+                            c.G(p.ln2w), c.G(p.ln2b), M, D, c.s));
+    // attention
+    TRY(wgrad(c, dx2, c.AB(a.attn), c.G(p.ow), M, D, D));
+    TRY(theia_colsum(dx2, c.G(p.ob), M, D, D, 0, c.s));
+    TRY(linear(c, dx2, c.PB(w.woT), nullptr, c.AB(m->dattn), M, D, D, 0));
+    TRY(theia_attention_bwd(c.AB(a.qkv), c.AB(a.attn), c.AB(m->dattn), c.AF(a.lse), c.AB(m->dqkv), B, 197, H, c.s));
+    TRY(wgrad(c, c.AB(m->dqkv), c.AB(a.ln1), c.G(p.qw), M, 3 * D, D));
+    TRY(theia_colsum(c.AB(m->dqkv), c.G(p.qb), M, 3 * D, 3 * D, 0, c.s));
+    TRY(linear(c, c.AB(m->dqkv), c.PB(w.wqkvT), nullptr, c.AB(m->dln), M, D, 3 * D, 0));
+    TRY(theia_layernorm_bwd(c.AB(m->dln), c.AB(m->x[l]), c.W(p.ln1w), c.AF(a.mean1), c.AF(a.rstd1), dx2, dx,
+                            c.G(p.ln1w), c.G(p.ln1b), M, D, c.s));
+  }
+  // embeddings: position / cls / patch projection
+  TRY(theia_batchsum(dx, c.G(m->pos), B, 197 * D, c.s));
+  e = cudaMemcpyAsync(c.G(m->cls), c.G(m->pos), sizeof(float) * D, cudaMemcpyDeviceToDevice, c.s);
+  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memcpy: %s", cudaGetErrorString(e));
+  TRY(wgrad(c, dx, c.AB(m->patches), c.G(m->pew), M, D, 768));
+  TRY(theia_colsum(dx, c.G(m->peb), M, D, D, 197, c.s));
+  return THEIA_OK;
+}
