@@ -166,6 +166,10 @@ int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channe
                         void* tokens_bf16_out, void* stream);
 int theia_model_backward(theia_model* m, const void* const* dpreds, void* stream);
 
+/* Per-launch CUDA-event timing of the GEMM kernel on its launching stream (bench.py roofline). */
+int theia_prof_enable(int on);
+int theia_prof_collect(double* total_ms, double* total_flops, long long* launches);
+
 /* debug knobs for bring-up (descriptor field overrides); key 0 clears all */
 int theia_debug_set(int key, long long value);
 

@@ -71,6 +71,11 @@ class OracleConfig:
     image: int = 224
     ln_eps: float = 1e-12  # ViTConfig.layer_norm_eps
     teachers: dict = field(default_factory=dict)  # name -> (C,H,W)
+    # When True, activations / GEMM weights are rounded to bf16 at exactly the points where the CUDA
+    # path stores them (fp32 accumulation everywhere).  Still the same algorithm; used by the GPU
+    # tests to separate kernel bugs from the precision effect of bf16 storage (ReLU-mask flips make
+    # the gradient a discontinuous function of the forward activations).
+    emulate_bf16: bool = False
 
     @property
     def tokens(self) -> int:
@@ -82,6 +87,10 @@ def make_config(backbone: str, teachers) -> OracleConfig:
     if isinstance(teachers, str):
         teachers = TEACHER_SETS[teachers]
     return OracleConfig(hidden=d, heads=h, teachers={t: MODEL_FEATURE_SIZES[t] for t in teachers})
+
+
+def _r(x: torch.Tensor, cfg: "OracleConfig") -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32) if cfg.emulate_bf16 else x
 
 
 def head_key(t: str) -> str:
@@ -205,26 +214,32 @@ def vit_forward(P: dict, pix: torch.Tensor, cfg: OracleConfig) -> torch.Tensor:
     if pix.shape[-1] != cfg.image or pix.shape[-2] != cfg.image:
         raise ValueError(f"Input image size ({pix.shape[-2]}*{pix.shape[-1]}) doesn't match model "
                          f"({cfg.image}*{cfg.image}).")  # modeling_vit.py:160-165
-    x = F.conv2d(pix, P[e + "patch_embeddings.projection.weight"],
+    x = F.conv2d(_r(pix, cfg), _r(P[e + "patch_embeddings.projection.weight"], cfg),
                  P[e + "patch_embeddings.projection.bias"], stride=cfg.patch)
     x = x.flatten(2).transpose(1, 2)  # [B,196,D]
     B = x.shape[0]
-    x = torch.cat([P[e + "cls_token"].expand(B, -1, -1), x], dim=1) + P[e + "position_embeddings"]
+    x = _r(torch.cat([P[e + "cls_token"].expand(B, -1, -1), x], dim=1) + P[e + "position_embeddings"], cfg)
     for l in range(cfg.layers):
         p = f"backbone.model.encoder.layer.{l}."
-        h = F.layer_norm(x, (D,), P[p + "layernorm_before.weight"], P[p + "layernorm_before.bias"], cfg.ln_eps)
-        q = F.linear(h, P[p + "attention.attention.query.weight"], P[p + "attention.attention.query.bias"])
-        k = F.linear(h, P[p + "attention.attention.key.weight"], P[p + "attention.attention.key.bias"])
-        v = F.linear(h, P[p + "attention.attention.value.weight"], P[p + "attention.attention.value.bias"])
+        h = _r(F.layer_norm(x, (D,), P[p + "layernorm_before.weight"], P[p + "layernorm_before.bias"], cfg.ln_eps), cfg)
+        q = _r(F.linear(h, _r(P[p + "attention.attention.query.weight"], cfg), P[p + "attention.attention.query.bias"]), cfg)
+        k = _r(F.linear(h, _r(P[p + "attention.attention.key.weight"], cfg), P[p + "attention.attention.key.bias"]), cfg)
+        v = _r(F.linear(h, _r(P[p + "attention.attention.value.weight"], cfg), P[p + "attention.attention.value.bias"]), cfg)
         N = x.shape[1]
         q, k, v = (t.view(B, N, nh, D // nh).transpose(1, 2) for t in (q, k, v))
-        a = torch.softmax((q @ k.transpose(2, 3)) * ((D // nh) ** -0.5), dim=-1) @ v
-        a = a.transpose(1, 2).reshape(B, N, D)
-        x = F.linear(a, P[p + "attention.output.dense.weight"], P[p + "attention.output.dense.bias"]) + x
-        h = F.layer_norm(x, (D,), P[p + "layernorm_after.weight"], P[p + "layernorm_after.bias"], cfg.ln_eps)
-        h = F.gelu(F.linear(h, P[p + "intermediate.dense.weight"], P[p + "intermediate.dense.bias"]))
-        x = F.linear(h, P[p + "output.dense.weight"], P[p + "output.dense.bias"]) + x
-    return F.layer_norm(x, (D,), P["backbone.model.layernorm.weight"], P["backbone.model.layernorm.bias"], cfg.ln_eps)
+        sc = (q @ k.transpose(2, 3)) * ((D // nh) ** -0.5)
+        if cfg.emulate_bf16:  # unnormalised probabilities rounded to bf16 before P.V, fp32 row sum
+            pe = torch.exp(sc - sc.amax(-1, keepdim=True))
+            a = (_r(pe, cfg) @ v) / pe.sum(-1, keepdim=True)
+        else:
+            a = torch.softmax(sc, dim=-1) @ v
+        a = _r(a.transpose(1, 2).reshape(B, N, D), cfg)
+        x = _r(F.linear(a, _r(P[p + "attention.output.dense.weight"], cfg), P[p + "attention.output.dense.bias"]) + x, cfg)
+        h = _r(F.layer_norm(x, (D,), P[p + "layernorm_after.weight"], P[p + "layernorm_after.bias"], cfg.ln_eps), cfg)
+        h = _r(F.gelu(F.linear(h, _r(P[p + "intermediate.dense.weight"], cfg), P[p + "intermediate.dense.bias"])), cfg)
+        x = _r(F.linear(h, _r(P[p + "output.dense.weight"], cfg), P[p + "output.dense.bias"]) + x, cfg)
+    return _r(F.layer_norm(x, (D,), P["backbone.model.layernorm.weight"], P["backbone.model.layernorm.bias"],
+                           cfg.ln_eps), cfg)
 
 
 def lconv_head_forward(P: dict, t: str, x: torch.Tensor, cfg: OracleConfig) -> torch.Tensor:
@@ -234,25 +249,27 @@ def lconv_head_forward(P: dict, t: str, x: torch.Tensor, cfg: OracleConfig) -> t
     B, C = x.shape[0], x.shape[2]
     g = cfg.image // cfg.patch
     y = x[:, 1:].reshape(B, g, g, C).permute(0, 3, 1, 2)  # drop CLS; b (h w) c -> b c h w
-    y = F.conv_transpose2d(y, P[p + "pad.1.weight"], P[p + "pad.1.bias"], stride=1)  # 14 -> 16
+    y = _r(F.conv_transpose2d(y, _r(P[p + "pad.1.weight"], cfg), P[p + "pad.1.bias"], stride=1), cfg)  # 14 -> 16
 
     def ln(y, k):
-        return F.layer_norm(y, y.shape[1:], P[p + f"adapter.{k}.weight"], P[p + f"adapter.{k}.bias"], 1e-5)
+        return _r(F.layer_norm(y, y.shape[1:], P[p + f"adapter.{k}.weight"], P[p + f"adapter.{k}.bias"], 1e-5), cfg)
+
+    def w(k):
+        return _r(P[p + f"adapter.{k}.weight"], cfg)
 
     y = ln(y, 0)
     if ht == 16:
-        y = F.relu(F.conv2d(y, P[p + "adapter.1.weight"], P[p + "adapter.1.bias"], padding=1))
+        y = _r(F.relu(F.conv2d(y, w(1), P[p + "adapter.1.bias"], padding=1)), cfg)
         y = ln(y, 3)
-        y = F.relu(F.conv2d(y, P[p + "adapter.4.weight"], P[p + "adapter.4.bias"], padding=1))
+        y = _r(F.relu(F.conv2d(y, w(4), P[p + "adapter.4.bias"], padding=1)), cfg)
         y = ln(y, 6)
     else:
-        y = F.relu(F.conv_transpose2d(y, P[p + "adapter.1.weight"], P[p + "adapter.1.bias"], stride=2, padding=1))
+        y = _r(F.relu(F.conv_transpose2d(y, w(1), P[p + "adapter.1.bias"], stride=2, padding=1)), cfg)
         y = ln(y, 3)
-        y = F.relu(F.conv_transpose2d(y, P[p + "adapter.4.weight"], P[p + "adapter.4.bias"], stride=2,
-                                      output_padding=1))
+        y = _r(F.relu(F.conv_transpose2d(y, w(4), P[p + "adapter.4.bias"], stride=2, output_padding=1)), cfg)
         y = ln(y, 6)
     y = y.flatten(2).transpose(1, 2)  # b c h w -> b (h w) c
-    return F.linear(y, P[p + "adapter.8.weight"], P[p + "adapter.8.bias"])
+    return F.linear(y, w(8), P[p + "adapter.8.bias"])
 
 
 def handle_feature_output(x, feature_reduce_method=None, num_discard_tokens=0):

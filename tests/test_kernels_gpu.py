@@ -1,0 +1,373 @@
+"""GPU parity of every C-ABI kernel against plain torch fp32 math on the same (bf16-rounded) inputs.
+Run on the B200 box:  python -m pytest tests -m gpu -q"""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from theia_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (scale * torch.randn(*shape, generator=g)).to(dtype).to(DEV)
+
+
+def relerr(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def gemm(lib, **kw):
+    d = L.GemmDesc()
+    d.splits, d.batch_z = 1, 1
+    for k, v in kw.items():
+        if k == "conv":
+            d.conv = v
+        elif torch.is_tensor(v):
+            setattr(d, k, v.data_ptr())
+        else:
+            setattr(d, k, v)
+    L.check(lib.theia_gemm(C.byref(d), S()), "theia_gemm")
+
+
+# ----------------------------------------------------------------------------- GEMM, K-major
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 128, 0), (591, 192, 192, 0), (394, 1280, 768, 0),
+                                      (128, 128, 64, 128), (1000, 576, 192, 192), (300, 768, 3072, 256),
+                                      (197, 32, 192, 0)])
+def test_gemm_k2d_bias(lib, M, N, K, bn):
+    a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, bias=bias, bn=bn)
+    ref = a.float() @ b.float().t() + bias
+    torch.cuda.synchronize()
+    assert relerr(out.float(), ref) < 6e-3
+
+
+def test_gemm_epilogues(lib):
+    M, N, K = 394, 768, 192
+    a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.08)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    aux = rnd(M, N, seed=4)
+    acc = a.float() @ b.float().t() + bias
+    # GELU: out2 = pre-activation, out = gelu
+    out, out2 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV), torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, bias=bias, out2=out2, epi=L.EPI_GELU)
+    assert relerr(out2.float(), acc) < 6e-3
+    assert relerr(out.float(), F.gelu(acc)) < 8e-3
+    # residual
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, bias=bias, aux=aux, epi=L.EPI_RESID)
+    assert relerr(out.float(), acc + aux.float()) < 6e-3
+    # accumulate in place (aux aliases out)
+    out.copy_(aux)
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, aux=out, epi=L.EPI_RESID)
+    assert relerr(out.float(), acc - bias + aux.float()) < 6e-3
+    # fp32 output
+    o32 = torch.zeros(M, N, dtype=torch.float32, device=DEV)
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=o32, ldo=N, bias=bias, epi=L.EPI_OUT_F32)
+    assert relerr(o32, acc) < 1e-5
+    # gelu' and relu-mask multipliers
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, aux=aux, epi=L.EPI_MUL_DGELU)
+    x = aux.float().requires_grad_(True)
+    F.gelu(x).sum().backward()
+    assert relerr(out.float(), (acc - bias) * x.grad) < 8e-3
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, aux=aux, epi=L.EPI_MUL_RELUMASK)
+    assert relerr(out.float(), (acc - bias) * (aux.float() > 0)) < 6e-3
+    # relu
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, bias=bias, epi=L.EPI_RELU)
+    assert relerr(out.float(), acc.clamp_min(0)) < 6e-3
+
+
+def test_gemm_poscls(lib):
+    Bn, D, K = 3, 192, 768
+    M = Bn * 197
+    a = rnd(M, K, seed=1)
+    a.view(Bn, 197, K)[:, 0] = 0  # CLS slot rows are zero patches
+    w = rnd(D, K, seed=2, scale=0.03)
+    bias, pos, cls = (rnd(D, seed=3, dtype=torch.float32), rnd(197, D, seed=4, dtype=torch.float32),
+                      rnd(D, seed=5, dtype=torch.float32))
+    out = torch.zeros(M, D, dtype=torch.bfloat16, device=DEV)
+    gemm(lib, M=M, N=D, K=K, A=a, lda=K, B=w, ldb=K, out=out, ldo=D, bias=bias, pos=pos, cls=cls, tokens=197,
+         epi=L.EPI_POSCLS)
+    ref = (a.float() @ w.float().t() + bias).view(Bn, 197, D) + pos
+    ref[:, 0] = cls + pos[0]
+    assert relerr(out.float().view(Bn, 197, D), ref) < 6e-3
+
+
+# ----------------------------------------------------------------------------- GEMM, MN-major (wgrad)
+@pytest.mark.parametrize("Mtok,Nout,Kin,splits,bn", [(512, 256, 256, 1, 256), (1000, 320, 192, 3, 192),
+                                                     (788, 768, 768, 4, 256), (640, 32, 192, 2, 0),
+                                                     (985, 576, 192, 5, 128)])
+def test_gemm_wgrad_mn_major(lib, Mtok, Nout, Kin, splits, bn):
+    dy, x = rnd(Mtok, Nout, seed=1), rnd(Mtok, Kin, seed=2)
+    dw = torch.zeros(Nout, Kin, dtype=torch.float32, device=DEV)
+    gemm(lib, M=Nout, N=Kin, K=Mtok, a_mode=L.OP_MN2D, b_mode=L.OP_MN2D, A=dy, lda=Nout, B=x, ldb=Kin, out=dw,
+         ldo=Kin, epi=L.EPI_ATOMIC, splits=splits, bn=bn)
+    ref = dy.float().t() @ x.float()
+    assert relerr(dw, ref) < 1e-4
+
+
+def test_gemm_mixed_major_b(lib):
+    """dgrad without a transposed weight copy: B operand MN-major (W stored [K_gemm][N_gemm])."""
+    M, Nout, Kin = 300, 320, 256  # y = dy[M,Nout] @ W[Nout,Kin]
+    dy, w = rnd(M, Nout, seed=1), rnd(Nout, Kin, seed=2, scale=0.05)
+    out = torch.zeros(M, Kin, dtype=torch.bfloat16, device=DEV)
+    gemm(lib, M=M, N=Kin, K=Nout, a_mode=L.OP_K2D, b_mode=L.OP_MN2D, A=dy, lda=Nout, B=w, ldb=Kin, out=out, ldo=Kin)
+    assert relerr(out.float(), dy.float() @ w.float()) < 6e-3
+
+
+# ----------------------------------------------------------------------------- implicit-GEMM conv
+def geom16(Cc, Hin, Bn, sw, sh, sb, shift0):
+    g = L.ConvGeom()
+    g.C, g.H, g.W, g.B = Cc, Hin, Hin, Bn
+    g.stride_w, g.stride_h, g.stride_b = sw, sh, sb
+    g.ntaps = 9
+    for t in range(9):
+        g.dh[t], g.dw[t] = t // 3 + shift0, t % 3 + shift0
+    g.tile_w, g.tile_h = 16, 8
+    g.out_h, g.out_w, g.out_img_rows, g.out_row_off, g.out_wpitch = 16, 16, 256, 0, 16
+    g.sy = g.sx = 1
+    return g
+
+
+@pytest.mark.parametrize("Cc,Bn", [(128, 3), (192, 2)])
+def test_conv3x3_fwd_relu_stats(lib, Cc, Bn):
+    x = rnd(Bn, 16, 16, Cc, seed=1)  # NHWC
+    w = rnd(Cc, Cc, 3, 3, seed=2, scale=0.05, dtype=torch.float32)  # Conv2d [co,ci,kh,kw]
+    bias = rnd(Cc, seed=3, dtype=torch.float32)
+    wp = w.permute(0, 2, 3, 1).reshape(Cc, 9 * Cc).to(torch.bfloat16).contiguous()  # [co][tap][ci]
+    out = torch.zeros(Bn * 256, Cc, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(Bn, 2, dtype=torch.float32, device=DEV)
+    g = geom16(Cc, 16, Bn, Cc, 16 * Cc, 256 * Cc, -1)
+    gemm(lib, M=Bn * 256, N=Cc, K=9 * Cc, a_mode=L.OP_CONV_K, A=x, B=wp, ldb=9 * Cc, conv=g, out=out, ldo=Cc,
+         bias=bias, stats=stats, epi=L.EPI_RELU | L.EPI_STATS)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().view(Cc, 3, 3, Cc).permute(0, 3, 1, 2), bias,
+                          padding=1)).permute(0, 2, 3, 1).reshape(Bn * 256, Cc)
+    assert relerr(out.float(), ref) < 6e-3
+    o = out.float().view(Bn, -1)
+    torch.testing.assert_close(stats[:, 0], o.sum(1), rtol=2e-4, atol=1e-2)
+    torch.testing.assert_close(stats[:, 1], (o * o).sum(1), rtol=2e-4, atol=1e-2)
+
+
+def test_pad_convtranspose_fwd_and_dgrad(lib):
+    Cc, Bn, D = 128, 2, 128
+    tok = rnd(Bn, 197, D, seed=1)
+    wt = rnd(Cc, Cc, 3, 3, seed=2, scale=0.05, dtype=torch.float32).to(torch.bfloat16).float()  # [ci,co,kh,kw]
+    bias = rnd(Cc, seed=3, dtype=torch.float32)
+    # fwd pack F[co][tap2][ci] = Wt[ci][co][2-kh2][2-kw2]
+    wf = wt.flip(2, 3).permute(1, 2, 3, 0).reshape(Cc, 9 * Cc).to(torch.bfloat16).contiguous()
+    out = torch.zeros(Bn * 256, Cc, dtype=torch.bfloat16, device=DEV)
+    g = geom16(Cc, 14, Bn, D, 14 * D, 197 * D, -2)
+    a_ptr = tok.data_ptr() + 2 * D
+    gemm(lib, M=Bn * 256, N=Cc, K=9 * Cc, a_mode=L.OP_CONV_K, A=a_ptr, B=wf, ldb=9 * Cc, conv=g, out=out, ldo=Cc,
+         bias=bias)
+    xin = tok[:, 1:].float().reshape(Bn, 14, 14, D).permute(0, 3, 1, 2)
+    ref = F.conv_transpose2d(xin, wt, bias).permute(0, 2, 3, 1).reshape(Bn * 256, Cc)
+    assert relerr(out.float(), ref) < 6e-3
+    # dgrad onto the token grid (rows 1..196 of each image), accumulated into an existing tensor
+    dy = rnd(Bn * 256, Cc, seed=5)
+    wd = wt.permute(0, 2, 3, 1).reshape(Cc, 9 * Cc).to(torch.bfloat16).contiguous()  # D[ci][tap][co]
+    dtok = rnd(Bn, 197, D, seed=6)
+    dtok0 = dtok.clone()
+    g2 = geom16(Cc, 16, Bn, Cc, 16 * Cc, 256 * Cc, 0)
+    g2.out_h, g2.out_w, g2.out_img_rows, g2.out_row_off, g2.out_wpitch = 14, 14, 197, 1, 14
+    gemm(lib, M=Bn * 256, N=D, K=9 * Cc, a_mode=L.OP_CONV_K, A=dy, B=wd, ldb=9 * Cc, conv=g2, out=dtok, ldo=D,
+         aux=dtok, epi=L.EPI_RESID)
+    xr = xin.clone().requires_grad_(True)
+    (F.conv_transpose2d(xr, wt, None) * dy.float().view(Bn, 16, 16, Cc).permute(0, 3, 1, 2)).sum().backward()
+    want = dtok0.float().clone()
+    want[:, 1:] += xr.grad.permute(0, 2, 3, 1).reshape(Bn, 196, D)
+    assert relerr(dtok.float(), want) < 6e-3
+    assert torch.equal(dtok[:, 0], dtok0[:, 0])  # CLS rows untouched
+
+
+def test_conv_wgrad(lib):
+    Cc, Bn = 128, 3
+    x = rnd(Bn, 16, 16, Cc, seed=1)
+    dy = rnd(Bn * 256, Cc, seed=2)
+    ws = torch.zeros(9, Cc, Cc, dtype=torch.float32, device=DEV)
+    g = geom16(Cc, 16, Bn, Cc, 16 * Cc, 256 * Cc, -1)
+    gemm(lib, M=Cc, N=Cc, K=Bn * 256, a_mode=L.OP_MN2D, b_mode=L.OP_CONV_MN, A=dy, lda=Cc, B=x, conv=g, out=ws,
+         ldo=Cc, epi=L.EPI_ATOMIC, batch_z=9, out_z_stride=Cc * Cc, splits=2, bn=128)
+    w = torch.zeros(Cc, Cc, 3, 3, device=DEV, requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, padding=1)
+    (y * dy.float().view(Bn, 16, 16, Cc).permute(0, 3, 1, 2)).sum().backward()
+    ref = w.grad.permute(2, 3, 0, 1).reshape(9, Cc, Cc)  # [tap][co][ci]
+    assert relerr(ws, ref) < 1e-4
+
+
+def test_pad_conv_wgrad(lib):
+    Cc, Bn, D = 128, 2, 128
+    tok = rnd(Bn, 197, D, seed=1)
+    dy = rnd(Bn * 256, Cc, seed=2)
+    ws = torch.zeros(9, Cc, Cc, dtype=torch.float32, device=DEV)
+    g = geom16(Cc, 14, Bn, D, 14 * D, 197 * D, -2)
+    gemm(lib, M=Cc, N=Cc, K=Bn * 256, a_mode=L.OP_MN2D, b_mode=L.OP_CONV_MN, A=dy, lda=Cc, B=tok.data_ptr() + 2 * D,
+         conv=g, out=ws, ldo=Cc, epi=L.EPI_ATOMIC, batch_z=9, out_z_stride=Cc * Cc, splits=1, bn=128)
+    wt = torch.zeros(Cc, Cc, 3, 3, device=DEV, requires_grad=True)
+    xin = tok[:, 1:].float().reshape(Bn, 14, 14, D).permute(0, 3, 1, 2)
+    y = F.conv_transpose2d(xin, wt, None)
+    (y * dy.float().view(Bn, 16, 16, Cc).permute(0, 3, 1, 2)).sum().backward()
+    # ws[tap2][co][ci] = dWt[ci][co][2-kh2][2-kw2]
+    ref = wt.grad.flip(2, 3).permute(2, 3, 1, 0).reshape(9, Cc, Cc)
+    assert relerr(ws, ref) < 1e-4
+
+
+# ----------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("M,D", [(591, 192), (300, 384), (394, 768)])
+def test_layernorm_fwd_bwd(lib, M, D):
+    x, dy, dadd = rnd(M, D, seed=1, scale=2.0), rnd(M, D, seed=2), rnd(M, D, seed=3)
+    gamma = 1 + 0.1 * rnd(D, seed=4, dtype=torch.float32)
+    beta = 0.1 * rnd(D, seed=5, dtype=torch.float32)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    L.check(lib.theia_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                    rstd.data_ptr(), M, D, 1e-12, S()))
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (D,), gr, br, 1e-12)
+    assert relerr(y.float(), ref) < 5e-3
+    ref.backward(dy.float())
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    L.check(lib.theia_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                    dadd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), M, D, S()))
+    assert relerr(dx.float(), xr.grad + dadd.float()) < 6e-3
+    assert relerr(dg, gr.grad) < 1e-3
+    assert relerr(db, br.grad) < 1e-3
+
+
+def test_ln3d_apply_and_bwd(lib):
+    Bn, Cc = 19, 64
+    n = 256 * Cc
+    x = F.relu(rnd(Bn, n, seed=1)).contiguous()
+    dy = rnd(Bn, n, seed=2)
+    gamma = 1 + 0.1 * rnd(n, seed=3, dtype=torch.float32)
+    beta = 0.1 * rnd(n, seed=4, dtype=torch.float32)
+    xf = x.float()
+    stats = torch.stack([xf.sum(1), (xf * xf).sum(1)], 1).contiguous()
+    y = torch.empty_like(x)
+    L.check(lib.theia_ln3d_apply(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), Bn,
+                                 n, 1e-5, S()))
+    xr = xf.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (n,), gr, br, 1e-5)
+    assert relerr(y.float(), ref) < 5e-3
+    ref.backward(dy.float())
+    red = torch.empty(Bn, 2, device=DEV)
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    L.check(lib.theia_ln3d_bwd(dy.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), red.data_ptr(),
+                               dx.data_ptr(), dg.data_ptr(), db.data_ptr(), Bn, n, 1e-5, 1, S()))
+    want = xr.grad * (xf > 0)
+    assert relerr(dx.float(), want) < 6e-3
+    assert relerr(dg, gr.grad) < 1e-3
+    assert relerr(db, br.grad) < 1e-3
+
+
+# ----------------------------------------------------------------------------- loss
+@pytest.mark.parametrize("tgt_dtype", [torch.float32, torch.bfloat16])
+def test_loss_fwd_bwd(lib, tgt_dtype):
+    from oracle import theia_oracle as O
+    Bn, n = 5, 256 * 96
+    pred = 1.5 * rnd(Bn, 256, 96, seed=1, dtype=torch.float32)
+    tgt = rnd(Bn, 256, 96, seed=2, dtype=tgt_dtype)
+    acc = torch.empty(Bn, 5, device=DEV)
+    out = torch.empty(3, device=DEV)
+    L.check(lib.theia_loss_fwd(pred.data_ptr(), tgt.data_ptr(), int(tgt_dtype == torch.bfloat16), acc.data_ptr(),
+                               out.data_ptr(), Bn, n, S()))
+    pr = pred.clone().requires_grad_(True)
+    ref = O.get_loss({"t": pr}, {"t": tgt.float()})
+    want = torch.stack([ref["mse_loss"], ref["cos_loss"], ref["l1_loss"]]).detach()
+    torch.testing.assert_close(out, want, rtol=2e-5, atol=1e-6)
+    coef = torch.tensor([0.3, 0.9, 0.1], device=DEV)
+    (0.3 * ref["mse_loss"] + 0.9 * ref["cos_loss"] + 0.1 * ref["l1_loss"]).backward()
+    d32 = torch.empty_like(pred)
+    L.check(lib.theia_loss_bwd(pred.data_ptr(), tgt.data_ptr(), int(tgt_dtype == torch.bfloat16), acc.data_ptr(),
+                               coef.data_ptr(), d32.data_ptr(), 1, Bn, n, S()))
+    assert relerr(d32, pr.grad) < 1e-4
+    d16 = torch.empty(pred.shape, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.theia_loss_bwd(pred.data_ptr(), tgt.data_ptr(), int(tgt_dtype == torch.bfloat16), acc.data_ptr(),
+                               coef.data_ptr(), d16.data_ptr(), 0, Bn, n, S()))
+    assert relerr(d16.float(), pr.grad) < 5e-3
+
+
+# ----------------------------------------------------------------------------- preprocess
+@pytest.mark.parametrize("chw", [0, 1])
+def test_preprocess(lib, chw):
+    from oracle import theia_oracle as O
+    Bn = 3
+    g = torch.Generator().manual_seed(0)
+    img = torch.randint(0, 256, (Bn, 224, 224, 3), dtype=torch.uint8, generator=g)
+    if chw:
+        img = img.permute(0, 3, 1, 2).contiguous()
+    out = torch.empty(Bn * 197, 768, dtype=torch.bfloat16, device=DEV)
+    mean, std = (C.c_float * 3)(*O.IMAGE_MEAN), (C.c_float * 3)(*O.IMAGE_STD)
+    d = img.to(DEV)
+    L.check(lib.theia_preprocess(d.data_ptr(), out.data_ptr(), Bn, chw, 1, 1, mean, std, S()))
+    pix = O.preprocess(img, do_resize=False)  # [B,3,224,224]
+    ref = F.unfold(pix, 16, stride=16).transpose(1, 2)  # [B,196, c*256+i*16+j]
+    o = out.float().view(Bn, 197, 768).cpu()
+    assert torch.all(o[:, 0] == 0)
+    assert relerr(o[:, 1:], ref) < 4e-3
+
+
+# ----------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("Bn,H", [(2, 3), (3, 12)])
+def test_attention_fwd_bwd(lib, Bn, H):
+    N, D = 197, H * 64
+    qkv = rnd(Bn * N, 3 * D, seed=1, scale=1.5)
+    do = rnd(Bn * N, D, seed=2)
+    out = torch.empty(Bn * N, D, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(Bn, H, N, device=DEV)
+    L.check(lib.theia_attention_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), Bn, N, H, S()))
+    x = qkv.float().view(Bn, N, 3, H, 64).requires_grad_(True)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(2, 3)) * 0.125
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(Bn * N, D)
+    assert relerr(out.float(), ref) < 8e-3
+    torch.testing.assert_close(lse, torch.logsumexp(s, -1).detach(), rtol=1e-4, atol=1e-4)
+    ref.backward(do.float())
+    dqkv = torch.zeros_like(qkv)
+    L.check(lib.theia_attention_bwd(qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), Bn,
+                                    N, H, S()))
+    g = x.grad.view(Bn * N, 3, D)
+    got = dqkv.float().view(Bn * N, 3, D)
+    for i, nm in enumerate("qkv"):
+        assert relerr(got[:, i], g[:, i]) < 1.5e-2, nm
+
+
+# ----------------------------------------------------------------------------- packing / reductions
+def test_pack_and_reductions(lib):
+    w = rnd(96, 160, seed=1, dtype=torch.float32)
+    o = torch.empty(160, 96, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.theia_transpose_cast_bf16(w.data_ptr(), o.data_ptr(), 96, 160, S()))
+    assert torch.equal(o, w.t().to(torch.bfloat16))
+    o2 = torch.empty(96 * 160 + 3, dtype=torch.bfloat16, device=DEV)
+    w2 = rnd(96 * 160 + 3, seed=2, dtype=torch.float32)
+    L.check(lib.theia_cast_bf16(w2.data_ptr(), o2.data_ptr(), w2.numel(), S()))
+    assert torch.equal(o2, w2.to(torch.bfloat16))
+    # conv weight [co][ci][3][3] -> dgrad pack D[ci][tap2][co] = W[co][ci][8-tap2]
+    Cc = 16
+    cw = rnd(Cc, Cc, 3, 3, seed=3, dtype=torch.float32)
+    pk = torch.empty(Cc, 9, Cc, dtype=torch.bfloat16, device=DEV)
+    L.check(lib.theia_gather4(cw.data_ptr(), pk.data_ptr(), 1, 0, Cc, 9, Cc, 1, 9, -1, 9 * Cc, 0, 8, S()))
+    assert torch.equal(pk, cw.flip(2, 3).reshape(Cc, Cc, 9).permute(1, 2, 0).to(torch.bfloat16))
+    x = rnd(985, 200, seed=4)
+    cs = torch.zeros(200, device=DEV)
+    L.check(lib.theia_colsum(x.data_ptr(), cs.data_ptr(), 985, 200, 200, 197, S()))
+    mask = (torch.arange(985, device=DEV) % 197 != 0).float()[:, None]
+    assert relerr(cs, (x.float() * mask).sum(0)) < 1e-5
+    bs = torch.empty(197 * 64, device=DEV)
+    xb = rnd(7, 197 * 64, seed=5)
+    L.check(lib.theia_batchsum(xb.data_ptr(), bs.data_ptr(), 7, 197 * 64, S()))
+    assert relerr(bs, xb.float().sum(0)) < 1e-5

@@ -50,6 +50,8 @@ SYMBOLS = {
     "theia_launch_count": (_ll, []),
     "theia_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
     "theia_debug_set": (_i, [_i, _ll]),
+    "theia_prof_enable": (_i, [_i]),
+    "theia_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "theia_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "theia_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "theia_ln3d_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),

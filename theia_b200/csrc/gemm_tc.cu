@@ -356,6 +356,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 static long long g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+// ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----
+constexpr int PROF_RING = 8192;
+static bool g_prof_on = false;
+static cudaEvent_t g_ev0[PROF_RING], g_ev1[PROF_RING];
+static double g_prof_flops[PROF_RING];
+static int g_prof_n = 0;
+static bool g_prof_init = false;
+
 static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
                      uint32_t box_inner, uint32_t box_outer) {
   uint64_t dims[2] = {inner, outer};
@@ -375,7 +383,14 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k
     attr_done = true;
   }
   int grid = k.total_items < num_sms() ? k.total_items : num_sms();
+  const bool prof = g_prof_on && g_prof_n < PROF_RING;
+  if (prof) cudaEventRecord(g_ev0[g_prof_n], stream);
   gemm_tc_kernel<BN><<<grid, 256, C::SMEM_BYTES, stream>>>(tmA, tmB, k);
+  if (prof) {
+    cudaEventRecord(g_ev1[g_prof_n], stream);
+    g_prof_flops[g_prof_n] = 2.0 * k.M * (double)k.N * (double)k.num_kb * BK * k.batch_z;
+    ++g_prof_n;
+  }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
@@ -394,6 +409,37 @@ extern "C" int theia_debug_set(int key, long long value) {
   if (key < 0 || key >= 8) return THEIA_ERR_ARG;
   g_dbg[key] = value;
   return 0;
+}
+
+extern "C" int theia_prof_enable(int on) {
+  if (on && !g_prof_init) {
+    for (int i = 0; i < PROF_RING; ++i) {
+      if (cudaEventCreate(&g_ev0[i]) != cudaSuccess || cudaEventCreate(&g_ev1[i]) != cudaSuccess)
+        return set_error(THEIA_ERR_CUDA, "cudaEventCreate failed");
+    }
+    g_prof_init = true;
+  }
+  g_prof_on = on != 0;
+  if (on) g_prof_n = 0;
+  return THEIA_OK;
+}
+
+// Sums the recorded GEMM launches (device time in ms, executed flops), then resets the ring.
+extern "C" int theia_prof_collect(double* total_ms, double* total_flops, long long* launches) {
+  double ms = 0.0, fl = 0.0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    cudaEventSynchronize(g_ev1[i]);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_ev0[i], g_ev1[i]) != cudaSuccess)
+      return set_error(THEIA_ERR_CUDA, "cudaEventElapsedTime failed");
+    ms += t;
+    fl += g_prof_flops[i];
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = g_prof_n;
+  g_prof_n = 0;
+  return THEIA_OK;
 }
 
 extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
