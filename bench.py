@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gemm-csv", default=None, help="dump per-launch GEMM timings of the timed region")
     args = ap.parse_args()
 
     from oracle import theia_oracle as O  # checker / CPU baseline only
@@ -242,6 +243,18 @@ def main():
     ms = timed(lambda i: step(d_images, d_targets), args.steps)
     import ctypes as C
     pm, pf, pn = C.c_double(), C.c_double(), C.c_longlong()
+    if args.gemm_csv and rank == 0:
+        torch.cuda.synchronize()
+        with open(args.gemm_csv, "w") as f:
+            f.write("idx,ms,M,N,K,a_mode,b_mode,epi,splits_z,BN,tflops\n")
+            i = 0
+            ms1, meta = C.c_double(), (C.c_int * 8)()
+            while lib.theia_prof_record(i, C.byref(ms1), meta) == 0:
+                z = meta[6] % 1000
+                fl = 2.0 * meta[0] * meta[1] * meta[2] * z
+                f.write(f"{i},{ms1.value:.5f},{meta[0]},{meta[1]},{meta[2]},{meta[3]},{meta[4]},{meta[5]},{meta[6]},"
+                        f"{meta[7]},{fl / (ms1.value * 1e-3) / 1e12 if ms1.value > 0 else 0:.1f}\n")
+                i += 1
     _lib.check(lib.theia_prof_collect(C.byref(pm), C.byref(pf), C.byref(pn)))
     _lib.check(lib.theia_prof_enable(0))
     launches = lib.theia_launch_count() - n0

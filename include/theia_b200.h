@@ -53,7 +53,8 @@ enum {
   THEIA_EPI_MUL_DGELU = 1 << 6, /* v *= gelu'(aux[m,n])                                             */
   THEIA_EPI_MUL_RELUMASK = 1 << 7, /* v = aux[m,n] > 0 ? v : 0                                      */
   THEIA_EPI_POSCLS = 1 << 8,    /* token t = m % tokens: t==0 ? cls[n]+pos[0,n] : v + pos[t,n]      */
-  THEIA_EPI_STATS = 1 << 9      /* per-image sum / sum-of-squares of the stored values -> stats     */
+  THEIA_EPI_STATS = 1 << 9,     /* per-image sum / sum-of-squares of the stored values -> stats     */
+  THEIA_EPI_COLSUM = 1 << 10    /* colsum[n] += sum over rows of the stored (bf16) values           */
 };
 
 typedef struct theia_conv_geom {
@@ -91,6 +92,7 @@ typedef struct theia_gemm_desc {
   int batch_z;      /* z slices (CONV_MN taps); out advances by out_z_stride elements per z */
   long long out_z_stride;
   int bn;           /* N tile: 0 = auto, else 128 / 192 / 256 */
+  float* colsum;    /* COLSUM: [N] fp32, accumulated */
 } theia_gemm_desc;
 
 int theia_gemm(const theia_gemm_desc* d, void* stream);
@@ -104,7 +106,8 @@ int theia_layernorm_fwd(const void* x, const float* gamma, const float* beta, vo
                         int M, int D, float eps, void* stream);
 /* dx = LN'(dy) (+ dadd); dgamma/dbeta are ACCUMULATED (+=) */
 int theia_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                        const void* dadd, void* dx, float* dgamma, float* dbeta, int M, int D, void* stream);
+                        const void* dadd, void* dx, float* dgamma, float* dbeta, float* dxsum, int M, int D,
+                        void* stream); /* dxsum (optional): [D] += column sums of the produced dx */
 /* nn.LayerNorm([C,H,W]) per image, NHWC storage, n = H*W*C (adapter_heads.py:306-324).  stats[b] =
  * {sum, sumsq} produced by the GEMM epilogue (THEIA_EPI_STATS). gamma/beta are the HWC-permuted affine. */
 int theia_ln3d_apply(const void* x, const float* stats, const float* gamma_hwc, const float* beta_hwc, void* y,
@@ -118,9 +121,10 @@ int theia_loss_fwd(const float* pred, const void* target, int target_is_bf16, fl
 /* dpred (bf16 or fp32) = coef3[0]*d(mse)/dp + coef3[1]*d(cos)/dp + coef3[2]*d(l1)/dp ; coef3 lives on the device */
 int theia_loss_bwd(const float* pred, const void* target, int target_is_bf16, const float* acc, const float* coef3,
                    void* dpred, int dpred_is_f32, int B, int n, void* stream);
-/* DeiT image processor without resize (backbones.py:337-339): uint8 HWC/CHW 224x224 -> bf16 patch rows
- * [B*197, 768] (row b*197 is the zero CLS slot; column = c*256 + i*16 + j) */
-int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_rescale,
+/* DeiT image processor (backbones.py:337-339; hf:image_processing_backends.py:361-414): uint8 HWC/CHW
+ * 224x224 -> [bicubic-antialias resize to 256 + centre crop 224 when do_resize] -> rescale/normalise ->
+ * bf16 patch rows [B*197, 768] (row b*197 is the zero CLS slot; column = c*256 + i*16 + j) */
+int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_resize, int do_rescale,
                      int do_normalize, const float* mean3, const float* std3, void* stream);
 /* attention (hf:modeling_vit.py:171-196,232-246): qkv [B*N,3*H*64] bf16 -> out [B*N,H*64]; lse [B,H,N] */
 int theia_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream);
@@ -159,16 +163,19 @@ int theia_model_num_params(const theia_model* m);
 /* state_dict key, shape and element offset (in the flat buffer) of parameter i */
 int theia_model_param_info(const theia_model* m, int i, char* name, int name_cap, long long* dims4, int* ndim,
                            long long* offset);
+/* test / bring-up accessor to a named internal activation of the last forward (see csrc/model.cu) */
+int theia_model_debug_ptr(theia_model* m, const char* name, int i, void** ptr, long long* elems, int* is_f32);
 int theia_model_bind(theia_model* m, float* master, float* grads, void* workspace);
 int theia_model_pack(theia_model* m, void* stream);
-int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channels_first, int do_rescale,
-                        int do_normalize, const float* mean3, const float* std3, int run_heads, float* const* preds,
+int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channels_first, int do_resize,
+                        int do_rescale, int do_normalize, const float* mean3, const float* std3, int run_heads, float* const* preds,
                         void* tokens_bf16_out, void* stream);
 int theia_model_backward(theia_model* m, const void* const* dpreds, void* stream);
 
 /* Per-launch CUDA-event timing of the GEMM kernel on its launching stream (bench.py roofline). */
 int theia_prof_enable(int on);
 int theia_prof_collect(double* total_ms, double* total_flops, long long* launches);
+int theia_prof_record(int i, double* ms, int* meta8);
 
 /* debug knobs for bring-up (descriptor field overrides); key 0 clears all */
 int theia_debug_set(int key, long long value);

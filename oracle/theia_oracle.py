@@ -207,7 +207,8 @@ def preprocess(x, do_resize=True, do_rescale=True, do_normalize=True,
     return x.contiguous()
 
 
-def vit_forward(P: dict, pix: torch.Tensor, cfg: OracleConfig) -> torch.Tensor:
+def vit_forward(P: dict, pix: torch.Tensor, cfg: OracleConfig, taps: Optional[dict] = None,
+                force: Optional[dict] = None) -> torch.Tensor:
     """ViTModel.forward (modeling_vit.py:428-458), pooler = Identity."""
     D, nh = cfg.hidden, cfg.heads
     e = "backbone.model.embeddings."
@@ -219,13 +220,26 @@ def vit_forward(P: dict, pix: torch.Tensor, cfg: OracleConfig) -> torch.Tensor:
     x = x.flatten(2).transpose(1, 2)  # [B,196,D]
     B = x.shape[0]
     x = _r(torch.cat([P[e + "cls_token"].expand(B, -1, -1), x], dim=1) + P[e + "position_embeddings"], cfg)
+
+    def tap(name, l, v):
+        """record an intermediate (taps) and/or teacher-force it (force): the VALUE becomes the given tensor,
+        the gradient still flows through the oracle's own op (tests: backward parity on identical activations)"""
+        if force is not None and (name, l) in force:
+            v = v + (force[(name, l)].to(v.dtype).view_as(v) - v).detach()
+        if taps is not None:
+            taps[(name, l)] = v.detach()
+        return v
+
+    x = tap("x", 0, x)
     for l in range(cfg.layers):
         p = f"backbone.model.encoder.layer.{l}."
         h = _r(F.layer_norm(x, (D,), P[p + "layernorm_before.weight"], P[p + "layernorm_before.bias"], cfg.ln_eps), cfg)
+        h = tap("ln1", l, h)
         q = _r(F.linear(h, _r(P[p + "attention.attention.query.weight"], cfg), P[p + "attention.attention.query.bias"]), cfg)
         k = _r(F.linear(h, _r(P[p + "attention.attention.key.weight"], cfg), P[p + "attention.attention.key.bias"]), cfg)
         v = _r(F.linear(h, _r(P[p + "attention.attention.value.weight"], cfg), P[p + "attention.attention.value.bias"]), cfg)
         N = x.shape[1]
+        q, k, v = tap("qkv", l, torch.cat([q, k, v], dim=-1)).split(D, dim=-1)
         q, k, v = (t.view(B, N, nh, D // nh).transpose(1, 2) for t in (q, k, v))
         sc = (q @ k.transpose(2, 3)) * ((D // nh) ** -0.5)
         if cfg.emulate_bf16:  # unnormalised probabilities rounded to bf16 before P.V, fp32 row sum
@@ -234,15 +248,23 @@ def vit_forward(P: dict, pix: torch.Tensor, cfg: OracleConfig) -> torch.Tensor:
         else:
             a = torch.softmax(sc, dim=-1) @ v
         a = _r(a.transpose(1, 2).reshape(B, N, D), cfg)
+        a = tap("attn", l, a)
         x = _r(F.linear(a, _r(P[p + "attention.output.dense.weight"], cfg), P[p + "attention.output.dense.bias"]) + x, cfg)
+        x = tap("xmid", l, x)
         h = _r(F.layer_norm(x, (D,), P[p + "layernorm_after.weight"], P[p + "layernorm_after.bias"], cfg.ln_eps), cfg)
-        h = _r(F.gelu(F.linear(h, _r(P[p + "intermediate.dense.weight"], cfg), P[p + "intermediate.dense.bias"])), cfg)
+        h = tap("ln2", l, h)
+        pre = F.linear(h, _r(P[p + "intermediate.dense.weight"], cfg), P[p + "intermediate.dense.bias"])
+        pre_t = tap("h", l, _r(pre, cfg))
+        h = _r(F.gelu(pre_t if force is not None else pre), cfg)
+        h = tap("a", l, h)
         x = _r(F.linear(h, _r(P[p + "output.dense.weight"], cfg), P[p + "output.dense.bias"]) + x, cfg)
+        x = tap("x", l + 1, x)
     return _r(F.layer_norm(x, (D,), P["backbone.model.layernorm.weight"], P["backbone.model.layernorm.bias"],
                            cfg.ln_eps), cfg)
 
 
-def lconv_head_forward(P: dict, t: str, x: torch.Tensor, cfg: OracleConfig) -> torch.Tensor:
+def lconv_head_forward(P: dict, t: str, x: torch.Tensor, cfg: OracleConfig, taps: Optional[dict] = None,
+                       force: Optional[dict] = None) -> torch.Tensor:
     """LightConvAdapterHead.forward (adapter_heads.py:352-359) for a 14x14 source."""
     ct, ht, wt = cfg.teachers[t]
     p = f"translator.translator_heads.{head_key(t)}."
@@ -251,6 +273,15 @@ def lconv_head_forward(P: dict, t: str, x: torch.Tensor, cfg: OracleConfig) -> t
     y = x[:, 1:].reshape(B, g, g, C).permute(0, 3, 1, 2)  # drop CLS; b (h w) c -> b c h w
     y = _r(F.conv_transpose2d(y, _r(P[p + "pad.1.weight"], cfg), P[p + "pad.1.bias"], stride=1), cfg)  # 14 -> 16
 
+    def tap(name, v):  # NHWC like the CUDA path stores it
+        if force is not None and (name, t) in force:
+            v = v + (force[(name, t)].to(v.dtype).permute(0, 3, 1, 2) - v).detach()
+        if taps is not None:
+            taps[(name, t)] = v.detach().permute(0, 2, 3, 1).contiguous()
+        return v
+
+    y = tap("padout", y)
+
     def ln(y, k):
         return _r(F.layer_norm(y, y.shape[1:], P[p + f"adapter.{k}.weight"], P[p + f"adapter.{k}.bias"], 1e-5), cfg)
 
@@ -258,11 +289,16 @@ def lconv_head_forward(P: dict, t: str, x: torch.Tensor, cfg: OracleConfig) -> t
         return _r(P[p + f"adapter.{k}.weight"], cfg)
 
     y = ln(y, 0)
+    y = tap("hln0", y)
     if ht == 16:
         y = _r(F.relu(F.conv2d(y, w(1), P[p + "adapter.1.bias"], padding=1)), cfg)
+        y = tap("c1", y)
         y = ln(y, 3)
+        y = tap("hln1", y)
         y = _r(F.relu(F.conv2d(y, w(4), P[p + "adapter.4.bias"], padding=1)), cfg)
+        y = tap("c2", y)
         y = ln(y, 6)
+        y = tap("hln2", y)
     else:
         y = _r(F.relu(F.conv_transpose2d(y, w(1), P[p + "adapter.1.bias"], stride=2, padding=1)), cfg)
         y = ln(y, 3)
@@ -287,8 +323,8 @@ def handle_feature_output(x, feature_reduce_method=None, num_discard_tokens=0):
     raise NotImplementedError(f"feature_reduce_method {feature_reduce_method} it not implemented.")
 
 
-def backbone_forward(P, images, cfg, **kw):
-    return vit_forward(P, preprocess(images, **kw).to(next(iter(P.values())).device), cfg)
+def backbone_forward(P, images, cfg, taps=None, force=None, **kw):
+    return vit_forward(P, preprocess(images, **kw).to(next(iter(P.values())).device), cfg, taps, force)
 
 
 def forward_feature(P, images, cfg, feature_reduce_method=None, **kw):
@@ -296,11 +332,15 @@ def forward_feature(P, images, cfg, feature_reduce_method=None, **kw):
     return handle_feature_output(backbone_forward(P, images, cfg, **kw), feature_reduce_method)
 
 
-def forward(P, images, cfg, target_model_names=None, **kw) -> dict:
+def forward(P, images, cfg, target_model_names=None, taps=None, force=None, **kw) -> dict:
     """RobotVisionFM.forward (rvfm.py:115-136)."""
-    x = backbone_forward(P, images, cfg, **kw)
+    x = backbone_forward(P, images, cfg, taps, force, **kw)
+    if force is not None and ("tokens", 0) in force:
+        x = x + (force[("tokens", 0)].to(x.dtype).view_as(x) - x).detach()
+    if taps is not None:
+        taps[("tokens", 0)] = x.detach()
     names = target_model_names if target_model_names is not None else list(cfg.teachers)
-    return {t: lconv_head_forward(P, t, x, cfg) for t in names}
+    return {t: lconv_head_forward(P, t, x, cfg, taps, force) for t in names}
 
 
 def get_loss(pred: dict, y: dict, target_loss_weights=None) -> dict:
@@ -338,11 +378,11 @@ def main_loss(losses: dict, kind: str = "cos_l1"):
     return 0.9 * losses["cos_loss"] + 0.1 * losses["l1_loss"]
 
 
-def distill_step(P: dict, images, targets: dict, cfg: OracleConfig, kind="cos_l1", **kw):
+def distill_step(P: dict, images, targets: dict, cfg: OracleConfig, kind="cos_l1", force=None, **kw):
     """Replay of train_rvfm.py:116-125 (forward, get_loss, main loss, backward) under autograd.
     Returns (preds, losses, grads)."""
     Pg = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
-    preds = forward(Pg, images, cfg, **kw)
+    preds = forward(Pg, images, cfg, force=force, **kw)
     losses = get_loss(preds, targets)
     ml = main_loss(losses, kind)
     ml.backward()

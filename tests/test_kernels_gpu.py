@@ -76,10 +76,13 @@ def test_gemm_epilogues(lib):
     gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=o32, ldo=N, bias=bias, epi=L.EPI_OUT_F32)
     assert relerr(o32, acc) < 1e-5
     # gelu' and relu-mask multipliers
-    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, aux=aux, epi=L.EPI_MUL_DGELU)
+    cs = torch.zeros(N, device=DEV)
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, aux=aux, epi=L.EPI_MUL_DGELU | L.EPI_COLSUM,
+         colsum=cs)
     x = aux.float().requires_grad_(True)
     F.gelu(x).sum().backward()
     assert relerr(out.float(), (acc - bias) * x.grad) < 8e-3
+    assert relerr(cs, out.float().sum(0)) < 1e-4
     gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, aux=aux, epi=L.EPI_MUL_RELUMASK)
     assert relerr(out.float(), (acc - bias) * (aux.float() > 0)) < 6e-3
     # relu
@@ -238,12 +241,14 @@ def test_layernorm_fwd_bwd(lib, M, D):
     assert relerr(y.float(), ref) < 5e-3
     ref.backward(dy.float())
     dx = torch.empty_like(x)
-    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    dg, db, dxs = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
     L.check(lib.theia_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                    dadd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), M, D, S()))
+                                    dadd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dxs.data_ptr(), M, D,
+                                    S()))
     assert relerr(dx.float(), xr.grad + dadd.float()) < 6e-3
     assert relerr(dg, gr.grad) < 1e-3
     assert relerr(db, br.grad) < 1e-3
+    assert relerr(dxs, dx.float().sum(0)) < 1e-4  # fused column sums of the produced dx (bias gradient)
 
 
 def test_ln3d_apply_and_bwd(lib):
@@ -313,12 +318,40 @@ def test_preprocess(lib, chw):
     out = torch.empty(Bn * 197, 768, dtype=torch.bfloat16, device=DEV)
     mean, std = (C.c_float * 3)(*O.IMAGE_MEAN), (C.c_float * 3)(*O.IMAGE_STD)
     d = img.to(DEV)
-    L.check(lib.theia_preprocess(d.data_ptr(), out.data_ptr(), Bn, chw, 1, 1, mean, std, S()))
+    L.check(lib.theia_preprocess(d.data_ptr(), out.data_ptr(), Bn, chw, 0, 1, 1, mean, std, S()))
     pix = O.preprocess(img, do_resize=False)  # [B,3,224,224]
     ref = F.unfold(pix, 16, stride=16).transpose(1, 2)  # [B,196, c*256+i*16+j]
     o = out.float().view(Bn, 197, 768).cpu()
     assert torch.all(o[:, 0] == 0)
     assert relerr(o[:, 1:], ref) < 4e-3
+
+
+@pytest.mark.parametrize("chw", [0, 1])
+def test_preprocess_with_bicubic_resize(lib, chw):
+    """do_resize=True (the reference's default): resize 256 bicubic-antialias on uint8 + centre crop 224.
+    Checked against the oracle running the torchvision CUDA path the reference itself takes for device tensors."""
+    from oracle import theia_oracle as O
+    Bn = 2
+    g = torch.Generator().manual_seed(1)
+    img = torch.randint(0, 256, (Bn, 224, 224, 3), dtype=torch.uint8, generator=g)
+    # smooth content too (random noise alone under-tests the interpolation)
+    yy, xx = torch.meshgrid(torch.arange(224), torch.arange(224), indexing="ij")
+    img[1] = ((yy[..., None] * 0.7 + xx[..., None] * 0.4 + torch.arange(3) * 40) % 256).to(torch.uint8)
+    if chw:
+        img = img.permute(0, 3, 1, 2).contiguous()
+    d = img.to(DEV)
+    out = torch.empty(Bn * 197, 768, dtype=torch.bfloat16, device=DEV)
+    mean, std = (C.c_float * 3)(*O.IMAGE_MEAN), (C.c_float * 3)(*O.IMAGE_STD)
+    L.check(lib.theia_preprocess(d.data_ptr(), out.data_ptr(), Bn, chw, 1, 1, 1, mean, std, S()))
+    pix = O.preprocess(d, do_resize=True)  # device tensor -> torchvision float path + round
+    ref = F.unfold(pix, 16, stride=16).transpose(1, 2)
+    o = out.float().view(Bn, 197, 768)
+    assert torch.all(o[:, 0] == 0)
+    assert relerr(o[:, 1:], ref) < 4e-3
+    # uint8 levels agree exactly almost everywhere (float summation order may move a .5 boundary)
+    lev = lambda x, c: x * (255 * O.IMAGE_STD[c]) + 255 * O.IMAGE_MEAN[c]
+    diff = (lev(o[:, 1:, :256], 0) - lev(ref[:, :, :256], 0)).abs()
+    assert (diff > 1.6).float().mean().item() < 1e-4
 
 
 # ----------------------------------------------------------------------------- attention

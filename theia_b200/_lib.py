@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "libtheia_b200.so")
 
 OP_K2D, OP_MN2D, OP_CONV_K, OP_CONV_MN = 0, 1, 2, 3
 EPI_GELU, EPI_RELU, EPI_RESID, EPI_OUT_F32, EPI_ATOMIC = 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5
-EPI_MUL_DGELU, EPI_MUL_RELUMASK, EPI_POSCLS, EPI_STATS = 1 << 6, 1 << 7, 1 << 8, 1 << 9
+EPI_MUL_DGELU, EPI_MUL_RELUMASK, EPI_POSCLS, EPI_STATS, EPI_COLSUM = 1 << 6, 1 << 7, 1 << 8, 1 << 9, 1 << 10
 MAX_TEACHERS = 8
 
 
@@ -32,7 +32,7 @@ class GemmDesc(C.Structure):
                 ("conv", ConvGeom), ("epi", C.c_int), ("out", C.c_void_p), ("ldo", C.c_longlong),
                 ("out2", C.c_void_p), ("bias", C.c_void_p), ("aux", C.c_void_p), ("pos", C.c_void_p),
                 ("cls", C.c_void_p), ("tokens", C.c_int), ("stats", C.c_void_p), ("rows_per_image", C.c_int),
-                ("splits", C.c_int), ("batch_z", C.c_int), ("out_z_stride", C.c_longlong), ("bn", C.c_int)]
+                ("splits", C.c_int), ("batch_z", C.c_int), ("out_z_stride", C.c_longlong), ("bn", C.c_int), ("colsum", C.c_void_p)]
 
 
 class ModelConfig(C.Structure):
@@ -51,14 +51,15 @@ SYMBOLS = {
     "theia_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
     "theia_debug_set": (_i, [_i, _ll]),
     "theia_prof_enable": (_i, [_i]),
+    "theia_prof_record": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i)]),
     "theia_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "theia_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
-    "theia_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "theia_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "theia_ln3d_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "theia_ln3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
     "theia_loss_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "theia_loss_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "theia_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp]),
+    "theia_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp]),
     "theia_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_gather4": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _vp]),
@@ -72,9 +73,10 @@ SYMBOLS = {
     "theia_model_workspace_bytes": (_ll, [_vp]),
     "theia_model_num_params": (_i, [_vp]),
     "theia_model_param_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_ll), C.POINTER(_i), C.POINTER(_ll)]),
+    "theia_model_debug_ptr": (_i, [_vp, C.c_char_p, _i, C.POINTER(_vp), C.POINTER(_ll), C.POINTER(_i)]),
     "theia_model_bind": (_i, [_vp, _vp, _vp, _vp]),
     "theia_model_pack": (_i, [_vp, _vp]),
-    "theia_model_forward": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i,
+    "theia_model_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i,
                                  C.POINTER(_vp), _vp, _vp]),
     "theia_model_backward": (_i, [_vp, C.POINTER(_vp), _vp]),
 }

@@ -86,79 +86,104 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  optional + dadd (residual grad).
-// dgamma/dbeta: per-lane register partials over the rows a warp visits, block-reduced, atomics.
+// dgamma/dbeta (and optionally the column sums of dx = bias gradient of the producer Linear): per-lane
+// register partials over the rows a warp visits, block-reduced in shared memory, one atomic per column
+// per block.  NCH = 16-byte chunks per lane (D <= 256*NCH); dy/x stay packed in registers between passes.
+template <int NCH>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in,
                                                             const bf16* __restrict__ dadd, bf16* __restrict__ dx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            int M, int D) {
-  extern __shared__ float red[];  // [2][D]
+                                                            float* __restrict__ dxsum, int M, int D) {
+  extern __shared__ float red[];  // [3][D]
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int nch = D >> 3;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
-  float ag[LN_MAXC][8], ab[LN_MAXC][8], gm[LN_MAXC][8];
+  float ag[NCH][8], ab[NCH][8], ax[NCH][8], gm[NCH][8];
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
+  for (int c = 0; c < NCH; ++c) {
     const int ch = lane + 32 * c;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) ag[c][e] = 0.f, ab[c][e] = 0.f, gm[c][e] = 0.f;
+    for (int e = 0; e < 8; ++e) ag[c][e] = 0.f, ab[c][e] = 0.f, ax[c][e] = 0.f, gm[c][e] = 0.f;
     if (ch < nch) load8f(gamma + ch * 8, gm[c]);
   }
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < M; row += warps_total) {
     const float mean = mean_in[row], rstd = rstd_in[row];
     const long long base = static_cast<long long>(row) * D;
-    float g[LN_MAXC][8], xh[LN_MAXC][8];
+    uint4 pd[NCH], px[NCH], pa[NCH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
-        float d[8], xv[8];
-        load8(dy + base + ch * 8, d);
-        load8(x + base + ch * 8, xv);
+        pd[c] = *reinterpret_cast<const uint4*>(dy + base + ch * 8);
+        px[c] = *reinterpret_cast<const uint4*>(x + base + ch * 8);
+        if (dadd) pa[c] = *reinterpret_cast<const uint4*>(dadd + base + ch * 8);
+      }
+    }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          xh[c][e] = (xv[e] - mean) * rstd;
-          g[c][e] = d[e] * gm[c][e];
-          s1 += g[c][e];
-          s2 += g[c][e] * xh[c][e];
-          ag[c][e] += d[e] * xh[c][e];
-          ab[c][e] += d[e];
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        const uint32_t* ud = reinterpret_cast<const uint32_t*>(&pd[c]);
+        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&px[c]);
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const float2 d = unpack_bf16x2(ud[e2]), xv = unpack_bf16x2(ux[e2]);
+          const float xh0 = (xv.x - mean) * rstd, xh1 = (xv.y - mean) * rstd;
+          const float g0 = d.x * gm[c][2 * e2], g1 = d.y * gm[c][2 * e2 + 1];
+          s1 += g0 + g1;
+          s2 += g0 * xh0 + g1 * xh1;
+          ag[c][2 * e2] += d.x * xh0, ag[c][2 * e2 + 1] += d.y * xh1;
+          ab[c][2 * e2] += d.x, ab[c][2 * e2 + 1] += d.y;
         }
       }
     }
     s1 = warp_sum(s1) / D;
     s2 = warp_sum(s2) / D;
 #pragma unroll
-    for (int c = 0; c < LN_MAXC; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
-        float o[8];
+        const uint32_t* ud = reinterpret_cast<const uint32_t*>(&pd[c]);
+        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&px[c]);
+        const uint32_t* ua = reinterpret_cast<const uint32_t*>(&pa[c]);
+        uint4 outp;
+        uint32_t* uo = reinterpret_cast<uint32_t*>(&outp);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rstd * (g[c][e] - s1 - xh[c][e] * s2);
-        if (dadd) {
-          float a[8];
-          load8(dadd + base + ch * 8, a);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] += a[e];
+        for (int e2 = 0; e2 < 4; ++e2) {
+          const float2 d = unpack_bf16x2(ud[e2]), xv = unpack_bf16x2(ux[e2]);
+          const float xh0 = (xv.x - mean) * rstd, xh1 = (xv.y - mean) * rstd;
+          float o0 = rstd * (d.x * gm[c][2 * e2] - s1 - xh0 * s2);
+          float o1 = rstd * (d.y * gm[c][2 * e2 + 1] - s1 - xh1 * s2);
+          if (dadd) {
+            const float2 a = unpack_bf16x2(ua[e2]);
+            o0 += a.x, o1 += a.y;
+          }
+          uo[e2] = pack_bf16x2(o0, o1);
+          if (dxsum) {
+            const float2 q = unpack_bf16x2(uo[e2]);
+            ax[c][2 * e2] += q.x, ax[c][2 * e2 + 1] += q.y;
+          }
         }
-        store8(dx + base + ch * 8, o);
+        *reinterpret_cast<uint4*>(dx + base + ch * 8) = outp;
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
+  for (int c = 0; c < NCH; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nch) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         atomicAdd(&red[ch * 8 + e], ag[c][e]);
         atomicAdd(&red[D + ch * 8 + e], ab[c][e]);
+        if (dxsum) atomicAdd(&red[2 * D + ch * 8 + e], ax[c][e]);
       }
     }
   }
@@ -166,6 +191,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
     atomicAdd(dgamma + i, red[i]);
     atomicAdd(dbeta + i, red[D + i]);
+    if (dxsum) atomicAdd(dxsum + i, red[2 * D + i]);
   }
 }
 
@@ -446,6 +472,64 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
   store8(out + row * 768 + k8 * 8, o);
 }
 
+// --------------------------------------------------------------------------------------------
+// DeiT processor WITH resize (the reference's default): bicubic antialias 224 -> 256 (torch
+// `_upsample_bicubic2d_aa`, a = -0.5, float accumulation: horizontal taps first, then vertical),
+// clamp, round-half-even to uint8 levels, centre crop 224 (= resized pixels 16..239), normalise.
+// The per-output tap tables are computed on the host exactly as ATen does and kept in constant memory.
+// --------------------------------------------------------------------------------------------
+struct ResizeTable {
+  int xmin[256];
+  int xsize[256];
+  float w[256][5];
+};
+__constant__ ResizeTable c_rt;
+
+__global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out,
+                                                                int B, int chw, float s0, float s1, float s2, float o0,
+                                                                float o1, float o2) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * 197 * 96;
+  if (t >= total) return;
+  const int k8 = static_cast<int>(t % 96);
+  const long long row = t / 96;
+  const int tok = static_cast<int>(row % 197);
+  const int b = static_cast<int>(row / 197);
+  float o[8];
+  if (tok == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  } else {
+    const int p = tok - 1, py = p / 14, px = p % 14;
+    const int k = k8 * 8;
+    const int c = k >> 8, i = (k >> 4) & 15, j = k & 15;
+    const int oy = py * 16 + i + 16;
+    const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const float of = c == 0 ? o0 : (c == 1 ? o1 : o2);
+    const int ymin = c_rt.xmin[oy], ysize = c_rt.xsize[oy];
+    const long long pix_stride = chw ? 1 : 3;
+    const long long row_stride = chw ? 224 : 224 * 3;
+    const uint8_t* base = chw ? img + (static_cast<long long>(b) * 3 + c) * 224 * 224
+                              : img + static_cast<long long>(b) * 224 * 224 * 3 + c;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ox = px * 16 + j + e + 16;
+      const int xmin = c_rt.xmin[ox], xsize = c_rt.xsize[ox];
+      float acc = 0.f;
+      for (int y = 0; y < ysize; ++y) {
+        const uint8_t* src = base + (ymin + y) * row_stride + xmin * pix_stride;
+        float r = static_cast<float>(src[0]) * c_rt.w[ox][0];
+        for (int x = 1; x < xsize; ++x) r += static_cast<float>(src[x * pix_stride]) * c_rt.w[ox][x];
+        if (y == 0) acc = r * c_rt.w[oy][0];
+        else acc += r * c_rt.w[oy][y];
+      }
+      acc = rintf(fminf(fmaxf(acc, 0.f), 255.f));
+      o[e] = (acc - of) * sc;
+    }
+  }
+  store8(out + row * 768 + k8 * 8, o);
+}
+
 // ============================================================================================
 // Generic strided gather (parameter packing / gradient unpacking).
 //   out[((a*n1 + b)*n2 + c)*n3 + d] = in[base + a*s0 + b*s1 + c*s2 + d*s3]
@@ -566,15 +650,22 @@ extern "C" int theia_layernorm_fwd(const void* x, const float* gamma, const floa
 }
 
 extern "C" int theia_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
-                                   const float* rstd, const void* dadd, void* dx, float* dgamma, float* dbeta, int M,
-                                   int D, void* stream) {
+                                   const float* rstd, const void* dadd, void* dx, float* dgamma, float* dbeta,
+                                   float* dxsum, int M, int D, void* stream) {
   if (D % 8 != 0 || D > 1024) return set_error(THEIA_ERR_ARG, "layernorm: D %% 8 == 0 and D <= 1024 required");
   if (M <= 0) return THEIA_OK;
-  int grid = num_sms() * 2;
+  int grid = num_sms() * 4;
   if (grid > (M + 7) / 8) grid = (M + 7) / 8;
-  layernorm_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), S(stream)>>>(
-      static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd, static_cast<const bf16*>(dadd),
-      static_cast<bf16*>(dx), dgamma, dbeta, M, D);
+  const size_t sm = 3 * D * sizeof(float);
+#define LNB(N)                                                                                                      \
+  layernorm_bwd_kernel<N><<<grid, 256, sm, S(stream)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), \
+                                                        gamma, mean, rstd, static_cast<const bf16*>(dadd),          \
+                                                        static_cast<bf16*>(dx), dgamma, dbeta, dxsum, M, D)
+  if (D <= 256) LNB(1);
+  else if (D <= 512) LNB(2);
+  else if (D <= 768) LNB(3);
+  else LNB(4);
+#undef LNB
   THEIA_CHECK_LAUNCH("layernorm_bwd");
   return THEIA_OK;
 }
@@ -643,8 +734,53 @@ extern "C" int theia_loss_bwd(const float* pred, const void* target, int target_
   return THEIA_OK;
 }
 
-extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_rescale,
-                                int do_normalize, const float* mean3, const float* std3, void* stream) {
+static double bicubic_aa_filter(float xf) {
+  // ATen upsample aa bicubic filter (a = -0.5); its literals are doubles, so it evaluates in double
+  double x = xf;
+  const float a = -0.5f;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0;
+  if (x < 2.0) return (((x - 5.0) * x + 8.0) * x - 4.0) * a;
+  return 0.0;
+}
+
+static int upload_resize_table() {
+  static bool done = false;
+  if (done) return 0;
+  static ResizeTable rt;
+  const float scale = 224.0f / 256.0f;
+  const float support = 2.0f;  // interp_size 4 * 0.5 (scale < 1: no widening)
+  const float invscale = 1.0f;
+  for (int o = 0; o < 256; ++o) {
+    const float center = scale * (o + 0.5f);
+    int xmin = static_cast<int>(center - support + 0.5f);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5f);
+    if (xmax > 224) xmax = 224;
+    const int xsize = xmax - xmin;
+    const float xmin_m_center = xmin - center;
+    float total = 0.f;
+    float w[5] = {0, 0, 0, 0, 0};
+    for (int j = 0; j < xsize && j < 5; ++j) {
+      const float wj = static_cast<float>(bicubic_aa_filter((j + xmin_m_center + 0.5f) * invscale));
+      w[j] = wj;
+      total += wj;
+    }
+    for (int j = 0; j < xsize && j < 5; ++j)
+      if (total != 0.f) w[j] /= total;
+    rt.xmin[o] = xmin;
+    rt.xsize[o] = xsize > 5 ? 5 : xsize;
+    for (int j = 0; j < 5; ++j) rt.w[o][j] = w[j];
+  }
+  cudaError_t e = cudaMemcpyToSymbol(c_rt, &rt, sizeof(rt));
+  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "resize table upload: %s", cudaGetErrorString(e));
+  done = true;
+  return 0;
+}
+
+extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_resize,
+                                int do_rescale, int do_normalize, const float* mean3, const float* std3,
+                                void* stream) {
   // out = (x - off) * scale  per channel
   float sc[3], of[3];
   for (int c = 0; c < 3; ++c) {
@@ -659,8 +795,16 @@ extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int
     }
   }
   const long long total = static_cast<long long>(B) * 197 * 96;
-  preprocess_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, S(stream)>>>(
-      images, static_cast<bf16*>(patches), B, channels_first, sc[0], sc[1], sc[2], of[0], of[1], of[2]);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (do_resize) {
+    int rc = upload_resize_table();
+    if (rc) return rc;
+    preprocess_resize_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), B, channels_first,
+                                                          sc[0], sc[1], sc[2], of[0], of[1], of[2]);
+  } else {
+    preprocess_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), B, channels_first, sc[0],
+                                                   sc[1], sc[2], of[0], of[1], of[2]);
+  }
   THEIA_CHECK_LAUNCH("preprocess");
   return THEIA_OK;
 }

@@ -7,8 +7,9 @@
 //                            = the convolution padding)
 //   warp 1   MMA issuer     (one thread, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue      (tcgen05.ld -> registers -> swizzled smem transpose -> coalesced
-//                            global stores with the fused epilogue)
+//   warps 4-11 epilogue     (tcgen05.ld -> registers -> swizzled smem transpose -> coalesced
+//                            global stores with the fused epilogue; two warps per TMEM lane quarter,
+//                            alternating 32-column chunks; epilogue flags are compile-time)
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring
 // (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -44,6 +45,7 @@ struct GemmK {
   const float* cls;
   int tokens;
   float* stats;
+  float* colsum;
   long long out_z_stride;
   uint32_t idesc;
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
@@ -52,7 +54,9 @@ struct GemmK {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int STAGING_BYTES = 4 * 32 * 32 * 4;
+constexpr int EPI_WARPS = 8;
+constexpr int NTHREADS = 128 + EPI_WARPS * 32;
+constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB
 
 template <int BN>
@@ -81,8 +85,34 @@ __device__ __forceinline__ Item decode_item(const GemmK& p, int item) {
   return it;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+// A&S 7.1.26 erf (|err| <= 1.5e-7) sharing one exp with the Gaussian pdf: the exact-erf GELU and its
+// derivative at ~12 instructions per element instead of erff()+expf().
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float e = __expf(-ax * ax);
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfa = 1.0f - poly * t * e;  // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.0f + copysignf(erfa, x));
+  pdf = 0.39894228040143268f * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float c, d;
+  gelu_parts(x, c, d);
+  return x * c;
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  float c, d;
+  gelu_parts(x, c, d);
+  return fmaf(x, d, c);
+}
+
+// EPI_CT >= 0: epilogue flags are a compile-time constant (hot combinations); -1: read p.epi.
+template <int BN, int EPI_CT>
+__global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmK p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -109,7 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
+      mbar_init(&tempty[s], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -202,24 +232,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ============================== epilogue ==============================
-    const int wq = warp - 4;  // TMEM lane quarter == warp % 4
-    float* stg = staging_all + wq * (32 * 32);
+    const int ew = warp - 4;      // 0..7
+    const int wq = ew & 3;        // TMEM lane quarter == warp % 4
+    const int hsel = ew >> 2;     // this warp takes the 32-column chunks with (chunk & 1) == hsel
+    float* stg = staging_all + ew * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int epi = p.epi;
+    const int epi = (EPI_CT >= 0) ? EPI_CT : p.epi;
+    const int c = lane & 7;
+    const int rsub = lane >> 3;
+    constexpr int NCHUNK = BN / 32;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const Item it = decode_item(p, item);
+      // ---- per-tile row bookkeeping: this lane touches rows rr = 4*i + rsub of its warp's slab ----
+      long long rowoff[8];
+      uint32_t okmask = 0;
+      int img = 0;
+      if (p.conv_out) img = it.m_blk / p.tiles_per_img;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = wq * 32 + i * 4 + rsub;
+        const int m = it.m_blk * BM + r;
+        long long orow;
+        bool ok;
+        if (p.conv_out) {
+          const int ht = it.m_blk - img * p.tiles_per_img;
+          const int hh = r / p.tile_w, ww = r - hh * p.tile_w;
+          const int h = ht * p.tile_h + hh;
+          ok = (h < p.out_h) && (ww < p.out_w);
+          orow = static_cast<long long>(img) * p.out_img_rows + p.out_row_off +
+                 static_cast<long long>(h * p.sy + p.py) * p.out_wpitch + (ww * p.sx + p.px);
+        } else {
+          ok = m < p.M;
+          orow = m;
+        }
+        rowoff[i] = orow * p.ldo;
+        okmask |= (ok ? 1u : 0u) << i;
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       float st_s = 0.f, st_ss = 0.f;
-      int img = 0;
-      if (p.conv_out) img = it.m_blk / p.tiles_per_img;
-      constexpr int NCHUNK = BN / 32;
 #pragma unroll 1
-      for (int ch = 0; ch < NCHUNK; ++ch) {
+      for (int ch = hsel; ch < NCHUNK; ch += 2) {
+        const bool last = (ch + 2 >= NCHUNK);
         const int nbase = it.n_blk * BN + ch * 32;
-        if (nbase >= p.N) {  // nothing to store; still release the accumulator below
-          if (ch == NCHUNK - 1) {
+        if (nbase >= p.N) {  // nothing to store; still release the accumulator
+          if (last) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -229,7 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + ch * 32, v);
         tmem_ld_wait();
-        if (ch == NCHUNK - 1) {  // all TMEM reads of this accumulator are done
+        if (last) {  // all TMEM reads of this warp for this accumulator are done
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -249,34 +307,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         // phase 2: 4 rows x 128 B per warp instruction, coalesced global access
-        const int c = lane & 7;
         const int n = nbase + c * 4;
-        const bool ncol_ok = n < p.N;
+        const uint32_t ok = (n < p.N) ? okmask : 0u;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && ncol_ok) bias4 = *reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll 2
+        if (p.bias != nullptr && ok) bias4 = *reinterpret_cast<const float4*>(p.bias + n);
+        float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
+        uint2 aux[8];
+        if (epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK)) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            aux[i] = ((ok >> i) & 1u) ? *reinterpret_cast<const uint2*>(p.aux + rowoff[i] + n) : make_uint2(0u, 0u);
+        }
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + (lane >> 3);  // row within the warp's 32-row slab
-          const int r = wq * 32 + rr;          // row within the tile
-          float4 f = reinterpret_cast<const float4*>(stg + rr * 32)[c ^ (rr & 7)];
-          long long orow;
-          bool ok = ncol_ok;
-          int m = it.m_blk * BM + r;
-          if (p.conv_out) {
-            const int ht = it.m_blk - img * p.tiles_per_img;
-            const int hh = r / p.tile_w, ww = r - hh * p.tile_w;
-            const int h = ht * p.tile_h + hh;
-            ok = ok && (h < p.out_h) && (ww < p.out_w);
-            orow = static_cast<long long>(img) * p.out_img_rows + p.out_row_off +
-                   static_cast<long long>(h * p.sy + p.py) * p.out_wpitch + (ww * p.sx + p.px);
-          } else {
-            ok = ok && (m < p.M);
-            orow = m;
-          }
-          if (!ok) continue;
-          const long long off = orow * p.ldo + n;
+          const int rr = i * 4 + rsub;
+          const float4 f = reinterpret_cast<const float4*>(stg + rr * 32)[c ^ (rr & 7)];
+          if (!((ok >> i) & 1u)) continue;
+          const long long off = rowoff[i] + n;
           float x0 = f.x + bias4.x, x1 = f.y + bias4.y, x2 = f.z + bias4.z, x3 = f.w + bias4.w;
           if (epi & THEIA_EPI_POSCLS) {
+            const int m = it.m_blk * BM + wq * 32 + rr;
             const int t = m % p.tokens;
             const float4 ps = *reinterpret_cast<const float4*>(p.pos + static_cast<long long>(t) * p.N + n);
             if (t == 0) {
@@ -291,16 +341,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             pre.x = pack_bf16x2(x0, x1);
             pre.y = pack_bf16x2(x2, x3);
             *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + off) = pre;
-            x0 = gelu_exact(x0), x1 = gelu_exact(x1), x2 = gelu_exact(x2), x3 = gelu_exact(x3);
+            x0 = gelu_fast(x0), x1 = gelu_fast(x1), x2 = gelu_fast(x2), x3 = gelu_fast(x3);
           }
           if (epi & THEIA_EPI_RELU) {
             x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f), x2 = fmaxf(x2, 0.f), x3 = fmaxf(x3, 0.f);
           }
           if (epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK)) {
-            const uint2 a = *reinterpret_cast<const uint2*>(p.aux + off);
-            const float2 a01 = unpack_bf16x2(a.x), a23 = unpack_bf16x2(a.y);
+            const float2 a01 = unpack_bf16x2(aux[i].x), a23 = unpack_bf16x2(aux[i].y);
             if (epi & THEIA_EPI_MUL_DGELU) {
-              x0 *= gelu_grad(a01.x), x1 *= gelu_grad(a01.y), x2 *= gelu_grad(a23.x), x3 *= gelu_grad(a23.y);
+              x0 *= dgelu_fast(a01.x), x1 *= dgelu_fast(a01.y), x2 *= dgelu_fast(a23.x), x3 *= dgelu_fast(a23.y);
             } else if (epi & THEIA_EPI_MUL_RELUMASK) {
               x0 = a01.x > 0.f ? x0 : 0.f, x1 = a01.y > 0.f ? x1 : 0.f;
               x2 = a23.x > 0.f ? x2 : 0.f, x3 = a23.y > 0.f ? x3 : 0.f;
@@ -310,10 +359,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (epi & THEIA_EPI_ATOMIC) {
             float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(it.z) * p.out_z_stride + off;
-            atomicAdd(o + 0, x0);
-            atomicAdd(o + 1, x1);
-            atomicAdd(o + 2, x2);
-            atomicAdd(o + 3, x3);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(x0), "f"(x1), "f"(x2), "f"(x3)
+                         : "memory");
           } else if (epi & THEIA_EPI_OUT_F32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(x0, x1, x2, x3);
           } else {
@@ -321,12 +368,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             o.x = pack_bf16x2(x0, x1);
             o.y = pack_bf16x2(x2, x3);
             *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + off) = o;
-            if (epi & THEIA_EPI_STATS) {
+            if (epi & (THEIA_EPI_STATS | THEIA_EPI_COLSUM)) {
               const float2 q01 = unpack_bf16x2(o.x), q23 = unpack_bf16x2(o.y);
-              st_s += (q01.x + q01.y) + (q23.x + q23.y);
-              st_ss += (q01.x * q01.x + q01.y * q01.y) + (q23.x * q23.x + q23.y * q23.y);
+              if (epi & THEIA_EPI_STATS) {
+                st_s += (q01.x + q01.y) + (q23.x + q23.y);
+                st_ss += (q01.x * q01.x + q01.y * q01.y) + (q23.x * q23.x + q23.y * q23.y);
+              }
+              if (epi & THEIA_EPI_COLSUM) cs0 += q01.x, cs1 += q01.y, cs2 += q23.x, cs3 += q23.y;
             }
           }
+        }
+        if (epi & THEIA_EPI_COLSUM) {  // column sums of the stored tile rows (bias gradient of the consumer)
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8), cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8), cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
+          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16), cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16), cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+          if (rsub == 0 && n < p.N)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + n), "f"(cs0), "f"(cs1),
+                         "f"(cs2), "f"(cs3)
+                         : "memory");
         }
         __syncwarp();
       }
@@ -361,6 +421,7 @@ constexpr int PROF_RING = 8192;
 static bool g_prof_on = false;
 static cudaEvent_t g_ev0[PROF_RING], g_ev1[PROF_RING];
 static double g_prof_flops[PROF_RING];
+static int g_prof_meta[PROF_RING][8];
 static int g_prof_n = 0;
 static bool g_prof_init = false;
 
@@ -372,12 +433,12 @@ static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
   return encode_tensor_map(tm, ptr, 2, dims, strides, box);
 }
 
-template <int BN>
+template <int BN, int EPI_CT>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k, cudaStream_t stream) {
   using C = Cfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
     attr_done = true;
@@ -385,16 +446,42 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k
   int grid = k.total_items < num_sms() ? k.total_items : num_sms();
   const bool prof = g_prof_on && g_prof_n < PROF_RING;
   if (prof) cudaEventRecord(g_ev0[g_prof_n], stream);
-  gemm_tc_kernel<BN><<<grid, 256, C::SMEM_BYTES, stream>>>(tmA, tmB, k);
+  gemm_tc_kernel<BN, EPI_CT><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, k);
   if (prof) {
     cudaEventRecord(g_ev1[g_prof_n], stream);
     g_prof_flops[g_prof_n] = 2.0 * k.M * (double)k.N * (double)k.num_kb * BK * k.batch_z;
+    int* mt = g_prof_meta[g_prof_n];
+    mt[0] = k.M, mt[1] = k.N, mt[2] = k.num_kb * BK, mt[3] = k.a_mode, mt[4] = k.b_mode, mt[5] = k.epi;
+    mt[6] = k.splits * 1000 + k.batch_z, mt[7] = BN;
     ++g_prof_n;
   }
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   return THEIA_OK;
+}
+
+// hot epilogue combinations get a compile-time specialisation; anything else runs the generic kernel
+template <int BN>
+static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k, cudaStream_t stream) {
+  switch (k.epi) {
+#define THEIA_EPI_CASE(E) \
+  case (E):               \
+    return launch<BN, (E)>(tmA, tmB, k, stream);
+    THEIA_EPI_CASE(0)
+    THEIA_EPI_CASE(THEIA_EPI_GELU)
+    THEIA_EPI_CASE(THEIA_EPI_RESID)
+    THEIA_EPI_CASE(THEIA_EPI_OUT_F32)
+    THEIA_EPI_CASE(THEIA_EPI_ATOMIC)
+    THEIA_EPI_CASE(THEIA_EPI_MUL_DGELU)
+    THEIA_EPI_CASE(THEIA_EPI_MUL_DGELU | THEIA_EPI_COLSUM)
+    THEIA_EPI_CASE(THEIA_EPI_POSCLS)
+    THEIA_EPI_CASE(THEIA_EPI_STATS)
+    THEIA_EPI_CASE(THEIA_EPI_RELU | THEIA_EPI_STATS)
+#undef THEIA_EPI_CASE
+    default:
+      return launch<BN, -1>(tmA, tmB, k, stream);
+  }
 }
 
 }  // namespace theia
@@ -421,6 +508,17 @@ extern "C" int theia_prof_enable(int on) {
   }
   g_prof_on = on != 0;
   if (on) g_prof_n = 0;
+  return THEIA_OK;
+}
+
+// Per-launch record i of the current ring: ms, M, N, K, a_mode, b_mode, epi, splits*1000+batch_z, BN
+extern "C" int theia_prof_record(int i, double* ms, int* meta8) {
+  if (i < 0 || i >= g_prof_n) return THEIA_ERR_ARG;
+  cudaEventSynchronize(g_ev1[i]);
+  float t = 0.f;
+  if (cudaEventElapsedTime(&t, g_ev0[i], g_ev1[i]) != cudaSuccess) return set_error(THEIA_ERR_CUDA, "elapsed");
+  *ms = t;
+  for (int k = 0; k < 8; ++k) meta8[k] = g_prof_meta[i][k];
   return THEIA_OK;
 }
 
@@ -472,6 +570,7 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   k.cls = d->cls;
   k.tokens = d->tokens > 0 ? d->tokens : 1;
   k.stats = d->stats;
+  k.colsum = d->colsum;
   k.out_z_stride = d->out_z_stride;
   k.batch_z = d->batch_z > 0 ? d->batch_z : 1;
   k.splits = d->splits > 0 ? d->splits : 1;
@@ -480,6 +579,7 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   if ((d->epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK)) && !d->aux)
     return set_error(THEIA_ERR_ARG, "epilogue needs aux");
   if ((d->epi & THEIA_EPI_POSCLS) && (!d->pos || !d->cls)) return set_error(THEIA_ERR_ARG, "POSCLS needs pos/cls");
+  if ((d->epi & THEIA_EPI_COLSUM) && !d->colsum) return set_error(THEIA_ERR_ARG, "COLSUM needs colsum");
   if ((d->epi & THEIA_EPI_STATS) && (!d->stats || d->a_mode != THEIA_OP_CONV_K))
     return set_error(THEIA_ERR_ARG, "STATS needs stats and a CONV_K A operand");
 
@@ -560,7 +660,7 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   if (g_dbg[5]) k.a_kstep = (uint32_t)g_dbg[5];
   if (g_dbg[6]) k.b_kstep = (uint32_t)g_dbg[6];
 
-  if (bn == 128) return launch<128>(tmA, tmB, k, stream);
-  if (bn == 192) return launch<192>(tmA, tmB, k, stream);
-  return launch<256>(tmA, tmB, k, stream);
+  if (bn == 128) return dispatch<128>(tmA, tmB, k, stream);
+  if (bn == 192) return dispatch<192>(tmA, tmB, k, stream);
+  return dispatch<256>(tmA, tmB, k, stream);
 }

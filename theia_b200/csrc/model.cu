@@ -300,6 +300,41 @@ extern "C" int theia_model_param_info(const theia_model* m, int i, char* name, i
   *offset = p.off;
   return THEIA_OK;
 }
+// Bring-up / test accessor: device pointer of a named internal activation (layer or head index i).
+extern "C" int theia_model_debug_ptr(theia_model* m, const char* name, int i, void** ptr, long long* elems,
+                                     int* is_f32) {
+  if (!m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
+  const std::string n(name);
+  const long long M = static_cast<long long>(m->last_B) * 197, P = static_cast<long long>(m->last_B) * 256;
+  const int D = m->D;
+  auto AB = [&](long long off) { return static_cast<void*>(reinterpret_cast<bf16*>(m->ws + m->o_actbf) + off); };
+  *is_f32 = 0;
+  if (n == "patches") { *ptr = AB(m->patches); *elems = M * 768; return 0; }
+  if (n == "tokens") { *ptr = AB(m->tokens); *elems = M * D; return 0; }
+  if (n == "dtok") { *ptr = AB(m->dtok); *elems = M * D; return 0; }
+  if (n == "x") { if (i < 0 || i > m->L) return THEIA_ERR_ARG; *ptr = AB(m->x[i]); *elems = M * D; return 0; }
+  if (i >= 0 && i < m->L) {
+    const LayerA& a = m->la[i];
+    if (n == "ln1") { *ptr = AB(a.ln1); *elems = M * D; return 0; }
+    if (n == "qkv") { *ptr = AB(a.qkv); *elems = M * 3 * D; return 0; }
+    if (n == "attn") { *ptr = AB(a.attn); *elems = M * D; return 0; }
+    if (n == "xmid") { *ptr = AB(a.xmid); *elems = M * D; return 0; }
+    if (n == "ln2") { *ptr = AB(a.ln2); *elems = M * D; return 0; }
+    if (n == "h") { *ptr = AB(a.h); *elems = M * 4 * D; return 0; }
+    if (n == "a") { *ptr = AB(a.a); *elems = M * 4 * D; return 0; }
+  }
+  if (i >= 0 && i < m->T) {
+    const HeadA& a = m->ha[i];
+    if (n == "padout") { *ptr = AB(a.padout); *elems = P * D; return 0; }
+    if (n == "hln0") { *ptr = AB(a.ln0); *elems = P * D; return 0; }
+    if (n == "c1") { *ptr = AB(a.c1); *elems = P * D; return 0; }
+    if (n == "hln1") { *ptr = AB(a.ln1); *elems = P * D; return 0; }
+    if (n == "c2") { *ptr = AB(a.c2); *elems = P * D; return 0; }
+    if (n == "hln2") { *ptr = AB(a.ln2); *elems = P * D; return 0; }
+  }
+  return set_error(THEIA_ERR_ARG, "unknown activation %s[%d]", name, i);
+}
+
 extern "C" int theia_model_bind(theia_model* m, float* master, float* grads, void* workspace) {
   if (!master || !workspace) return set_error(THEIA_ERR_ARG, "bind: null");
   m->master = master;
@@ -340,10 +375,10 @@ theia_gemm_desc gemm_base(int M, int N, int K) {
 
 // y[M,N] = x[M,K] * w[N,K]^T (+bias) with epilogue flags
 int linear(const Ctx& c, const bf16* x, const bf16* w, const float* bias, void* out, int M, int N, int K, int epi,
-           const void* aux = nullptr, void* out2 = nullptr) {
+           const void* aux = nullptr, void* out2 = nullptr, float* colsum = nullptr) {
   theia_gemm_desc d = gemm_base(M, N, K);
   d.A = x, d.lda = K, d.B = w, d.ldb = K;
-  d.out = out, d.ldo = N, d.bias = bias, d.epi = epi, d.aux = aux, d.out2 = out2;
+  d.out = out, d.ldo = N, d.bias = bias, d.epi = epi, d.aux = aux, d.out2 = out2, d.colsum = colsum;
   return theia_gemm(&d, c.s);
 }
 
@@ -460,8 +495,8 @@ extern "C" int theia_model_pack(theia_model* m, void* stream) {
 // images uint8 [B,224,224,3] (or [B,3,224,224]) -> tokens (bf16, workspace) and, when
 // run_heads, preds[t] fp32 [B,256,C_t] (caller-owned).  tokens_f32 (optional) receives the
 // final-LayerNorm output [B,197,D] in fp32 for forward_feature().
-extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channels_first, int do_rescale,
-                                   int do_normalize, const float* mean3, const float* std3, int run_heads,
+extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channels_first, int do_resize,
+                                   int do_rescale, int do_normalize, const float* mean3, const float* std3, int run_heads,
                                    float* const* preds, void* tokens_bf16_out, void* stream) {
   if (!m->master || !m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
   if (B < 1 || B > m->Bmax) return set_error(THEIA_ERR_ARG, "batch %d outside [1,%d]", B, m->Bmax);
@@ -469,7 +504,8 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
   const int D = m->D, C = m->D, H = m->H, L = m->L;
   const int M = B * 197, P = B * 256;
   m->last_B = B;
-  TRY(theia_preprocess(images, c.AB(m->patches), B, channels_first, do_rescale, do_normalize, mean3, std3, c.s));
+  TRY(theia_preprocess(images, c.AB(m->patches), B, channels_first, do_resize, do_rescale, do_normalize, mean3, std3,
+                       c.s));
   {  // patch embedding + CLS + position embeddings (hf:modeling_vit.py:100-128,153-168)
     theia_gemm_desc d = gemm_base(M, D, 768);
     d.A = c.AB(m->patches), d.lda = 768, d.B = c.PB(m->wpe), d.ldb = 768;
@@ -592,31 +628,31 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
   // final LayerNorm
   bf16* dx = c.AB(m->dx0);
   bf16* dx2 = c.AB(m->dx1);
+  // column sums of each produced dx are the bias gradients of the Linear that produced that residual
+  // stream value (fc2 / attention out-proj / patch projection): fused into the LayerNorm backward
   TRY(theia_layernorm_bwd(c.AB(m->dtok), c.AB(m->x[L]), c.W(m->lnfw), c.AF(m->meanf), c.AF(m->rstdf), nullptr, dx,
-                          c.G(m->lnfw), c.G(m->lnfb), M, D, c.s));
+                          c.G(m->lnfw), c.G(m->lnfb), c.G(m->lp[L - 1].f2b), M, D, c.s));
   for (int l = L - 1; l >= 0; --l) {
     const LayerP& p = m->lp[l];
     const LayerW& w = m->lw[l];
     const LayerA& a = m->la[l];
     // MLP
     TRY(wgrad(c, dx, c.AB(a.a), c.G(p.f2w), M, D, 4 * D));
-    TRY(theia_colsum(dx, c.G(p.f2b), M, D, D, 0, c.s));
-    TRY(linear(c, dx, c.PB(w.w2T), nullptr, c.AB(m->dh), M, 4 * D, D, THEIA_EPI_MUL_DGELU, c.AB(a.h)));
+    TRY(linear(c, dx, c.PB(w.w2T), nullptr, c.AB(m->dh), M, 4 * D, D, THEIA_EPI_MUL_DGELU | THEIA_EPI_COLSUM,
+               c.AB(a.h), nullptr, c.G(p.f1b)));
     TRY(wgrad(c, c.AB(m->dh), c.AB(a.ln2), c.G(p.f1w), M, 4 * D, D));
-    TRY(theia_colsum(c.AB(m->dh), c.G(p.f1b), M, 4 * D, 4 * D, 0, c.s));
     TRY(linear(c, c.AB(m->dh), c.PB(w.w1T), nullptr, c.AB(m->dln), M, D, 4 * D, 0));
     TRY(theia_layernorm_bwd(c.AB(m->dln), c.AB(a.xmid), c.W(p.ln2w), c.AF(a.mean2), c.AF(a.rstd2), dx, dx2,
-                            c.G(p.ln2w), c.G(p.ln2b), M, D, c.s));
+                            c.G(p.ln2w), c.G(p.ln2b), c.G(p.ob), M, D, c.s));
     // attention
     TRY(wgrad(c, dx2, c.AB(a.attn), c.G(p.ow), M, D, D));
-    TRY(theia_colsum(dx2, c.G(p.ob), M, D, D, 0, c.s));
     TRY(linear(c, dx2, c.PB(w.woT), nullptr, c.AB(m->dattn), M, D, D, 0));
     TRY(theia_attention_bwd(c.AB(a.qkv), c.AB(a.attn), c.AB(m->dattn), c.AF(a.lse), c.AB(m->dqkv), B, 197, H, c.s));
     TRY(wgrad(c, c.AB(m->dqkv), c.AB(a.ln1), c.G(p.qw), M, 3 * D, D));
     TRY(theia_colsum(c.AB(m->dqkv), c.G(p.qb), M, 3 * D, 3 * D, 0, c.s));
     TRY(linear(c, c.AB(m->dqkv), c.PB(w.wqkvT), nullptr, c.AB(m->dln), M, D, 3 * D, 0));
     TRY(theia_layernorm_bwd(c.AB(m->dln), c.AB(m->x[l]), c.W(p.ln1w), c.AF(a.mean1), c.AF(a.rstd1), dx2, dx,
-                            c.G(p.ln1w), c.G(p.ln1b), M, D, c.s));
+                            c.G(p.ln1w), c.G(p.ln1b), l > 0 ? c.G(m->lp[l - 1].f2b) : nullptr, M, D, c.s));
   }
   // embeddings: position / cls / patch projection
   TRY(theia_batchsum(dx, c.G(m->pos), B, 197 * D, c.s));

@@ -324,8 +324,6 @@ class RobotVisionFM(nn.Module):
             raise NotImplementedError("theia_b200 takes uint8 images in [0,255] (the reference's training input)")
         chw = 1 if (x.shape[1] in (1, 3) and x.shape[-1] not in (1, 3)) else 0
         H, W = (x.shape[2], x.shape[3]) if chw else (x.shape[1], x.shape[2])
-        if do_resize:
-            raise NotImplementedError("do_resize=True (bicubic 256 + centre crop) is not built yet: pass do_resize=False")
         if H != 224 or W != 224:
             raise ValueError(f"Input image size ({H}*{W}) doesn't match model (224*224).")  # hf:modeling_vit.py:160-165
         return x.to(self._flat.device, non_blocking=True).contiguous(), chw
@@ -349,7 +347,7 @@ class RobotVisionFM(nn.Module):
                     ptrs[i] = p.data_ptr()
         self._fwd_id += 1
         L.check(L.lib().theia_model_forward(
-            self._handle, images.data_ptr(), B, chw, int(kw.get("do_rescale", True)),
+            self._handle, images.data_ptr(), B, chw, int(bool(do_resize)), int(kw.get("do_rescale", True)),
             int(kw.get("do_normalize", True)), mean, std, int(run_heads), ptrs,
             0 if tokens_out is None else tokens_out.data_ptr(), L.stream_ptr()), "theia_model_forward")
         self._last_B = B
