@@ -59,13 +59,18 @@ constexpr int NTHREADS = 128 + EPI_WARPS * 32;
 constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;
 constexpr int SMEM_LIMIT = 232448;  // 227 KB
 
-template <int BN>
+constexpr int AUX_SLOTS = 3;                                  // per-warp ring depth (32x32 bf16 chunks)
+constexpr int AUX_RING_BYTES = EPI_WARPS * AUX_SLOTS * 2048;  // 48 KB
+constexpr int AUXF = THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK;
+
+template <int BN, bool RING>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (SMEM_LIMIT - STAGING_BYTES - 1024 - 256) / STAGE_BYTES;
+  static constexpr int EXTRA = STAGING_BYTES + (RING ? AUX_RING_BYTES : 0);
+  static constexpr int STAGES = (SMEM_LIMIT - EXTRA - 1024 - 256) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EXTRA + 256 + 1024;
 };
 
 struct Item {
@@ -85,40 +90,55 @@ __device__ __forceinline__ Item decode_item(const GemmK& p, int item) {
   return it;
 }
 
-// A&S 7.1.26 erf (|err| <= 1.5e-7) sharing one exp with the Gaussian pdf: the exact-erf GELU and its
-// derivative at ~12 instructions per element instead of erff()+expf().
-__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
-  const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  const float e = __expf(-ax * ax);
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erfa = 1.0f - poly * t * e;  // erf(|x|/sqrt2)
-  cdf = 0.5f * (1.0f + copysignf(erfa, x));
-  pdf = 0.39894228040143268f * e;
+// Exact-erf GELU pieces from Abramowitz-Stegun 7.1.26 (|erf err| <= 1.5e-7): one MUFU.RCP, one MUFU.EX2
+// (shared with the Gaussian pdf) and five FMAs -- ~15 instructions per element instead of erff()+expf().
+// SoA helpers over small register arrays so the compiler interleaves the independent dependency chains
+// (the epilogue runs with only two warps per scheduler: ILP has to hide the fixed-latency stalls).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
-__device__ __forceinline__ float gelu_fast(float x) {
-  float c, d;
-  gelu_parts(x, c, d);
-  return x * c;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
-__device__ __forceinline__ float dgelu_fast(float x) {
-  float c, d;
-  gelu_parts(x, c, d);
-  return fmaf(x, d, c);
+template <int NV, bool WANT_PDF>
+__device__ __forceinline__ void normal_cdf_pdf(const float (&x)[NV], float (&cdf)[NV], float (&pdf)[NV]) {
+  float t[NV], e[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const float ax = fabsf(x[k]);
+    t[k] = rcp_approx(fmaf(ax, 0.3275911f * 0.70710678118654752f, 1.0f));
+    const float u = ax * 0.84932180028801907f;  // sqrt(log2(e) / 2)
+    e[k] = ex2_approx(-(u * u));                // exp(-x^2 / 2)
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    float pl = fmaf(t[k], 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+    pl = fmaf(pl, t[k], 0.5f * 1.421413741f);
+    pl = fmaf(pl, t[k], 0.5f * -0.284496736f);
+    pl = fmaf(pl, t[k], 0.5f * 0.254829592f);
+    const float hq = pl * t[k] * e[k];  // 0.5 * erfc(|x| / sqrt 2)
+    cdf[k] = 0.5f + copysignf(0.5f - hq, x[k]);
+    if (WANT_PDF) pdf[k] = 0.39894228040143268f * e[k];
+  }
 }
 
 // EPI_CT >= 0: epilogue flags are a compile-time constant (hot combinations); -1: read p.epi.
 template <int BN, int EPI_CT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmK p) {
-  using C = Cfg<BN>;
+  // compile-time specialised kernels that read an aux operand stage it through a cp.async ring in shared
+  // memory (48 KB in flight per SM: registers alone cannot keep enough HBM reads outstanding)
+  constexpr bool RING = (EPI_CT >= 0) && ((EPI_CT & AUXF) != 0);
+  using C = Cfg<BN, RING>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* staging_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + STAGING_BYTES);
+  uint8_t* aux_ring_all = smem + C::STAGES * C::STAGE_BYTES + STAGING_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EXTRA);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
   uint64_t* tfull = bars + 2 * C::STAGES;
@@ -242,6 +262,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int c = lane & 7;
     const int rsub = lane >> 3;
     constexpr int NCHUNK = BN / 32;
+    // ---- aux ring (RING kernels): chunk q of this warp lives in slot q % AUX_SLOTS; the prefetch cursor
+    // (pitem, pch) runs AUX_SLOTS chunks ahead of the processing position, across tile boundaries ----
+    uint8_t* ring = aux_ring_all + ew * (AUX_SLOTS * 2048);
+    int pitem = blockIdx.x, pch = hsel, slot = 0;
+    auto ring_issue = [&](int sl) {
+      if (pitem < p.total_items) {
+        const Item pit = decode_item(p, pitem);
+        const int nn = pit.n_blk * BN + pch * 32 + c * 4;
+        const int pimg = p.conv_out ? pit.m_blk / p.tiles_per_img : 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = wq * 32 + i * 4 + rsub;
+          long long orow;
+          bool okr;
+          if (p.conv_out) {
+            const int ht = pit.m_blk - pimg * p.tiles_per_img;
+            const int hh = r / p.tile_w, ww = r - hh * p.tile_w;
+            const int h = ht * p.tile_h + hh;
+            okr = (h < p.out_h) && (ww < p.out_w);
+            orow = static_cast<long long>(pimg) * p.out_img_rows + p.out_row_off +
+                   static_cast<long long>(h * p.sy + p.py) * p.out_wpitch + (ww * p.sx + p.px);
+          } else {
+            orow = pit.m_blk * BM + r;
+            okr = orow < p.M;
+          }
+          const uint32_t dst = smem_u32(ring + sl * 2048 + (i * 32 + lane) * 8);
+          if (okr && nn < p.N) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p.aux + orow * p.ldo + nn)
+                         : "memory");
+          } else {
+            asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(dst), "r"(0u) : "memory");
+          }
+        }
+        pch += 2;
+        if (pch >= NCHUNK) {
+          pch = hsel;
+          pitem += gridDim.x;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (RING) {
+#pragma unroll
+      for (int sidx = 0; sidx < AUX_SLOTS; ++sidx) ring_issue(sidx);
+    }
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const Item it = decode_item(p, item);
       // ---- per-tile row bookkeeping: this lane touches rows rr = 4*i + rsub of its warp's slab ----
@@ -276,11 +341,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int ch = hsel; ch < NCHUNK; ch += 2) {
         const bool last = (ch + 2 >= NCHUNK);
         const int nbase = it.n_blk * BN + ch * 32;
+        if (RING) asm volatile("cp.async.wait_group %0;" ::"n"(AUX_SLOTS - 1) : "memory");  // this chunk's aux landed
         if (nbase >= p.N) {  // nothing to store; still release the accumulator
           if (last) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          if (RING) {
+            ring_issue(slot);
+            slot = (slot + 1 == AUX_SLOTS) ? 0 : slot + 1;
           }
           continue;
         }
@@ -306,77 +376,122 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         __syncwarp();
-        // phase 2: 4 rows x 128 B per warp instruction, coalesced global access
+        // phase 2: 4 rows x 128 B per warp instruction, coalesced global access; two passes of 4 rows
+        // (16 values per lane) so the per-element math runs as 16 interleaved chains
         const int n = nbase + c * 4;
         const uint32_t ok = (n < p.N) ? okmask : 0u;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias != nullptr && ok) bias4 = *reinterpret_cast<const float4*>(p.bias + n);
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
         uint2 aux[8];
-        if (epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK)) {
+        if (RING) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) aux[i] = *reinterpret_cast<const uint2*>(ring + slot * 2048 + (i * 32 + lane) * 8);
+        } else if (epi & AUXF) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             aux[i] = ((ok >> i) & 1u) ? *reinterpret_cast<const uint2*>(p.aux + rowoff[i] + n) : make_uint2(0u, 0u);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + rsub;
-          const float4 f = reinterpret_cast<const float4*>(stg + rr * 32)[c ^ (rr & 7)];
-          if (!((ok >> i) & 1u)) continue;
-          const long long off = rowoff[i] + n;
-          float x0 = f.x + bias4.x, x1 = f.y + bias4.y, x2 = f.z + bias4.z, x3 = f.w + bias4.w;
+        for (int half = 0; half < 2; ++half) {
+          float xv[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = (half * 4 + j) * 4 + rsub;
+            const float4 f = reinterpret_cast<const float4*>(stg + rr * 32)[c ^ (rr & 7)];
+            xv[4 * j + 0] = f.x + bias4.x, xv[4 * j + 1] = f.y + bias4.y;
+            xv[4 * j + 2] = f.z + bias4.z, xv[4 * j + 3] = f.w + bias4.w;
+          }
           if (epi & THEIA_EPI_POSCLS) {
-            const int m = it.m_blk * BM + wq * 32 + rr;
-            const int t = m % p.tokens;
-            const float4 ps = *reinterpret_cast<const float4*>(p.pos + static_cast<long long>(t) * p.N + n);
-            if (t == 0) {
-              const float4 cl = *reinterpret_cast<const float4*>(p.cls + n);
-              x0 = cl.x + ps.x, x1 = cl.y + ps.y, x2 = cl.z + ps.z, x3 = cl.w + ps.w;
-            } else {
-              x0 += ps.x, x1 += ps.y, x2 += ps.z, x3 += ps.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = half * 4 + j;
+              if (!((ok >> i) & 1u)) continue;
+              const int m = it.m_blk * BM + wq * 32 + i * 4 + rsub;
+              const int t = m % p.tokens;
+              const float4 ps = *reinterpret_cast<const float4*>(p.pos + static_cast<long long>(t) * p.N + n);
+              if (t == 0) {
+                const float4 cl = *reinterpret_cast<const float4*>(p.cls + n);
+                xv[4 * j + 0] = cl.x + ps.x, xv[4 * j + 1] = cl.y + ps.y;
+                xv[4 * j + 2] = cl.z + ps.z, xv[4 * j + 3] = cl.w + ps.w;
+              } else {
+                xv[4 * j + 0] += ps.x, xv[4 * j + 1] += ps.y, xv[4 * j + 2] += ps.z, xv[4 * j + 3] += ps.w;
+              }
             }
           }
           if (epi & THEIA_EPI_GELU) {
-            uint2 pre;
-            pre.x = pack_bf16x2(x0, x1);
-            pre.y = pack_bf16x2(x2, x3);
-            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + off) = pre;
-            x0 = gelu_fast(x0), x1 = gelu_fast(x1), x2 = gelu_fast(x2), x3 = gelu_fast(x3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int i = half * 4 + j;
+              uint2 pre;
+              pre.x = pack_bf16x2(xv[4 * j + 0], xv[4 * j + 1]);
+              pre.y = pack_bf16x2(xv[4 * j + 2], xv[4 * j + 3]);
+              if ((ok >> i) & 1u) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + rowoff[i] + n) = pre;
+            }
+            float cdf[16], pdf[16];
+            normal_cdf_pdf<16, false>(xv, cdf, pdf);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) xv[k] *= cdf[k];
           }
           if (epi & THEIA_EPI_RELU) {
-            x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f), x2 = fmaxf(x2, 0.f), x3 = fmaxf(x3, 0.f);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) xv[k] = fmaxf(xv[k], 0.f);
           }
-          if (epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK)) {
-            const float2 a01 = unpack_bf16x2(aux[i].x), a23 = unpack_bf16x2(aux[i].y);
+          if (epi & AUXF) {
+            float av[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a01 = unpack_bf16x2(aux[half * 4 + j].x), a23 = unpack_bf16x2(aux[half * 4 + j].y);
+              av[4 * j + 0] = a01.x, av[4 * j + 1] = a01.y, av[4 * j + 2] = a23.x, av[4 * j + 3] = a23.y;
+            }
             if (epi & THEIA_EPI_MUL_DGELU) {
-              x0 *= dgelu_fast(a01.x), x1 *= dgelu_fast(a01.y), x2 *= dgelu_fast(a23.x), x3 *= dgelu_fast(a23.y);
+              float cdf[16], pdf[16];
+              normal_cdf_pdf<16, true>(av, cdf, pdf);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) xv[k] *= fmaf(av[k], pdf[k], cdf[k]);
             } else if (epi & THEIA_EPI_MUL_RELUMASK) {
-              x0 = a01.x > 0.f ? x0 : 0.f, x1 = a01.y > 0.f ? x1 : 0.f;
-              x2 = a23.x > 0.f ? x2 : 0.f, x3 = a23.y > 0.f ? x3 : 0.f;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) xv[k] = av[k] > 0.f ? xv[k] : 0.f;
             } else {
-              x0 += a01.x, x1 += a01.y, x2 += a23.x, x3 += a23.y;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) xv[k] += av[k];
             }
           }
-          if (epi & THEIA_EPI_ATOMIC) {
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(it.z) * p.out_z_stride + off;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(x0), "f"(x1), "f"(x2), "f"(x3)
-                         : "memory");
-          } else if (epi & THEIA_EPI_OUT_F32) {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(x0, x1, x2, x3);
-          } else {
-            uint2 o;
-            o.x = pack_bf16x2(x0, x1);
-            o.y = pack_bf16x2(x2, x3);
-            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + off) = o;
-            if (epi & (THEIA_EPI_STATS | THEIA_EPI_COLSUM)) {
-              const float2 q01 = unpack_bf16x2(o.x), q23 = unpack_bf16x2(o.y);
-              if (epi & THEIA_EPI_STATS) {
-                st_s += (q01.x + q01.y) + (q23.x + q23.y);
-                st_ss += (q01.x * q01.x + q01.y * q01.y) + (q23.x * q23.x + q23.y * q23.y);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = half * 4 + j;
+            const bool rok = (ok >> i) & 1u;
+            const long long off = rowoff[i] + n;
+            const float x0 = xv[4 * j + 0], x1 = xv[4 * j + 1], x2 = xv[4 * j + 2], x3 = xv[4 * j + 3];
+            if (epi & THEIA_EPI_ATOMIC) {
+              float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(it.z) * p.out_z_stride + off;
+              if (rok)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(x0), "f"(x1), "f"(x2),
+                             "f"(x3)
+                             : "memory");
+            } else if (epi & THEIA_EPI_OUT_F32) {
+              if (rok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(x0, x1, x2, x3);
+            } else {
+              uint2 o;
+              o.x = pack_bf16x2(x0, x1);
+              o.y = pack_bf16x2(x2, x3);
+              if (rok) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + off) = o;
+              if (epi & (THEIA_EPI_STATS | THEIA_EPI_COLSUM)) {
+                const float msk = rok ? 1.f : 0.f;
+                const float2 q01 = unpack_bf16x2(o.x), q23 = unpack_bf16x2(o.y);
+                if (epi & THEIA_EPI_STATS) {
+                  st_s += msk * ((q01.x + q01.y) + (q23.x + q23.y));
+                  st_ss += msk * ((q01.x * q01.x + q01.y * q01.y) + (q23.x * q23.x + q23.y * q23.y));
+                }
+                if (epi & THEIA_EPI_COLSUM)
+                  cs0 += msk * q01.x, cs1 += msk * q01.y, cs2 += msk * q23.x, cs3 += msk * q23.y;
               }
-              if (epi & THEIA_EPI_COLSUM) cs0 += q01.x, cs1 += q01.y, cs2 += q23.x, cs3 += q23.y;
             }
           }
+        }
+        if (RING) {  // aux of this chunk is consumed: refill the slot with the chunk AUX_SLOTS ahead
+          ring_issue(slot);
+          slot = (slot + 1 == AUX_SLOTS) ? 0 : slot + 1;
         }
         if (epi & THEIA_EPI_COLSUM) {  // column sums of the stored tile rows (bias gradient of the consumer)
           cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8), cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
@@ -401,6 +516,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (RING) asm volatile("cp.async.wait_all;" ::: "memory");
   }
 
   tc_fence_before();
@@ -435,7 +551,7 @@ static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
 
 template <int BN, int EPI_CT>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, (EPI_CT >= 0) && ((EPI_CT & AUXF) != 0)>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
