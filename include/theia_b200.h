@@ -130,6 +130,10 @@ int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_f
 int theia_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream);
 int theia_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N,
                         int H, void* stream);
+/* tcgen05 version (S / dP accumulators in TMEM, TMA-fed, persistent): same contract */
+int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream);
+int theia_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B,
+                           int N, int H, void* stream);
 /* parameter packing helpers */
 int theia_gather4(const void* in, void* out, int in_is_f32, int out_is_f32, int n0, int n1, int n2, int n3,
                   long long s0, long long s1, long long s2, long long s3, long long base, void* stream);

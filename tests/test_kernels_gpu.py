@@ -355,14 +355,16 @@ def test_preprocess_with_bicubic_resize(lib, chw):
 
 
 # ----------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("Bn,H", [(2, 3), (3, 12)])
-def test_attention_fwd_bwd(lib, Bn, H):
+@pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
+@pytest.mark.parametrize("Bn,H", [(2, 3), (3, 12), (40, 6)])
+def test_attention_fwd_bwd(lib, Bn, H, impl):
     N, D = 197, H * 64
     qkv = rnd(Bn * N, 3 * D, seed=1, scale=1.5)
     do = rnd(Bn * N, D, seed=2)
-    out = torch.empty(Bn * N, D, dtype=torch.bfloat16, device=DEV)
+    out = torch.full((Bn * N, D), float("nan"), dtype=torch.bfloat16, device=DEV)
     lse = torch.empty(Bn, H, N, device=DEV)
-    L.check(lib.theia_attention_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), Bn, N, H, S()))
+    fwd = lib.theia_attention_fwd if impl == "mma_sync" else lib.theia_attention_tc_fwd
+    L.check(fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), Bn, N, H, S()))
     x = qkv.float().view(Bn, N, 3, H, 64).requires_grad_(True)
     q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
     s = (q @ k.transpose(2, 3)) * 0.125
@@ -370,9 +372,9 @@ def test_attention_fwd_bwd(lib, Bn, H):
     assert relerr(out.float(), ref) < 8e-3
     torch.testing.assert_close(lse, torch.logsumexp(s, -1).detach(), rtol=1e-4, atol=1e-4)
     ref.backward(do.float())
-    dqkv = torch.zeros_like(qkv)
-    L.check(lib.theia_attention_bwd(qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), Bn,
-                                    N, H, S()))
+    dqkv = torch.full_like(qkv, float("nan"))
+    bwd = lib.theia_attention_bwd if impl == "mma_sync" else lib.theia_attention_tc_bwd
+    L.check(bwd(qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), Bn, N, H, S()))
     g = x.grad.view(Bn * N, 3, D)
     got = dqkv.float().view(Bn * N, 3, D)
     for i, nm in enumerate("qkv"):

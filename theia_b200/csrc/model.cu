@@ -520,7 +520,7 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
     TRY(theia_layernorm_fwd(c.AB(m->x[l]), c.W(p.ln1w), c.W(p.ln1b), c.AB(a.ln1), c.AF(a.mean1), c.AF(a.rstd1), M, D,
                             m->cfg.ln_eps, c.s));
     TRY(linear(c, c.AB(a.ln1), c.PB(w.wqkv), c.W(p.qb), c.AB(a.qkv), M, 3 * D, D, 0));
-    TRY(theia_attention_fwd(c.AB(a.qkv), c.AB(a.attn), c.AF(a.lse), B, 197, H, c.s));
+    TRY(theia_attention_tc_fwd(c.AB(a.qkv), c.AB(a.attn), c.AF(a.lse), B, 197, H, c.s));
     TRY(linear(c, c.AB(a.attn), c.PB(w.wo), c.W(p.ob), c.AB(a.xmid), M, D, D, THEIA_EPI_RESID, c.AB(m->x[l])));
     TRY(theia_layernorm_fwd(c.AB(a.xmid), c.W(p.ln2w), c.W(p.ln2b), c.AB(a.ln2), c.AF(a.mean2), c.AF(a.rstd2), M, D,
                             m->cfg.ln_eps, c.s));
@@ -647,7 +647,7 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     // attention
     TRY(wgrad(c, dx2, c.AB(a.attn), c.G(p.ow), M, D, D));
     TRY(linear(c, dx2, c.PB(w.woT), nullptr, c.AB(m->dattn), M, D, D, 0));
-    TRY(theia_attention_bwd(c.AB(a.qkv), c.AB(a.attn), c.AB(m->dattn), c.AF(a.lse), c.AB(m->dqkv), B, 197, H, c.s));
+    TRY(theia_attention_tc_bwd(c.AB(a.qkv), c.AB(a.attn), c.AB(m->dattn), c.AF(a.lse), c.AB(m->dqkv), B, 197, H, c.s));
     TRY(wgrad(c, c.AB(m->dqkv), c.AB(a.ln1), c.G(p.qw), M, 3 * D, D));
     TRY(theia_colsum(c.AB(m->dqkv), c.G(p.qb), M, 3 * D, 3 * D, 0, c.s));
     TRY(linear(c, c.AB(m->dqkv), c.PB(w.wqkvT), nullptr, c.AB(m->dln), M, D, 3 * D, 0));
