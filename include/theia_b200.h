@@ -67,6 +67,11 @@ typedef struct theia_conv_geom {
   int out_h, out_w;                       /* valid output extent (rows with h>=out_h or w>=out_w are not stored) */
   /* output row of pixel (b,h,w) = b*out_img_rows + out_row_off + (h*sy+py)*out_wpitch + (w*sx+px) */
   int out_img_rows, out_row_off, out_wpitch, sy, sx, py, px;
+  int in_stride;    /* gather stride of the NHWC operand (1, or 2 for the dgrad / wgrad of a stride-2 transposed
+                       conv): input pixel = in_stride * output pixel + (dh, dw), via TMA element strides     */
+  int b_tap_rows;   /* CONV_K: 0 = B is [N][ntaps*C]; >0 = B is tap-major [tap][b_tap_rows][C] and wtap[t] selects
+                       the weight tap of GEMM tap t (one 9-tap pack serves all parity classes)                  */
+  int wtap[9];
 } theia_conv_geom;
 
 typedef struct theia_gemm_desc {

@@ -406,3 +406,83 @@ def test_pack_and_reductions(lib):
     xb = rnd(7, 197 * 64, seed=5)
     L.check(lib.theia_batchsum(xb.data_ptr(), bs.data_ptr(), 7, 197 * 64, S()))
     assert relerr(bs, xb.float().sum(0)) < 1e-5
+
+
+# ----------------------------------------------------------------------------- stride-2 transposed convs (64x64 heads)
+def _classes(p):
+    """output parity -> list of (kh, dh) with input index = sub-grid index + dh (kernel 3, stride 2, padding p)"""
+    return {par: [(kh, (par + p - kh) // 2) for kh in range(3) if (par + p - kh) % 2 == 0] for par in (0, 1)}
+
+
+def _convt_geom(Cc, Bn, Hin, pitch_in, tile_w, tile_h, sub_h, sub_w, Hout_pitch, py, px, taps):
+    g = L.ConvGeom()
+    g.C, g.H, g.W, g.B = Cc, Hin, Hin, Bn
+    g.stride_w, g.stride_h, g.stride_b = Cc, pitch_in * Cc, pitch_in * pitch_in * Cc
+    g.ntaps = len(taps)
+    for t, (wt_idx, dh, dw) in enumerate(taps):
+        g.dh[t], g.dw[t], g.wtap[t] = dh, dw, wt_idx
+    g.tile_w, g.tile_h = tile_w, tile_h
+    g.out_h, g.out_w = sub_h, sub_w
+    g.out_img_rows, g.out_row_off, g.out_wpitch = Hout_pitch * Hout_pitch, 0, Hout_pitch
+    g.sy = g.sx = 2
+    g.py, g.px = py, px
+    g.in_stride = 1
+    g.b_tap_rows = Cc
+    return g
+
+
+@pytest.mark.parametrize("which", ["t1_16to31", "t2_31to64"])
+def test_convtranspose_stride2_fwd_dgrad_wgrad(lib, which):
+    Cc, Bn = 128, 2
+    if which == "t1_16to31":
+        Hin, pin, Hout, pout, pad, opad, tw, th = 16, 16, 31, 32, 1, 0, 16, 8
+    else:
+        Hin, pin, Hout, pout, pad, opad, tw, th = 31, 32, 64, 64, 0, 1, 32, 4
+    xin = torch.zeros(Bn, pin, pin, Cc, dtype=torch.bfloat16, device=DEV)
+    xin[:, :Hin, :Hin] = rnd(Bn, Hin, Hin, Cc, seed=1)
+    wt = rnd(Cc, Cc, 3, 3, seed=2, scale=0.05, dtype=torch.float32).to(torch.bfloat16).float()  # [ci,co,kh,kw]
+    bias = rnd(Cc, seed=3, dtype=torch.float32)
+    wF = wt.permute(2, 3, 1, 0).reshape(9, Cc, Cc).to(torch.bfloat16).contiguous()  # [tap][co][ci]
+    wD = wt.permute(2, 3, 0, 1).reshape(9, Cc, Cc).to(torch.bfloat16).contiguous()  # [tap][ci][co]
+    # ---------------- forward: 4 output-parity classes, each a dense stride-1 gather ----------------
+    y = torch.zeros(Bn, pout, pout, Cc, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(Bn, 2, device=DEV)
+    cls = _classes(pad)
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = [(kh * 3 + kw, dh, dw) for kh, dh in cls[py] for kw, dw in cls[px]]
+            sub_h, sub_w = (Hout - 1 - py) // 2 + 1, (Hout - 1 - px) // 2 + 1
+            g = _convt_geom(Cc, Bn, Hin, pin, tw, th, sub_h, sub_w, pout, py, px, taps)
+            tiles = (sub_h + th - 1) // th
+            gemm(lib, M=Bn * tiles * 128, N=Cc, K=len(taps) * Cc, a_mode=L.OP_CONV_K, A=xin, B=wF, conv=g, out=y, ldo=Cc,
+                 bias=bias, stats=stats, epi=L.EPI_RELU | L.EPI_STATS)
+    xr = xin[:, :Hin, :Hin].float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    pre = F.conv_transpose2d(xr, wr, bias, stride=2, padding=pad, output_padding=opad)
+    ref = F.relu(pre).permute(0, 2, 3, 1)
+    assert relerr(y[:, :Hout, :Hout].float(), ref) < 6e-3
+    if pout > Hout:
+        assert torch.all(y[:, Hout:] == 0) and torch.all(y[:, :, Hout:] == 0)  # padding row/col never written
+    o = y.float().view(Bn, -1)
+    torch.testing.assert_close(stats[:, 0], o.sum(1), rtol=2e-4, atol=2e-2)
+    # ---------------- backward operands ----------------
+    dy = torch.zeros(Bn, pout, pout, Cc, dtype=torch.bfloat16, device=DEV)
+    dy[:, :Hout, :Hout] = rnd(Bn, Hout, Hout, Cc, seed=5)
+    (F.conv_transpose2d(xr, wr, None, stride=2, padding=pad, output_padding=opad) *
+     dy[:, :Hout, :Hout].float().permute(0, 3, 1, 2)).sum().backward()
+    # dgrad: dX[ih] = sum_k dY[2 ih - p + k] W : one GEMM, 9 taps, TMA element stride 2
+    taps9 = [(t, t // 3 - pad, t % 3 - pad) for t in range(9)]
+    g = _convt_geom(Cc, Bn, pout if pout > Hout else Hout, pout, tw, th, Hin, Hin, pin, 0, 0, taps9)
+    g.sy = g.sx = 1
+    g.in_stride = 2
+    tiles = (Hin + th - 1) // th
+    dx = torch.zeros(Bn, pin, pin, Cc, dtype=torch.bfloat16, device=DEV)
+    gemm(lib, M=Bn * tiles * 128, N=Cc, K=9 * Cc, a_mode=L.OP_CONV_K, A=dy, B=wD, conv=g, out=dx, ldo=Cc)
+    assert relerr(dx[:, :Hin, :Hin].float(), xr.grad.permute(0, 2, 3, 1)) < 6e-3
+    # wgrad: ws[tap][ci][co] = sum_pix X[pix, ci] * dY[2 pix - p + k, co]
+    ws = torch.zeros(9, Cc, Cc, device=DEV)
+    g2 = _convt_geom(Cc, Bn, pout if pout > Hout else Hout, pout, tw, 64 // tw, pin, pin, pin, 0, 0, taps9)
+    g2.in_stride = 2
+    gemm(lib, M=Cc, N=Cc, K=Bn * pin * pin, a_mode=L.OP_MN2D, b_mode=L.OP_CONV_MN, A=xin, lda=Cc, B=dy, conv=g2, out=ws,
+         ldo=Cc, epi=L.EPI_ATOMIC, batch_z=9, out_z_stride=Cc * Cc, splits=2, bn=128)
+    assert relerr(ws, wr.grad.permute(2, 3, 0, 1).reshape(9, Cc, Cc)) < 1e-4

@@ -23,7 +23,8 @@ class ConvGeom(C.Structure):
                 ("ntaps", C.c_int), ("dh", C.c_int * 9), ("dw", C.c_int * 9),
                 ("tile_w", C.c_int), ("tile_h", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
                 ("out_img_rows", C.c_int), ("out_row_off", C.c_int), ("out_wpitch", C.c_int),
-                ("sy", C.c_int), ("sx", C.c_int), ("py", C.c_int), ("px", C.c_int)]
+                ("sy", C.c_int), ("sx", C.c_int), ("py", C.c_int), ("px", C.c_int),
+                ("in_stride", C.c_int), ("b_tap_rows", C.c_int), ("wtap", C.c_int * 9)]
 
 
 class GemmDesc(C.Structure):

@@ -30,6 +30,9 @@ struct GemmK {
   int m_tiles, n_tiles, total_items;
   int a_mode, b_mode;
   int cchunks;  // CONV_K: 64-channel chunks per tap
+  int es;       // gather stride of the NHWC operand
+  int b_tap_rows;
+  int wtap[9];
   int dh[9], dw[9];
   int tile_w, tile_h, tiles_per_img;
   int kb_per_img, rows_per_kb;  // CONV_MN
@@ -194,11 +197,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {  // CONV_K
             const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
             const int b = it.m_blk / p.tiles_per_img, ht = it.m_blk - b * p.tiles_per_img;
-            tma_load_4d(&tmA, sa, &full[stage], cc * 64, p.dw[tap], ht * p.tile_h + p.dh[tap], b);
+            tma_load_4d(&tmA, sa, &full[stage], cc * 64, p.dw[tap], p.es * ht * p.tile_h + p.dh[tap], b);
           }
           // ---- B ----
           if (p.b_mode == THEIA_OP_K2D) {
-            tma_load_2d(&tmB, sb, &full[stage], kb * BK, n0);
+            if (p.b_tap_rows > 0) {  // tap-major weight pack [tap][rows][C]
+              const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+              tma_load_2d(&tmB, sb, &full[stage], cc * 64, p.wtap[tap] * p.b_tap_rows + n0);
+            } else {
+              tma_load_2d(&tmB, sb, &full[stage], kb * BK, n0);
+            }
           } else if (p.b_mode == THEIA_OP_MN2D) {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) tma_load_2d(&tmB, sb + i * 8192, &full[stage], n0 + 64 * i, kb * BK);
@@ -207,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
               tma_load_4d(&tmB, sb + i * 8192, &full[stage], n0 + 64 * i, p.dw[it.z],
-                          hb * p.rows_per_kb + p.dh[it.z], b);
+                          p.es * hb * p.rows_per_kb + p.dh[it.z], b);
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -715,8 +723,10 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
       return set_error(THEIA_ERR_ARG, "CONV_K: tile must be 128 pixels, C %% 64 == 0");
     uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
     uint64_t strides[3] = {(uint64_t)g.stride_w * 2, (uint64_t)g.stride_h * 2, (uint64_t)g.stride_b * 2};
-    uint32_t box[4] = {64, (uint32_t)g.tile_w, (uint32_t)g.tile_h, 1};
-    rc = encode_tensor_map(&tmA, d->A, 4, dims, strides, box);
+    const uint32_t es = g.in_stride > 1 ? (uint32_t)g.in_stride : 1u;
+    uint32_t box[4] = {64, es * (uint32_t)g.tile_w, es * (uint32_t)g.tile_h, 1};
+    uint32_t estr[4] = {1, es, es, 1};
+    rc = encode_tensor_map(&tmA, d->A, 4, dims, strides, box, estr);
     k.cchunks = g.C / 64;
     k.tile_w = g.tile_w;
     k.tile_h = g.tile_h;
@@ -731,7 +741,12 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   }
   if (rc) return rc;
   // ---- B ----
-  if (d->b_mode == THEIA_OP_K2D) {
+  if (d->b_mode == THEIA_OP_K2D && d->a_mode == THEIA_OP_CONV_K && g.b_tap_rows > 0) {
+    // tap-major weight pack [9][b_tap_rows][C]: one 2-D map over all taps
+    rc = encode_2d(&tmB, d->B, (uint64_t)g.C, (uint64_t)9 * g.b_tap_rows, (uint64_t)g.C, 64, bn);
+    k.b_tap_rows = g.b_tap_rows;
+    for (int i = 0; i < 9; ++i) k.wtap[i] = g.wtap[i];
+  } else if (d->b_mode == THEIA_OP_K2D) {
     rc = encode_2d(&tmB, d->B, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, 64, bn);
   } else if (d->b_mode == THEIA_OP_MN2D) {
     rc = encode_2d(&tmB, d->B, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, 64);
@@ -743,8 +758,10 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
     if (d->K != g.B * g.out_h * g.tile_w) return set_error(THEIA_ERR_ARG, "CONV_MN: K != B*out_h*tile_w");
     uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B};
     uint64_t strides[3] = {(uint64_t)g.stride_w * 2, (uint64_t)g.stride_h * 2, (uint64_t)g.stride_b * 2};
-    uint32_t box[4] = {64, (uint32_t)g.tile_w, (uint32_t)(64 / g.tile_w), 1};
-    rc = encode_tensor_map(&tmB, d->B, 4, dims, strides, box);
+    const uint32_t es = g.in_stride > 1 ? (uint32_t)g.in_stride : 1u;
+    uint32_t box[4] = {64, es * (uint32_t)g.tile_w, es * (uint32_t)(64 / g.tile_w), 1};
+    uint32_t estr[4] = {1, es, es, 1};
+    rc = encode_tensor_map(&tmB, d->B, 4, dims, strides, box, estr);
     k.rows_per_kb = 64 / g.tile_w;
     k.kb_per_img = (g.out_h * g.tile_w) / 64;
     if (k.batch_z != g.ntaps) return set_error(THEIA_ERR_ARG, "CONV_MN: batch_z must equal ntaps");
@@ -753,6 +770,7 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   }
   if (rc) return rc;
   for (int i = 0; i < 9; ++i) k.dh[i] = g.dh[i], k.dw[i] = g.dw[i];
+  k.es = g.in_stride > 1 ? g.in_stride : 1;
 
   k.num_kb = (d->K + BK - 1) / BK;
   if (k.splits > k.num_kb) k.splits = k.num_kb;

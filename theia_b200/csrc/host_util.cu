@@ -50,7 +50,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int encode_tensor_map(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box) {
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return set_error(THEIA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error(THEIA_ERR_ARG, "TMA base not 16-byte aligned");
@@ -61,7 +61,7 @@ int encode_tensor_map(CUtensorMap* tm, const void* ptr, int rank, const uint64_t
   for (int i = 0; i < rank; ++i) {
     gdims[i] = dims[i];
     gbox[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (box[i] > 256) return set_error(THEIA_ERR_ARG, "TMA box dim > 256");
   }
   for (int i = 0; i + 1 < rank; ++i) {

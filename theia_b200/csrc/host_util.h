@@ -14,7 +14,7 @@ int num_sms();
 // rank-D bf16 tensor map, 128-byte swizzle, zero OOB fill. dims[0] is the contiguous dim,
 // strides_bytes has rank-1 entries (dims 1..rank-1).
 int encode_tensor_map(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box);
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 #define THEIA_CHECK_LAUNCH(what)                                                                   \
   do {                                                                                             \
