@@ -115,11 +115,14 @@ int theia_layernorm_bwd(const void* dy, const void* x, const float* gamma, const
                         void* stream); /* dxsum (optional): [D] += column sums of the produced dx */
 /* nn.LayerNorm([C,H,W]) per image, NHWC storage, n = H*W*C (adapter_heads.py:306-324).  stats[b] =
  * {sum, sumsq} produced by the GEMM epilogue (THEIA_EPI_STATS). gamma/beta are the HWC-permuted affine. */
+/* C, Wp, Wv: Wp > 0 = the map is stored zero-padded [Wp x Wp x C] with Wv x Wv valid pixels (the 31x31 stage of
+ * the 64x64 heads is kept at pitch 32); padding is written as zero and excluded from the statistics */
 int theia_ln3d_apply(const void* x, const float* stats, const float* gamma_hwc, const float* beta_hwc, void* y,
-                     int B, int n, float eps, void* stream);
+                     int B, int n, float eps, int C, int Wp, int Wv, void* stream);
 /* red: scratch [B][2]; dgamma/dbeta (HWC) ACCUMULATED; relu_mask: also apply the producer's ReLU mask (x>0) */
 int theia_ln3d_bwd(const void* dy, const void* x, const float* stats, const float* gamma_hwc, float* red, void* dx,
-                   float* dgamma_hwc, float* dbeta_hwc, int B, int n, float eps, int relu_mask, void* stream);
+                   float* dgamma_hwc, float* dbeta_hwc, int B, int n, float eps, int relu_mask, int C, int Wp, int Wv,
+                   void* stream);
 /* Loss terms of one teacher (src/theia/models/rvfm.py:153-176): acc scratch [B][5]; out3 = {mse, cos, l1} */
 int theia_loss_fwd(const float* pred, const void* target, int target_is_bf16, float* acc, float* out3, int B, int n,
                    void* stream);
@@ -142,6 +145,9 @@ int theia_attention_tc_bwd(const void* qkv, const void* out, const void* dout, c
 /* parameter packing helpers */
 int theia_gather4(const void* in, void* out, int in_is_f32, int out_is_f32, int n0, int n1, int n2, int n3,
                   long long s0, long long s1, long long s2, long long s3, long long base, void* stream);
+/* LayerNorm[C,H,W] affine layouts: reference [C][Hv][Wv] <-> NHWC zero-padded [Hp][Wp][C] (fp32) */
+int theia_chw_to_hwc(const float* in, float* out, int C, int Hv, int Wv, int Hp, int Wp, void* stream);
+int theia_hwc_to_chw(const float* in, float* out, int C, int Hv, int Wv, int Hp, int Wp, void* stream);
 int theia_cast_bf16(const float* in, void* out, long long n, void* stream);
 int theia_transpose_cast_bf16(const float* in, void* out, int R, int C, void* stream);
 /* out[n] += sum_m x[m,n] (rows with m % skip_mod == 0 skipped when skip_mod > 0) */

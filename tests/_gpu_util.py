@@ -32,7 +32,12 @@ def fetch_all(m, cfg, B):
         for name, w in (("ln1", D), ("qkv", 3 * D), ("attn", D), ("xmid", D), ("ln2", D), ("h", 4 * D), ("a", 4 * D)):
             out[(name, l)] = fetch(m, name, l, (B, 197, w))
         out[("x", l + 1)] = fetch(m, "x", l + 1, (B, 197, D))
-    for i, t in enumerate(cfg.teachers):
-        for name in ("padout", "hln0", "c1", "hln1", "c2", "hln2"):
+    for i, (t, (ct, ht, wt)) in enumerate(cfg.teachers.items()):
+        v1, p1, v2 = (16, 16, 16) if ht == 16 else (31, 32, 64)
+        for name in ("padout", "hln0"):
             out[(name, t)] = fetch(m, name, i, (B, 16, 16, D))
+        for name in ("c1", "hln1"):  # the 31x31 stage of the 64x64 heads is stored at pitch 32 (zero padded)
+            out[(name, t)] = fetch(m, name, i, (B, p1, p1, D))[:, :v1, :v1].contiguous()
+        for name in ("c2", "hln2"):
+            out[(name, t)] = fetch(m, name, i, (B, v2, v2, D))
     return out

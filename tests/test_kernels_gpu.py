@@ -262,7 +262,7 @@ def test_ln3d_apply_and_bwd(lib):
     stats = torch.stack([xf.sum(1), (xf * xf).sum(1)], 1).contiguous()
     y = torch.empty_like(x)
     L.check(lib.theia_ln3d_apply(x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), Bn,
-                                 n, 1e-5, S()))
+                                 n, 1e-5, Cc, 0, 0, S()))
     xr = xf.clone().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     ref = F.layer_norm(xr, (n,), gr, br, 1e-5)
@@ -272,7 +272,7 @@ def test_ln3d_apply_and_bwd(lib):
     dx = torch.empty_like(x)
     dg, db = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
     L.check(lib.theia_ln3d_bwd(dy.data_ptr(), x.data_ptr(), stats.data_ptr(), gamma.data_ptr(), red.data_ptr(),
-                               dx.data_ptr(), dg.data_ptr(), db.data_ptr(), Bn, n, 1e-5, 1, S()))
+                               dx.data_ptr(), dg.data_ptr(), db.data_ptr(), Bn, n, 1e-5, 1, Cc, 0, 0, S()))
     want = xr.grad * (xf > 0)
     assert relerr(dx.float(), want) < 6e-3
     assert relerr(dg, gr.grad) < 1e-3
@@ -486,3 +486,44 @@ def test_convtranspose_stride2_fwd_dgrad_wgrad(lib, which):
     gemm(lib, M=Cc, N=Cc, K=Bn * pin * pin, a_mode=L.OP_MN2D, b_mode=L.OP_CONV_MN, A=xin, lda=Cc, B=dy, conv=g2, out=ws,
          ldo=Cc, epi=L.EPI_ATOMIC, batch_z=9, out_z_stride=Cc * Cc, splits=2, bn=128)
     assert relerr(ws, wr.grad.permute(2, 3, 0, 1).reshape(9, Cc, Cc)) < 1e-4
+
+
+def test_ln3d_padded_31_in_32(lib):
+    """LayerNorm([C,31,31]) of the 64x64 heads, stored zero-padded at pitch 32 (NHWC)."""
+    Bn, Cc, Wv, Wp = 5, 64, 31, 32
+    xv = F.relu(rnd(Bn, Wv, Wv, Cc, seed=1))
+    dyv = rnd(Bn, Wv, Wv, Cc, seed=2)
+    x = torch.zeros(Bn, Wp, Wp, Cc, dtype=torch.bfloat16, device=DEV)
+    dy = torch.zeros_like(x)
+    x[:, :Wv, :Wv], dy[:, :Wv, :Wv] = xv, dyv
+    g_chw = 1 + 0.1 * rnd(Cc, Wv, Wv, seed=3, dtype=torch.float32)
+    b_chw = 0.1 * rnd(Cc, Wv, Wv, seed=4, dtype=torch.float32)
+    g_hwc, b_hwc = torch.empty(Wp * Wp * Cc, device=DEV), torch.empty(Wp * Wp * Cc, device=DEV)
+    L.check(lib.theia_chw_to_hwc(g_chw.data_ptr(), g_hwc.data_ptr(), Cc, Wv, Wv, Wp, Wp, S()))
+    L.check(lib.theia_chw_to_hwc(b_chw.data_ptr(), b_hwc.data_ptr(), Cc, Wv, Wv, Wp, Wp, S()))
+    assert torch.equal(g_hwc.view(Wp, Wp, Cc)[:Wv, :Wv], g_chw.permute(1, 2, 0)) and g_hwc.view(Wp, Wp, Cc)[Wv:].abs().sum() == 0
+    back = torch.empty_like(g_chw)
+    L.check(lib.theia_hwc_to_chw(g_hwc.data_ptr(), back.data_ptr(), Cc, Wv, Wv, Wp, Wp, S()))
+    assert torch.equal(back, g_chw)
+    xf = xv.float().reshape(Bn, -1)
+    stats = torch.stack([xf.sum(1), (xf * xf).sum(1)], 1).contiguous()
+    n = Wp * Wp * Cc
+    y = torch.full_like(x, float("nan"))
+    L.check(lib.theia_ln3d_apply(x.data_ptr(), stats.data_ptr(), g_hwc.data_ptr(), b_hwc.data_ptr(), y.data_ptr(), Bn, n,
+                                 1e-5, Cc, Wp, Wv, S()))
+    xr = xv.float().permute(0, 3, 1, 2).clone().requires_grad_(True)  # [B,C,31,31]
+    gr, br = g_chw.clone().requires_grad_(True), b_chw.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (Cc, Wv, Wv), gr, br, 1e-5)
+    assert relerr(y[:, :Wv, :Wv].float(), ref.permute(0, 2, 3, 1)) < 5e-3
+    assert torch.all(y[:, Wv:] == 0) and torch.all(y[:, :, Wv:] == 0)
+    ref.backward(dyv.float().permute(0, 3, 1, 2))
+    red = torch.empty(Bn, 2, device=DEV)
+    dx = torch.full_like(x, float("nan"))
+    dg, db = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    L.check(lib.theia_ln3d_bwd(dy.data_ptr(), x.data_ptr(), stats.data_ptr(), g_hwc.data_ptr(), red.data_ptr(),
+                               dx.data_ptr(), dg.data_ptr(), db.data_ptr(), Bn, n, 1e-5, 1, Cc, Wp, Wv, S()))
+    want = (xr.grad * (xr > 0)).permute(0, 2, 3, 1)
+    assert relerr(dx[:, :Wv, :Wv].float(), want) < 6e-3
+    assert torch.all(dx[:, Wv:] == 0) and torch.all(dx[:, :, Wv:] == 0)
+    assert relerr(dg.view(Wp, Wp, Cc)[:Wv, :Wv], gr.grad.permute(1, 2, 0)) < 1e-3
+    assert relerr(db.view(Wp, Wp, Cc)[:Wv, :Wv], br.grad.permute(1, 2, 0)) < 1e-3

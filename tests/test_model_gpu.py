@@ -67,7 +67,8 @@ def test_readme_quickstart_zeros():
 
 @pytest.mark.parametrize("backbone,tset,B", [("facebook/deit-tiny-patch16-224", "dinov2", 2),
                                              ("facebook/deit-tiny-patch16-224", "cdiv", 3),
-                                             ("facebook/deit-small-patch16-224", "dinov2", 5)])
+                                             ("facebook/deit-small-patch16-224", "dinov2", 5),
+                                             ("facebook/deit-tiny-patch16-224", "cddsv", 2)])
 def test_distill_step_parity_vs_oracle(backbone, tset, B):
     cfg, P, m = build(backbone, tset)
     images, targets = O.synthetic_batch(cfg, B, seed=0, device=DEV)
@@ -155,6 +156,28 @@ def test_default_resize_path_against_reference_golden():
     losses = m.get_loss(pred, targets)
     for k, v in fx["losses"].items():
         assert abs(float(losses[k]) - v) <= 1e-3 * abs(v), k
+
+
+def test_cddsv_64x64_heads_against_reference_golden():
+    """BASELINE config #4 head set (adds SAM 64x64x256 and Depth-Anything 64x64x32: stride-2 transposed convs,
+    LayerNorm over [C,31,31] / [C,64,64]) against the fixture produced by the real reference."""
+    fx = torch.load(os.path.join(GOLDEN, "tiny_cddsv_b1.pt"), weights_only=False)
+    cfg, P, m = build(fx["backbone"], fx["teachers"], seed=fx["seed"])
+    images, targets = O.synthetic_batch(cfg, fx["B"], seed=fx["seed"], device=DEV)
+    pred = m(images, **fx["kwargs"])
+    for t, gq in fx["pred"].items():
+        assert tuple(pred[t].shape) == gq["shape"]
+        assert relerr(_sl(pred[t]).cpu(), gq["sample"]) < 3e-2, t
+    losses = m.get_loss(pred, targets)
+    for k, v in fx["losses"].items():
+        assert abs(float(losses[k]) - v) <= 1e-3 * abs(v), k
+    for k in ("mse_losses_per_model", "cos_losses_per_model", "l1_losses_per_model"):
+        for t, v in fx["losses_per_model"][k].items():
+            assert abs(losses[k][t] - v) <= 1e-3 * abs(v), (k, t)
+    (0.9 * losses["cos_loss"] + 0.1 * losses["l1_loss"]).backward()
+    g = dict(m.named_parameters())
+    for k, s in fx["grad_sample"].items():
+        assert relerr(_sl(g[k].grad).cpu(), s) < 0.3, k
 
 
 def test_training_reduces_loss_and_repacks_weights():

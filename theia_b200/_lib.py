@@ -56,8 +56,10 @@ SYMBOLS = {
     "theia_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "theia_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "theia_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
-    "theia_ln3d_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
-    "theia_ln3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp]),
+    "theia_ln3d_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _vp]),
+    "theia_ln3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp]),
+    "theia_chw_to_hwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "theia_hwc_to_chw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "theia_loss_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "theia_loss_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp]),

@@ -201,13 +201,23 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
 // ============================================================================================
 __global__ void __launch_bounds__(256) ln3d_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         bf16* __restrict__ y, int n, long long total, float eps) {
+                                                         bf16* __restrict__ y, int n, long long total, float eps,
+                                                         int C, int Wp, int Wv) {
   const long long i8 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i8 >= total) return;
   const int b = static_cast<int>(i8 / n);
   const int j = static_cast<int>(i8 - static_cast<long long>(b) * n);
-  const float mean = stats[2 * b] / n;
-  const float var = fmaxf(stats[2 * b + 1] / n - mean * mean, 0.f);
+  float ns = static_cast<float>(n);
+  if (Wp > 0) {  // padded storage [Wp x Wp] of a [Wv x Wv] map: padding stays zero and is not counted
+    const int pos = j / C, w = pos % Wp, h = pos / Wp;
+    ns = static_cast<float>(Wv) * Wv * C;
+    if (w >= Wv || h >= Wv) {
+      *reinterpret_cast<uint4*>(y + i8) = make_uint4(0u, 0u, 0u, 0u);
+      return;
+    }
+  }
+  const float mean = stats[2 * b] / ns;
+  const float var = fmaxf(stats[2 * b + 1] / ns - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
   float v[8], g[8], bb[8], o[8];
   load8(x + i8, v);
@@ -225,10 +235,18 @@ __global__ void __launch_bounds__(256) ln3d_bwd_reduce_kernel(const bf16* __rest
                                                               const float* __restrict__ stats,
                                                               const float* __restrict__ gamma, float* __restrict__ red,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              int n, int B, float eps) {
+                                                              int n, int B, float eps, int C, int Wp, int Wv) {
   __shared__ float sred[LN3D_GROUP][2];
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  const bool act = j < n;
+  bool act = j < n;
+  float ns = static_cast<float>(n);
+  if (Wp > 0) {
+    ns = static_cast<float>(Wv) * Wv * C;
+    if (act) {
+      const int pos = j / C, w = pos % Wp, h = pos / Wp;
+      act = (w < Wv) && (h < Wv);
+    }
+  }
   const int b0 = blockIdx.y * LN3D_GROUP;
   if (threadIdx.x < LN3D_GROUP * 2) (&sred[0][0])[threadIdx.x] = 0.f;
   __syncthreads();
@@ -242,8 +260,8 @@ __global__ void __launch_bounds__(256) ln3d_bwd_reduce_kernel(const bf16* __rest
     if (b >= B) break;
     float s1 = 0.f, s2 = 0.f;
     if (act) {
-      const float mean = stats[2 * b] / n;
-      const float var = fmaxf(stats[2 * b + 1] / n - mean * mean, 0.f);
+      const float mean = stats[2 * b] / ns;
+      const float var = fmaxf(stats[2 * b + 1] / ns - mean * mean, 0.f);
       const float rstd = rsqrtf(var + eps);
       float d[8], xv[8];
       const long long off = static_cast<long long>(b) * n + j;
@@ -286,15 +304,25 @@ __global__ void __launch_bounds__(256) ln3d_bwd_apply_kernel(const bf16* __restr
                                                              const float* __restrict__ stats,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ red, bf16* __restrict__ dx,
-                                                             int n, long long total, float eps, int relu_mask) {
+                                                             int n, long long total, float eps, int relu_mask, int C,
+                                                             int Wp, int Wv) {
   const long long i8 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i8 >= total) return;
   const int b = static_cast<int>(i8 / n);
   const int j = static_cast<int>(i8 - static_cast<long long>(b) * n);
-  const float mean = stats[2 * b] / n;
-  const float var = fmaxf(stats[2 * b + 1] / n - mean * mean, 0.f);
+  float ns = static_cast<float>(n);
+  if (Wp > 0) {
+    const int pos = j / C, w = pos % Wp, h = pos / Wp;
+    ns = static_cast<float>(Wv) * Wv * C;
+    if (w >= Wv || h >= Wv) {
+      *reinterpret_cast<uint4*>(dx + i8) = make_uint4(0u, 0u, 0u, 0u);
+      return;
+    }
+  }
+  const float mean = stats[2 * b] / ns;
+  const float var = fmaxf(stats[2 * b + 1] / ns - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
-  const float c1 = red[2 * b] / n, c2 = red[2 * b + 1] / n;
+  const float c1 = red[2 * b] / ns, c2 = red[2 * b + 1] / ns;
   float d[8], xv[8], g8[8], o[8];
   load8(dy + i8, d);
   load8(x + i8, xv);
@@ -552,6 +580,25 @@ __global__ void __launch_bounds__(256) gather4_kernel(const TI* __restrict__ in,
   out[t] = static_cast<TO>(v);
 }
 
+// LayerNorm[C,H,W] affine: [C][Hv][Wv] (reference layout) <-> [Hp][Wp][C] (NHWC, zero padded)
+__global__ void __launch_bounds__(256) chw_to_hwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                         int Hv, int Wv, int Hp, int Wp) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(Hp) * Wp * C) return;
+  const int c = static_cast<int>(t % C);
+  const int pos = static_cast<int>(t / C), w = pos % Wp, h = pos / Wp;
+  out[t] = (h < Hv && w < Wv) ? in[(static_cast<long long>(c) * Hv + h) * Wv + w] : 0.f;
+}
+__global__ void __launch_bounds__(256) hwc_to_chw_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                         int Hv, int Wv, int Hp, int Wp) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(C) * Hv * Wv) return;
+  const int w = static_cast<int>(t % Wv);
+  const int h = static_cast<int>((t / Wv) % Hv);
+  const int c = static_cast<int>(t / (static_cast<long long>(Wv) * Hv));
+  out[t] = in[(static_cast<long long>(h) * Wp + w) * C + c];
+}
+
 // tiled transpose-cast: out[c][r] = (bf16) in[r][c]   (fp32 [R,Cc] -> bf16 [Cc,R])
 __global__ void transpose_cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, int R, int Cc) {
   __shared__ float tile[32][33];
@@ -671,30 +718,30 @@ extern "C" int theia_layernorm_bwd(const void* dy, const void* x, const float* g
 }
 
 extern "C" int theia_ln3d_apply(const void* x, const float* stats, const float* gamma_hwc, const float* beta_hwc,
-                                void* y, int B, int n, float eps, void* stream) {
-  if (n % 8 != 0) return set_error(THEIA_ERR_ARG, "ln3d: n %% 8 != 0");
+                                void* y, int B, int n, float eps, int C, int Wp, int Wv, void* stream) {
+  if (n % 8 != 0 || C % 8 != 0) return set_error(THEIA_ERR_ARG, "ln3d: n, C %% 8 != 0");
   const long long total = static_cast<long long>(B) * n;
   const long long thr = total / 8;
   ln3d_apply_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, S(stream)>>>(
-      static_cast<const bf16*>(x), stats, gamma_hwc, beta_hwc, static_cast<bf16*>(y), n, total, eps);
+      static_cast<const bf16*>(x), stats, gamma_hwc, beta_hwc, static_cast<bf16*>(y), n, total, eps, C, Wp, Wv);
   THEIA_CHECK_LAUNCH("ln3d_apply");
   return THEIA_OK;
 }
 
 extern "C" int theia_ln3d_bwd(const void* dy, const void* x, const float* stats, const float* gamma_hwc, float* red,
                               void* dx, float* dgamma_hwc, float* dbeta_hwc, int B, int n, float eps, int relu_mask,
-                              void* stream) {
-  if (n % 8 != 0) return set_error(THEIA_ERR_ARG, "ln3d: n %% 8 != 0");
+                              int C, int Wp, int Wv, void* stream) {
+  if (n % 8 != 0 || C % 8 != 0) return set_error(THEIA_ERR_ARG, "ln3d: n, C %% 8 != 0");
   cudaError_t e = cudaMemsetAsync(red, 0, sizeof(float) * 2 * B, S(stream));
   if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
   dim3 g1((n / 8 + 255) / 256, (B + LN3D_GROUP - 1) / LN3D_GROUP);
   ln3d_bwd_reduce_kernel<<<g1, 256, 0, S(stream)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats,
-                                                    gamma_hwc, red, dgamma_hwc, dbeta_hwc, n, B, eps);
+                                                    gamma_hwc, red, dgamma_hwc, dbeta_hwc, n, B, eps, C, Wp, Wv);
   THEIA_CHECK_LAUNCH("ln3d_bwd_reduce");
   const long long total = static_cast<long long>(B) * n;
   ln3d_bwd_apply_kernel<<<static_cast<unsigned>((total / 8 + 255) / 256), 256, 0, S(stream)>>>(
       static_cast<const bf16*>(dy), static_cast<const bf16*>(x), stats, gamma_hwc, red, static_cast<bf16*>(dx), n,
-      total, eps, relu_mask);
+      total, eps, relu_mask, C, Wp, Wv);
   THEIA_CHECK_LAUNCH("ln3d_bwd_apply");
   return THEIA_OK;
 }
@@ -823,6 +870,19 @@ extern "C" int theia_gather4(const void* in, void* out, int in_is_f32, int out_i
   else
     return set_error(THEIA_ERR_UNSUPPORTED, "gather4: unsupported dtype combination");
   THEIA_CHECK_LAUNCH("gather4");
+  return THEIA_OK;
+}
+
+extern "C" int theia_chw_to_hwc(const float* in, float* out, int C, int Hv, int Wv, int Hp, int Wp, void* stream) {
+  const long long total = static_cast<long long>(Hp) * Wp * C;
+  chw_to_hwc_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, S(stream)>>>(in, out, C, Hv, Wv, Hp, Wp);
+  THEIA_CHECK_LAUNCH("chw_to_hwc");
+  return THEIA_OK;
+}
+extern "C" int theia_hwc_to_chw(const float* in, float* out, int C, int Hv, int Wv, int Hp, int Wp, void* stream) {
+  const long long total = static_cast<long long>(C) * Hv * Wv;
+  hwc_to_chw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, S(stream)>>>(in, out, C, Hv, Wv, Hp, Wp);
+  THEIA_CHECK_LAUNCH("hwc_to_chw");
   return THEIA_OK;
 }
 

@@ -29,6 +29,9 @@ struct LayerP {
 struct HeadP {
   int padw, padb, g0, b0, c1w, c1b, g1, b1, c2w, c2b, g2, b2, lw, lb;
   int ct;
+  int hw;          // target H = W: 16 (Conv2d 3x3 stack) or 64 (two stride-2 ConvTranspose2d, adapter_heads.py:304-315)
+  int v1, p1;      // stage-1 map: valid extent / storage pitch (16/16 or 31/32)
+  int v2, p2;      // stage-2 map (16/16 or 64/64)
 };
 
 // bf16 packed weights (offsets in elements of the bf16 pack buffer)
@@ -130,8 +133,8 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   if (cfg->image != 224 || cfg->patch != 16) return set_error(THEIA_ERR_UNSUPPORTED, "only 224/16 ViT geometry");
   if (cfg->num_teachers < 0 || cfg->num_teachers > THEIA_MAX_TEACHERS) return set_error(THEIA_ERR_ARG, "num_teachers");
   for (int t = 0; t < cfg->num_teachers; ++t) {
-    if (cfg->teacher_hw[t] != 16)
-      return set_error(THEIA_ERR_UNSUPPORTED, "teacher %s: only 16x16 targets are built so far (got %d)",
+    if (cfg->teacher_hw[t] != 16 && cfg->teacher_hw[t] != 64)
+      return set_error(THEIA_ERR_UNSUPPORTED, "teacher %s: target maps must be 16x16 or 64x64 (got %d)",
                        cfg->teacher_names[t], cfg->teacher_hw[t]);
     if (cfg->teacher_c[t] % 8 != 0) return set_error(THEIA_ERR_UNSUPPORTED, "teacher channels %% 8 != 0");
   }
@@ -176,18 +179,21 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
     const std::string p = "translator.translator_heads." + legit(cfg->teacher_names[t]) + ".";
     HeadP q;
     q.ct = cfg->teacher_c[t];
+    q.hw = cfg->teacher_hw[t];
+    q.v1 = q.hw == 16 ? 16 : 31, q.p1 = q.hw == 16 ? 16 : 32;
+    q.v2 = q.hw == 16 ? 16 : 64, q.p2 = q.v2;
     q.padw = add_param(m, p + "pad.1.weight", {C, C, 3, 3});
     q.padb = add_param(m, p + "pad.1.bias", {C});
     q.g0 = add_param(m, p + "adapter.0.weight", {C, 16, 16});
     q.b0 = add_param(m, p + "adapter.0.bias", {C, 16, 16});
     q.c1w = add_param(m, p + "adapter.1.weight", {C, C, 3, 3});
     q.c1b = add_param(m, p + "adapter.1.bias", {C});
-    q.g1 = add_param(m, p + "adapter.3.weight", {C, 16, 16});
-    q.b1 = add_param(m, p + "adapter.3.bias", {C, 16, 16});
+    q.g1 = add_param(m, p + "adapter.3.weight", {C, q.v1, q.v1});
+    q.b1 = add_param(m, p + "adapter.3.bias", {C, q.v1, q.v1});
     q.c2w = add_param(m, p + "adapter.4.weight", {C, C, 3, 3});
     q.c2b = add_param(m, p + "adapter.4.bias", {C});
-    q.g2 = add_param(m, p + "adapter.6.weight", {C, 16, 16});
-    q.b2 = add_param(m, p + "adapter.6.bias", {C, 16, 16});
+    q.g2 = add_param(m, p + "adapter.6.weight", {C, q.v2, q.v2});
+    q.b2 = add_param(m, p + "adapter.6.bias", {C, q.v2, q.v2});
     q.lw = add_param(m, p + "adapter.8.weight", {q.ct, C});
     q.lb = add_param(m, p + "adapter.8.bias", {q.ct});
     m->hp.push_back(q);
@@ -222,8 +228,9 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
     w.c2D = pb.take(W9, AL);
     w.l = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
     w.lT = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
+    const long long npix[3] = {256, 1LL * m->hp[t].p1 * m->hp[t].p1, 1LL * m->hp[t].p2 * m->hp[t].p2};
     for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 2; ++j) w.gb[i][j] = pf.take(256LL * C, AL);
+      for (int j = 0; j < 2; ++j) w.gb[i][j] = pf.take(npix[i] * C, AL);
     m->hw.push_back(w);
   }
   m->patches = ab.take(M * 768, AL);
@@ -248,14 +255,18 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   m->tokens = ab.take(M * D, AL);
   m->meanf = af.take(M, AL);
   m->rstdf = af.take(M, AL);
+  long long Pmax = P;
   for (int t = 0; t < T; ++t) {
     HeadA a;
+    const long long P1 = static_cast<long long>(B) * m->hp[t].p1 * m->hp[t].p1;
+    const long long P2 = static_cast<long long>(B) * m->hp[t].p2 * m->hp[t].p2;
+    if (P2 > Pmax) Pmax = P2;
     a.padout = ab.take(P * C, AL);
     a.ln0 = ab.take(P * C, AL);
-    a.c1 = ab.take(P * C, AL);
-    a.ln1 = ab.take(P * C, AL);
-    a.c2 = ab.take(P * C, AL);
-    a.ln2 = ab.take(P * C, AL);
+    a.c1 = ab.take(P1 * C, AL);
+    a.ln1 = ab.take(P1 * C, AL);
+    a.c2 = ab.take(P2 * C, AL);
+    a.ln2 = ab.take(P2 * C, AL);
     a.stats = af.take(3LL * B * 2, AL);
     m->ha.push_back(a);
   }
@@ -266,11 +277,11 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   m->dqkv = ab.take(M * 3 * D, AL);
   m->dh = ab.take(M * 4 * D, AL);
   m->dattn = ab.take(M * D, AL);
-  m->dA0 = ab.take(P * C, AL);
-  m->dA1 = ab.take(P * C, AL);
+  m->dA0 = ab.take(Pmax * C, AL);
+  m->dA1 = ab.take(Pmax * C, AL);
   m->red = af.take(2LL * B, AL);
   m->wscratch = af.take(9LL * C * C, AL);
-  m->gbscratch = af.take(2LL * 256 * C, AL);
+  m->gbscratch = af.take(2LL * (Pmax / B) * C, AL);
   m->n_packbf = pb.n, m->n_packf32 = pf.n, m->n_actbf = ab.n, m->n_actf32 = af.n;
   long long o = 0;
   m->o_packbf = o;
@@ -325,12 +336,13 @@ extern "C" int theia_model_debug_ptr(theia_model* m, const char* name, int i, vo
   }
   if (i >= 0 && i < m->T) {
     const HeadA& a = m->ha[i];
+    const long long P1 = 1LL * m->last_B * m->hp[i].p1 * m->hp[i].p1, P2 = 1LL * m->last_B * m->hp[i].p2 * m->hp[i].p2;
     if (n == "padout") { *ptr = AB(a.padout); *elems = P * D; return 0; }
     if (n == "hln0") { *ptr = AB(a.ln0); *elems = P * D; return 0; }
-    if (n == "c1") { *ptr = AB(a.c1); *elems = P * D; return 0; }
-    if (n == "hln1") { *ptr = AB(a.ln1); *elems = P * D; return 0; }
-    if (n == "c2") { *ptr = AB(a.c2); *elems = P * D; return 0; }
-    if (n == "hln2") { *ptr = AB(a.ln2); *elems = P * D; return 0; }
+    if (n == "c1") { *ptr = AB(a.c1); *elems = P1 * D; return 0; }
+    if (n == "hln1") { *ptr = AB(a.ln1); *elems = P1 * D; return 0; }
+    if (n == "c2") { *ptr = AB(a.c2); *elems = P2 * D; return 0; }
+    if (n == "hln2") { *ptr = AB(a.ln2); *elems = P2 * D; return 0; }
   }
   return set_error(THEIA_ERR_ARG, "unknown activation %s[%d]", name, i);
 }
@@ -414,6 +426,95 @@ void conv_geom_16(theia_conv_geom& g, int C, int Hin, int B, long long sw, long 
   g.sy = g.sx = 1, g.py = g.px = 0;
 }
 
+// ---- stride-2 ConvTranspose2d(k3) of the 64x64 heads ------------------------------------------------
+// Forward: the outputs of parity (py,px) form a dense stride-1 gather with 1/2/2/4 taps -> 4 GEMM launches
+// over sub-grids, no zero stuffing.  in: [B, vin x vin (pitch pin), C]; out: [B, vout x vout (pitch pout), C].
+// Weights: ONE tap-major pack [9][Cout][Cin]; each launch names the taps it uses (wtap).
+int convT2x_fwd(const Ctx& c, const bf16* x, int vin, int pin, const bf16* w9, const float* bias, bf16* out, int vout,
+                int pout, int pad, int C, int B, float* stats) {
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      theia_conv_geom g;
+      memset(&g, 0, sizeof(g));
+      g.C = C, g.H = vin, g.W = vin, g.B = B;
+      g.stride_w = C, g.stride_h = 1LL * pin * C, g.stride_b = 1LL * pin * pin * C;
+      int nt = 0;
+      for (int kh = 0; kh < 3; ++kh) {
+        if ((py + pad - kh) % 2 != 0) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          if ((px + pad - kw) % 2 != 0) continue;
+          g.dh[nt] = (py + pad - kh) / 2, g.dw[nt] = (px + pad - kw) / 2, g.wtap[nt] = kh * 3 + kw;
+          ++nt;
+        }
+      }
+      g.ntaps = nt;
+      const int sub_h = (vout - 1 - py) / 2 + 1, sub_w = (vout - 1 - px) / 2 + 1;
+      g.tile_w = sub_w <= 16 ? 16 : 32, g.tile_h = 128 / g.tile_w;
+      g.out_h = sub_h, g.out_w = sub_w;
+      g.out_img_rows = pout * pout, g.out_row_off = 0, g.out_wpitch = pout;
+      g.sy = g.sx = 2, g.py = py, g.px = px;
+      g.in_stride = 1, g.b_tap_rows = C;
+      const int tiles = (sub_h + g.tile_h - 1) / g.tile_h;
+      theia_gemm_desc d = gemm_base(B * tiles * 128, C, nt * C);
+      d.a_mode = THEIA_OP_CONV_K;
+      d.A = x, d.B = w9;
+      d.conv = g;
+      d.out = out, d.ldo = C, d.bias = bias, d.epi = THEIA_EPI_RELU | THEIA_EPI_STATS, d.stats = stats;
+      TRY(theia_gemm(&d, c.s));
+    }
+  return THEIA_OK;
+}
+
+// geometry shared by the dgrad / wgrad of a stride-2 transposed conv: gather dY[2*i - pad + k] with TMA element
+// stride 2 over the INPUT grid (vin x vin at pitch pin); dY is [B, vout x vout (pitch pout), C].
+void convT2x_bwd_geom(theia_conv_geom& g, int C, int B, int vin, int pin, int vout, int pout, int pad) {
+  memset(&g, 0, sizeof(g));
+  g.C = C, g.H = pout > vout ? pout : vout, g.W = g.H, g.B = B;  // padded rows/cols of dY are zero
+  g.stride_w = C, g.stride_h = 1LL * pout * C, g.stride_b = 1LL * pout * pout * C;
+  g.ntaps = 9;
+  for (int t = 0; t < 9; ++t) g.dh[t] = t / 3 - pad, g.dw[t] = t % 3 - pad, g.wtap[t] = t;
+  g.tile_w = pin <= 16 ? 16 : 32, g.tile_h = 128 / g.tile_w;
+  g.out_h = vin, g.out_w = vin;
+  g.out_img_rows = pin * pin, g.out_row_off = 0, g.out_wpitch = pin;
+  g.sy = g.sx = 1;
+  g.in_stride = 2, g.b_tap_rows = C;
+}
+
+// dX[B, vin x vin (pitch pin), C] = sum_k dY[2 i - pad + k] * Wt[ci,co,k]; weights tap-major [9][Cin][Cout]
+int convT2x_dgrad(const Ctx& c, const bf16* dy, const bf16* w9d, bf16* dx, int C, int B, int vin, int pin, int vout,
+                  int pout, int pad) {
+  theia_conv_geom g;
+  convT2x_bwd_geom(g, C, B, vin, pin, vout, pout, pad);
+  const int tiles = (vin + g.tile_h - 1) / g.tile_h;
+  theia_gemm_desc d = gemm_base(B * tiles * 128, C, 9 * C);
+  d.a_mode = THEIA_OP_CONV_K;
+  d.A = dy, d.B = w9d;
+  d.conv = g;
+  d.out = dx, d.ldo = C;
+  return theia_gemm(&d, c.s);
+}
+
+// ws[tap][Cin][Cout] += X[pix, Cin]^T * dY[2 pix - pad + tap, Cout]   (X at pitch pin, padding rows are zero)
+int convT2x_wgrad(const Ctx& c, const bf16* x, const bf16* dy, float* wsout, int C, int B, int vin, int pin, int vout,
+                  int pout, int pad) {
+  theia_conv_geom g;
+  convT2x_bwd_geom(g, C, B, vin, pin, vout, pout, pad);
+  g.tile_h = 64 / g.tile_w;
+  g.out_h = pin;  // K-blocks run over the pitched input grid
+  const int Ppix = B * pin * pin;
+  theia_gemm_desc d = gemm_base(C, C, Ppix);
+  d.a_mode = THEIA_OP_MN2D, d.b_mode = THEIA_OP_CONV_MN;
+  d.A = x, d.lda = C, d.B = dy;
+  d.conv = g;
+  d.out = wsout, d.ldo = C, d.epi = THEIA_EPI_ATOMIC;
+  d.batch_z = 9, d.out_z_stride = 1LL * C * C;
+  const int bn = (C % 256 == 0) ? 256 : (C % 192 == 0 ? 192 : 128);
+  d.bn = bn;
+  const int tiles = 9 * ((C + 127) / 128) * ((C + bn - 1) / bn);
+  d.splits = pick_splits(tiles, Ppix / 64);
+  return theia_gemm(&d, c.s);
+}
+
 // stride-1 3x3 conv as implicit GEMM over an NHWC tensor; weights packed [Cout][tap][Cin]
 int conv3x3(const Ctx& c, const bf16* x, const theia_conv_geom& g, const bf16* w, const float* bias, void* out,
             long long ldo, int Cout, int epi, float* stats, const void* aux) {
@@ -477,17 +578,26 @@ extern "C" int theia_model_pack(theia_model* m, void* stream) {
     // dgrad pack D[ci][tap][co] = Wt[ci][co][tap]
     TRY(theia_gather4(c.W(p.padw), c.PB(w.padD), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
     // Conv2d weight [Cout][Cin][3][3]: fwd F[co][tap][ci]; dgrad D[ci][tap2][co] = W[co][ci][8-tap2]
-    TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1F), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
-    TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1D), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
-    TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2F), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
-    TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2D), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
+    if (p.hw == 16) {
+      TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1F), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
+      TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1D), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
+      TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2F), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
+      TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2D), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
+    } else {
+      // ConvTranspose2d(s2) weight [Cin][Cout][3][3] -> tap-major F[tap][co][ci] and D[tap][ci][co]
+      TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1F), 1, 0, 9, C, C, 1, 1, 9, C9, 0, 0, c.s));
+      TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1D), 1, 0, 9, C, C, 1, 1, C9, 9, 0, 0, c.s));
+      TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2F), 1, 0, 9, C, C, 1, 1, 9, C9, 0, 0, c.s));
+      TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2D), 1, 0, 9, C, C, 1, 1, C9, 9, 0, 0, c.s));
+    }
     TRY(theia_cast_bf16(c.W(p.lw), c.PB(w.l), 1LL * p.ct * C, c.s));
     TRY(theia_transpose_cast_bf16(c.W(p.lw), c.PB(w.lT), p.ct, C, c.s));
-    // LN affine [C][16][16] -> [16*16][C]
+    // LN affine [C][Hv][Wv] -> NHWC [Hp][Wp][C] (zero padded for the 31x31 stage)
     const int gbp[3][2] = {{p.g0, p.b0}, {p.g1, p.b1}, {p.g2, p.b2}};
+    const int vv[3] = {16, p.v1, p.v2}, pp[3] = {16, p.p1, p.p2};
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 2; ++j)
-        TRY(theia_gather4(c.W(gbp[i][j]), c.PF(w.gb[i][j]), 1, 1, 1, 1, 256, C, 0, 0, 1, 256, 0, c.s));
+        TRY(theia_chw_to_hwc(c.W(gbp[i][j]), c.PF(w.gb[i][j]), C, vv[i], vv[i], pp[i], pp[i], c.s));
   }
   return THEIA_OK;
 }
@@ -547,13 +657,23 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
     // pad: ConvTranspose2d(3x3, s1) 14 -> 16 over the spatial tokens (CLS skipped by the base offset)
     conv_geom_16(g, C, 14, B, D, 14LL * D, 197LL * D, -2);
     TRY(conv3x3(c, c.AB(m->tokens) + D, g, c.PB(w.padF), c.W(p.padb), c.AB(a.padout), C, C, THEIA_EPI_STATS, st0, nullptr));
-    TRY(theia_ln3d_apply(c.AB(a.padout), st0, c.PF(w.gb[0][0]), c.PF(w.gb[0][1]), c.AB(a.ln0), B, 256 * C, 1e-5f, c.s));
-    conv_geom_16(g, C, 16, B, C, 16LL * C, 256LL * C, -1);
-    TRY(conv3x3(c, c.AB(a.ln0), g, c.PB(w.c1F), c.W(p.c1b), c.AB(a.c1), C, C, THEIA_EPI_RELU | THEIA_EPI_STATS, st1, nullptr));
-    TRY(theia_ln3d_apply(c.AB(a.c1), st1, c.PF(w.gb[1][0]), c.PF(w.gb[1][1]), c.AB(a.ln1), B, 256 * C, 1e-5f, c.s));
-    TRY(conv3x3(c, c.AB(a.ln1), g, c.PB(w.c2F), c.W(p.c2b), c.AB(a.c2), C, C, THEIA_EPI_RELU | THEIA_EPI_STATS, st2, nullptr));
-    TRY(theia_ln3d_apply(c.AB(a.c2), st2, c.PF(w.gb[2][0]), c.PF(w.gb[2][1]), c.AB(a.ln2), B, 256 * C, 1e-5f, c.s));
-    TRY(linear(c, c.AB(a.ln2), c.PB(w.l), c.W(p.lb), preds[t], P, p.ct, C, THEIA_EPI_OUT_F32));
+    TRY(theia_ln3d_apply(c.AB(a.padout), st0, c.PF(w.gb[0][0]), c.PF(w.gb[0][1]), c.AB(a.ln0), B, 256 * C, 1e-5f, C, 0,
+                         0, c.s));
+    if (p.hw == 16) {
+      conv_geom_16(g, C, 16, B, C, 16LL * C, 256LL * C, -1);
+      TRY(conv3x3(c, c.AB(a.ln0), g, c.PB(w.c1F), c.W(p.c1b), c.AB(a.c1), C, C, THEIA_EPI_RELU | THEIA_EPI_STATS, st1, nullptr));
+      TRY(theia_ln3d_apply(c.AB(a.c1), st1, c.PF(w.gb[1][0]), c.PF(w.gb[1][1]), c.AB(a.ln1), B, 256 * C, 1e-5f, C, 0, 0, c.s));
+      TRY(conv3x3(c, c.AB(a.ln1), g, c.PB(w.c2F), c.W(p.c2b), c.AB(a.c2), C, C, THEIA_EPI_RELU | THEIA_EPI_STATS, st2, nullptr));
+      TRY(theia_ln3d_apply(c.AB(a.c2), st2, c.PF(w.gb[2][0]), c.PF(w.gb[2][1]), c.AB(a.ln2), B, 256 * C, 1e-5f, C, 0, 0, c.s));
+      TRY(linear(c, c.AB(a.ln2), c.PB(w.l), c.W(p.lb), preds[t], P, p.ct, C, THEIA_EPI_OUT_F32));
+    } else {
+      // adapter_heads.py:304-315: ConvT(s2,p1) 16->31, ReLU, LN[C,31,31], ConvT(s2,op1) 31->64, ReLU, LN[C,64,64], Linear
+      TRY(convT2x_fwd(c, c.AB(a.ln0), 16, 16, c.PB(w.c1F), c.W(p.c1b), c.AB(a.c1), 31, 32, 1, C, B, st1));
+      TRY(theia_ln3d_apply(c.AB(a.c1), st1, c.PF(w.gb[1][0]), c.PF(w.gb[1][1]), c.AB(a.ln1), B, 1024 * C, 1e-5f, C, 32, 31, c.s));
+      TRY(convT2x_fwd(c, c.AB(a.ln1), 31, 32, c.PB(w.c2F), c.W(p.c2b), c.AB(a.c2), 64, 64, 0, C, B, st2));
+      TRY(theia_ln3d_apply(c.AB(a.c2), st2, c.PF(w.gb[2][0]), c.PF(w.gb[2][1]), c.AB(a.ln2), B, 4096 * C, 1e-5f, C, 0, 0, c.s));
+      TRY(linear(c, c.AB(a.ln2), c.PB(w.l), c.W(p.lb), preds[t], B * 4096, p.ct, C, THEIA_EPI_OUT_F32));
+    }
   }
   return THEIA_OK;
 }
@@ -585,10 +705,11 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     float* st0 = c.AF(a.stats);
     float* st1 = st0 + 2 * B;
     float* st2 = st1 + 2 * B;
+    const long long P2 = static_cast<long long>(B) * p.p2 * p.p2;  // rows of the last stage
     // Linear(C -> C_t)
-    TRY(wgrad(c, dp, c.AB(a.ln2), c.G(p.lw), P, p.ct, C));
-    TRY(theia_colsum(dp, c.G(p.lb), P, p.ct, p.ct, 0, c.s));
-    TRY(linear(c, dp, c.PB(w.lT), nullptr, dA0, P, C, p.ct, 0));
+    TRY(wgrad(c, dp, c.AB(a.ln2), c.G(p.lw), static_cast<int>(P2), p.ct, C));
+    TRY(theia_colsum(dp, c.G(p.lb), static_cast<int>(P2), p.ct, p.ct, 0, c.s));
+    TRY(linear(c, dp, c.PB(w.lT), nullptr, dA0, static_cast<int>(P2), C, p.ct, 0));
     theia_conv_geom g;
     const int gbp[3][2] = {{p.g0, p.b0}, {p.g1, p.b1}, {p.g2, p.b2}};
     const bf16* lnin[3] = {c.AB(a.padout), c.AB(a.c1), c.AB(a.c2)};
@@ -597,22 +718,32 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     const int convw[3] = {p.padw, p.c1w, p.c2w};
     const int convb[3] = {p.padb, p.c1b, p.c2b};
     const long long convD[3] = {w.padD, w.c1D, w.c2D};
+    const int vv[3] = {16, p.v1, p.v2}, pp[3] = {16, p.p1, p.p2};
     for (int i = 2; i >= 0; --i) {
-      // LayerNorm([C,16,16]) backward (+ ReLU mask of the conv that produced its input)
-      TRY(zero_f32(c, gbs, 2LL * 256 * C));
-      TRY(theia_ln3d_bwd(dA0, lnin[i], sts[i], c.PF(w.gb[i][0]), red, dA1, gbs, gbs + 256 * C, B, 256 * C, 1e-5f,
-                         i > 0 ? 1 : 0, c.s));
-      TRY(theia_gather4(gbs, c.G(gbp[i][0]), 1, 1, 1, C, 16, 16, 0, 1, 16LL * C, C, 0, c.s));
-      TRY(theia_gather4(gbs + 256 * C, c.G(gbp[i][1]), 1, 1, 1, C, 16, 16, 0, 1, 16LL * C, C, 0, c.s));
+      // LayerNorm([C,H,W]) backward (+ ReLU mask of the conv that produced its input)
+      const long long npix = 1LL * pp[i] * pp[i];
+      const int rows = static_cast<int>(B * npix);
+      TRY(zero_f32(c, gbs, 2 * npix * C));
+      TRY(theia_ln3d_bwd(dA0, lnin[i], sts[i], c.PF(w.gb[i][0]), red, dA1, gbs, gbs + npix * C, B,
+                         static_cast<int>(npix * C), 1e-5f, i > 0 ? 1 : 0, C, pp[i] != vv[i] ? pp[i] : 0, vv[i], c.s));
+      TRY(theia_hwc_to_chw(gbs, c.G(gbp[i][0]), C, vv[i], vv[i], pp[i], pp[i], c.s));
+      TRY(theia_hwc_to_chw(gbs + npix * C, c.G(gbp[i][1]), C, vv[i], vv[i], pp[i], pp[i], c.s));
       // conv i backward: dA1 = gradient of its (pre-activation) output
-      TRY(theia_colsum(dA1, c.G(convb[i]), P, C, C, 0, c.s));
+      TRY(theia_colsum(dA1, c.G(convb[i]), rows, C, C, 0, c.s));
       TRY(zero_f32(c, wsc, 9LL * C * C));
-      if (i > 0) {
+      if (i > 0 && p.hw == 16) {
         conv_geom_16(g, C, 16, B, C, 16LL * C, 256LL * C, -1);
         TRY(conv_wgrad(c, dA1, convin[i], g, wsc, C));
         // grad W[co][ci][tap] = ws[tap][co][ci]
         TRY(theia_gather4(wsc, c.G(convw[i]), 1, 1, C, C, 9, 1, C, 1, 1LL * C * C, 0, 0, c.s));
         TRY(conv3x3(c, dA1, g, c.PB(convD[i]), nullptr, dA0, C, C, 0, nullptr, nullptr));
+      } else if (i > 0) {
+        // stride-2 ConvTranspose2d: input map vv[i-1] (pitch pp[i-1]) -> output map vv[i] (pitch pp[i])
+        const int pad = i == 1 ? 1 : 0;
+        TRY(convT2x_wgrad(c, convin[i], dA1, wsc, C, B, vv[i - 1], pp[i - 1], vv[i], pp[i], pad));
+        // grad Wt[ci][co][tap] = ws[tap][ci][co]
+        TRY(theia_gather4(wsc, c.G(convw[i]), 1, 1, C, C, 9, 1, C, 1, 1LL * C * C, 0, 0, c.s));
+        TRY(convT2x_dgrad(c, dA1, c.PB(convD[i]), dA0, C, B, vv[i - 1], pp[i - 1], vv[i], pp[i], pad));
       } else {
         conv_geom_16(g, C, 14, B, D, 14LL * D, 197LL * D, -2);
         TRY(conv_wgrad(c, dA1, c.AB(m->tokens) + D, g, wsc, C));
