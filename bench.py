@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--backbone", default="base", choices=list(BACKBONES))
     ap.add_argument("--teachers", default="cdiv")
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--gemm-csv", default=None, help="dump per-launch GEMM timings of the timed region")
@@ -310,8 +310,12 @@ def main():
     gemm_alg_tflop = 3.0 * (fwd_g - attn_g) * B / 1e3  # algorithmic GEMM/conv FLOPs of one step (3x forward)
     achieved = gemm_alg_tflop / (gemm_ms_step / 1e3) if gemm_ms_step > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.backbone == "base":
+        traffic = json.load(open(tpath)).get("traffic_bytes_per_launch_mean")  # ncu --set full capture, see profiles/
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv, all instances)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src + ", sustained figure (kernel timed inside a long step)",
                 "launches_per_step": pn.value / args.steps, "kernel_ms_per_step": gemm_ms_step,
                 "kernel_share_of_step": gemm_ms_step / ms_step,
@@ -328,7 +332,7 @@ def main():
         ic, tc = O.synthetic_batch(cfgO, Bc, seed=0)
         O.distill_step(Pc, ic, tc, cfgO, do_resize=False)  # warm-up
         t0 = time.perf_counter()
-        nrep = 2
+        nrep = 1
         for _ in range(nrep):
             O.distill_step(Pc, ic, tc, cfgO, do_resize=False)
         dt = (time.perf_counter() - t0) / nrep
