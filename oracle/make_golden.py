@@ -69,6 +69,7 @@ CASES = [
     ("tiny_dinov2_b2", "facebook/deit-tiny-patch16-224", "dinov2", 2, False),
     ("tiny_cdiv_b2_resize", "facebook/deit-tiny-patch16-224", "cdiv", 2, True),
     ("tiny_cddsv_b1", "facebook/deit-tiny-patch16-224", "cddsv", 1, False),
+    ("tiny_dinov2_cls_b3", "facebook/deit-tiny-patch16-224", "dinov2+cls", 3, False),  # distill_cls (train_rvfm.py:239-246)
 ]
 
 
@@ -77,7 +78,7 @@ def main():
     os.makedirs(os.path.join(os.path.dirname(HERE), "tests", "golden"), exist_ok=True)
     torch.manual_seed(0)
     for name, backbone, tset, B, do_resize in CASES:
-        cfg = O.make_config(backbone, tset)
+        cfg = O.make_config(backbone, tset.replace("+cls", ""), distill_cls=tset.endswith("+cls"))
         P = O.init_params(cfg, seed=0)
         ref = RobotVisionFM(backbone=backbone, pretrained=False, translator="lconv",
                             target_feature_sizes=dict(cfg.teachers), translator_kwargs={"hidden_size_factor": 1.0})

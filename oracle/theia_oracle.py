@@ -82,11 +82,20 @@ class OracleConfig:
         return (self.image // self.patch) ** 2 + 1
 
 
-def make_config(backbone: str, teachers) -> OracleConfig:
+def make_config(backbone: str, teachers, distill_cls: bool = False) -> OracleConfig:
+    """distill_cls: train_rvfm.py:239-246 -- ViT / DINOv2 / CLIP teachers also get a '<name>_cls' target of size
+    (C_t,) predicted by a LinearAdapterHead on the CLS token."""
     d, h = BACKBONES[backbone]
     if isinstance(teachers, str):
         teachers = TEACHER_SETS[teachers]
-    return OracleConfig(hidden=d, heads=h, teachers={t: MODEL_FEATURE_SIZES[t] for t in teachers})
+    sizes = {}
+    for t in teachers:
+        sizes[t] = MODEL_FEATURE_SIZES[t[:-4]][:1] if t.endswith("_cls") else MODEL_FEATURE_SIZES[t]
+    if distill_cls:
+        for t in list(teachers):
+            if "google/vit" in t or "facebook/dino" in t or "openai/clip" in t:
+                sizes[t + "_cls"] = MODEL_FEATURE_SIZES[t][:1]
+    return OracleConfig(hidden=d, heads=h, teachers=sizes)
 
 
 def _r(x: torch.Tensor, cfg: "OracleConfig") -> torch.Tensor:
@@ -128,8 +137,13 @@ def param_shapes(cfg: OracleConfig) -> dict:
     s["backbone.model.layernorm.weight"] = (D,)
     s["backbone.model.layernorm.bias"] = (D,)
     C = D  # hidden_size_factor 1.0 (configs/model/translator/lconv.yaml:3)
-    for t, (ct, ht, wt) in cfg.teachers.items():
+    for t, size in cfg.teachers.items():
         p = f"translator.translator_heads.{head_key(t)}."
+        if len(size) == 1:  # LinearAdapterHead (adapter_heads.py:28-58)
+            s[p + "adapter.0.weight"] = (size[0], C)
+            s[p + "adapter.0.bias"] = (size[0],)
+            continue
+        ct, ht, wt = size
         s[p + "pad.1.weight"] = (C, C, 3, 3)  # ConvTranspose2d: [Cin, Cout, kh, kw]
         s[p + "pad.1.bias"] = (C,)
         if ht == 16:
@@ -165,7 +179,7 @@ def init_params(cfg: OracleConfig, seed: int = 0, dtype=torch.float32) -> dict:
             else:
                 v = 0.02 * torch.randn(shp, generator=g).clamp_(-2, 2)
         else:
-            if "adapter.0" in k or "adapter.3" in k or "adapter.6" in k:  # LN[C,H,W] affine
+            if len(shp) == 3:  # LN[C,H,W] affine
                 v = (1.0 if k.endswith("weight") else 0.0) + 0.1 * torch.randn(shp, generator=g)
             else:
                 fan_in = shp[1] * (9 if len(shp) == 4 else 1) if len(shp) > 1 else cfg.hidden * 9
@@ -265,9 +279,12 @@ def vit_forward(P: dict, pix: torch.Tensor, cfg: OracleConfig, taps: Optional[di
 
 def lconv_head_forward(P: dict, t: str, x: torch.Tensor, cfg: OracleConfig, taps: Optional[dict] = None,
                        force: Optional[dict] = None) -> torch.Tensor:
-    """LightConvAdapterHead.forward (adapter_heads.py:352-359) for a 14x14 source."""
-    ct, ht, wt = cfg.teachers[t]
+    """LightConvAdapterHead.forward (adapter_heads.py:352-359) for a 14x14 source; LinearAdapterHead.forward
+    (adapter_heads.py:51-58) for '<name>_cls' targets."""
     p = f"translator.translator_heads.{head_key(t)}."
+    if len(cfg.teachers[t]) == 1:
+        return F.linear(x[:, 0], _r(P[p + "adapter.0.weight"], cfg), P[p + "adapter.0.bias"])
+    ct, ht, wt = cfg.teachers[t]
     B, C = x.shape[0], x.shape[2]
     g = cfg.image // cfg.patch
     y = x[:, 1:].reshape(B, g, g, C).permute(0, 3, 1, 2)  # drop CLS; b (h w) c -> b c h w
@@ -395,6 +412,6 @@ def synthetic_batch(cfg: OracleConfig, B: int, seed: int = 0, device="cpu"):
     g = torch.Generator().manual_seed(1000 + seed)
     images = torch.randint(0, 256, (B, cfg.image, cfg.image, 3), dtype=torch.uint8, generator=g)
     g2 = torch.Generator().manual_seed(2000 + seed)
-    targets = {t: torch.randn((B, h * w, c), generator=g2).to(torch.bfloat16).float()
-               for t, (c, h, w) in cfg.teachers.items()}
+    targets = {t: torch.randn((B, sz[1] * sz[2], sz[0]) if len(sz) == 3 else (B, sz[0]), generator=g2)
+               .to(torch.bfloat16).float() for t, sz in cfg.teachers.items()}
     return images.to(device), {k: v.to(device) for k, v in targets.items()}

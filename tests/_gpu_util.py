@@ -32,7 +32,10 @@ def fetch_all(m, cfg, B):
         for name, w in (("ln1", D), ("qkv", 3 * D), ("attn", D), ("xmid", D), ("ln2", D), ("h", 4 * D), ("a", 4 * D)):
             out[(name, l)] = fetch(m, name, l, (B, 197, w))
         out[("x", l + 1)] = fetch(m, "x", l + 1, (B, 197, D))
-    for i, (t, (ct, ht, wt)) in enumerate(cfg.teachers.items()):
+    for i, (t, size) in enumerate(cfg.teachers.items()):
+        if len(size) == 1:
+            continue  # CLS head: a single Linear, nothing stored
+        ht = size[1]
         v1, p1, v2 = (16, 16, 16) if ht == 16 else (31, 32, 64)
         for name in ("padout", "hln0"):
             out[(name, t)] = fetch(m, name, i, (B, 16, 16, D))

@@ -39,7 +39,10 @@ def relerr(a, b):
 
 
 def build(backbone, tset, seed=0, max_batch=0):
-    cfg = O.make_config(backbone, tset)
+    if isinstance(tset, str) and tset.endswith("+cls"):
+        cfg = O.make_config(backbone, tset[:-4], distill_cls=True)
+    else:
+        cfg = O.make_config(backbone, tset)
     P = O.init_params(cfg, seed=seed)
     m = RobotVisionFM(backbone=backbone, translator="lconv", target_feature_sizes=dict(cfg.teachers),
                       translator_kwargs={"hidden_size_factor": 1.0}, max_batch=max_batch)
@@ -68,7 +71,8 @@ def test_readme_quickstart_zeros():
 @pytest.mark.parametrize("backbone,tset,B", [("facebook/deit-tiny-patch16-224", "dinov2", 2),
                                              ("facebook/deit-tiny-patch16-224", "cdiv", 3),
                                              ("facebook/deit-small-patch16-224", "dinov2", 5),
-                                             ("facebook/deit-tiny-patch16-224", "cddsv", 2)])
+                                             ("facebook/deit-tiny-patch16-224", "cddsv", 2),
+                                             ("facebook/deit-tiny-patch16-224", "cdiv+cls", 3)])
 def test_distill_step_parity_vs_oracle(backbone, tset, B):
     cfg, P, m = build(backbone, tset)
     images, targets = O.synthetic_batch(cfg, B, seed=0, device=DEV)
@@ -178,6 +182,20 @@ def test_cddsv_64x64_heads_against_reference_golden():
     g = dict(m.named_parameters())
     for k, s in fx["grad_sample"].items():
         assert relerr(_sl(g[k].grad).cpu(), s) < 0.3, k
+
+
+def test_cls_distillation_heads_against_reference_golden():
+    """distill_cls (train_rvfm.py:239-246): '<teacher>_cls' targets predicted from the CLS token by a Linear head."""
+    fx = torch.load(os.path.join(GOLDEN, "tiny_dinov2_cls_b3.pt"), weights_only=False)
+    cfg, P, m = build(fx["backbone"], fx["teachers"], seed=fx["seed"])
+    images, targets = O.synthetic_batch(cfg, fx["B"], seed=fx["seed"], device=DEV)
+    pred = m(images, **fx["kwargs"])
+    assert tuple(pred["facebook/dinov2-large_cls"].shape) == (fx["B"], 1024)
+    for t, gq in fx["pred"].items():
+        assert relerr(_sl(pred[t]).cpu(), gq["sample"]) < 3e-2, t
+    losses = m.get_loss(pred, targets)
+    for k, v in fx["losses"].items():
+        assert abs(float(losses[k]) - v) <= 1e-3 * abs(v), k
 
 
 def test_training_reduces_loss_and_repacks_weights():

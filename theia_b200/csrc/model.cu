@@ -133,8 +133,8 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   if (cfg->image != 224 || cfg->patch != 16) return set_error(THEIA_ERR_UNSUPPORTED, "only 224/16 ViT geometry");
   if (cfg->num_teachers < 0 || cfg->num_teachers > THEIA_MAX_TEACHERS) return set_error(THEIA_ERR_ARG, "num_teachers");
   for (int t = 0; t < cfg->num_teachers; ++t) {
-    if (cfg->teacher_hw[t] != 16 && cfg->teacher_hw[t] != 64)
-      return set_error(THEIA_ERR_UNSUPPORTED, "teacher %s: target maps must be 16x16 or 64x64 (got %d)",
+    if (cfg->teacher_hw[t] != 16 && cfg->teacher_hw[t] != 64 && cfg->teacher_hw[t] != 1)
+      return set_error(THEIA_ERR_UNSUPPORTED, "teacher %s: target maps must be 16x16, 64x64 or a CLS vector (got %d)",
                        cfg->teacher_names[t], cfg->teacher_hw[t]);
     if (cfg->teacher_c[t] % 8 != 0) return set_error(THEIA_ERR_UNSUPPORTED, "teacher channels %% 8 != 0");
   }
@@ -180,6 +180,14 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
     HeadP q;
     q.ct = cfg->teacher_c[t];
     q.hw = cfg->teacher_hw[t];
+    if (q.hw == 1) {  // LinearAdapterHead on the CLS token (adapter_heads.py:28-58; train_rvfm.py:239-246)
+      q.v1 = q.p1 = q.v2 = q.p2 = 0;
+      q.padw = q.padb = q.g0 = q.b0 = q.c1w = q.c1b = q.g1 = q.b1 = q.c2w = q.c2b = q.g2 = q.b2 = -1;
+      q.lw = add_param(m, p + "adapter.0.weight", {q.ct, C});
+      q.lb = add_param(m, p + "adapter.0.bias", {q.ct});
+      m->hp.push_back(q);
+      continue;
+    }
     q.v1 = q.hw == 16 ? 16 : 31, q.p1 = q.hw == 16 ? 16 : 32;
     q.v2 = q.hw == 16 ? 16 : 64, q.p2 = q.v2;
     q.padw = add_param(m, p + "pad.1.weight", {C, C, 3, 3});
@@ -219,6 +227,13 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   }
   for (int t = 0; t < T; ++t) {
     HeadW w;
+    memset(&w, 0, sizeof(w));
+    if (m->hp[t].hw == 1) {
+      w.l = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
+      w.lT = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
+      m->hw.push_back(w);
+      continue;
+    }
     const long long W9 = 9LL * C * C;
     w.padF = pb.take(W9, AL);
     w.padD = pb.take(W9, AL);
@@ -258,6 +273,11 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   long long Pmax = P;
   for (int t = 0; t < T; ++t) {
     HeadA a;
+    memset(&a, 0, sizeof(a));
+    if (m->hp[t].hw == 1) {
+      m->ha.push_back(a);
+      continue;
+    }
     const long long P1 = static_cast<long long>(B) * m->hp[t].p1 * m->hp[t].p1;
     const long long P2 = static_cast<long long>(B) * m->hp[t].p2 * m->hp[t].p2;
     if (P2 > Pmax) Pmax = P2;
@@ -572,6 +592,11 @@ extern "C" int theia_model_pack(theia_model* m, void* stream) {
   for (int t = 0; t < m->T; ++t) {
     const HeadP& p = m->hp[t];
     const HeadW& w = m->hw[t];
+    if (p.hw == 1) {
+      TRY(theia_cast_bf16(c.W(p.lw), c.PB(w.l), 1LL * p.ct * C, c.s));
+      TRY(theia_transpose_cast_bf16(c.W(p.lw), c.PB(w.lT), p.ct, C, c.s));
+      continue;
+    }
     const long long C9 = 9LL * C;
     // ConvTranspose2d weight [Cin][Cout][3][3]: fwd pack F[co][tap2][ci] = Wt[ci][co][8-tap2]
     TRY(theia_gather4(c.W(p.padw), c.PB(w.padF), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
@@ -649,6 +674,13 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
     const HeadP& p = m->hp[t];
     const HeadW& w = m->hw[t];
     const HeadA& a = m->ha[t];
+    if (p.hw == 1) {  // pred[B, C_t] = tokens[:, 0] W^T + b : rows of A are the CLS rows (pitch 197*D)
+      theia_gemm_desc d = gemm_base(B, p.ct, C);
+      d.A = c.AB(m->tokens), d.lda = 197LL * D, d.B = c.PB(w.l), d.ldb = C;
+      d.out = preds[t], d.ldo = p.ct, d.bias = c.W(p.lb), d.epi = THEIA_EPI_OUT_F32;
+      TRY(theia_gemm(&d, c.s));
+      continue;
+    }
     float* st0 = c.AF(a.stats);
     float* st1 = st0 + 2 * B;
     float* st2 = st1 + 2 * B;
@@ -702,6 +734,23 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     const HeadW& w = m->hw[t];
     const HeadA& a = m->ha[t];
     const bf16* dp = static_cast<const bf16*>(dpreds[t]);
+    if (p.hw == 1) {
+      {  // dW[C_t, C] = dp^T cls_tokens
+        theia_gemm_desc d = gemm_base(p.ct, C, B);
+        d.a_mode = THEIA_OP_MN2D, d.b_mode = THEIA_OP_MN2D;
+        d.A = dp, d.lda = p.ct, d.B = c.AB(m->tokens), d.ldb = 197LL * D;
+        d.out = c.G(p.lw), d.ldo = C, d.epi = THEIA_EPI_ATOMIC;
+        TRY(theia_gemm(&d, c.s));
+      }
+      TRY(theia_colsum(dp, c.G(p.lb), B, p.ct, p.ct, 0, c.s));
+      {  // d tokens[:, 0] += dp W
+        theia_gemm_desc d = gemm_base(B, C, p.ct);
+        d.A = dp, d.lda = p.ct, d.B = c.PB(w.lT), d.ldb = p.ct;
+        d.out = c.AB(m->dtok), d.ldo = 197LL * D, d.epi = THEIA_EPI_RESID, d.aux = c.AB(m->dtok);
+        TRY(theia_gemm(&d, c.s));
+      }
+      continue;
+    }
     float* st0 = c.AF(a.stats);
     float* st1 = st0 + 2 * B;
     float* st2 = st1 + 2 * B;

@@ -156,9 +156,6 @@ class RobotVisionFM(nn.Module):
         self.hidden, self.heads = BACKBONES[backbone]
         self.image_mean, self.image_std = IMAGE_MEAN, IMAGE_STD
         self._teachers = list(target_feature_sizes.keys()) if target_feature_sizes else []
-        for t in self._teachers:
-            if "_cls" in t:
-                raise NotImplementedError("CLS-token distillation heads (LinearAdapterHead) are not built yet")
         self._max_batch = int(kwargs.pop("max_batch", 0))
         self._handle = None
         self._handle_batch = 0
@@ -206,7 +203,11 @@ class RobotVisionFM(nn.Module):
             raise NotImplementedError("too many teachers")
         self._name_keepalive = [t.encode() for t in self._teachers]
         for i, t in enumerate(self._teachers):
-            c, hh, ww = self.target_feature_sizes[t]
+            size = tuple(self.target_feature_sizes[t])
+            if len(size) == 1 or "_cls" in t:  # LinearAdapterHead on the CLS token (feature_translators.py:195-199)
+                c, hh, ww = size[0], 1, 1
+            else:
+                c, hh, ww = size
             if hh != ww:
                 raise NotImplementedError("Currently does not support non-square feature maps")
             cfg.teacher_names[i] = self._name_keepalive[i]
@@ -341,8 +342,9 @@ class RobotVisionFM(nn.Module):
         if run_heads:
             for i, t in enumerate(self._teachers):
                 if t in names:
-                    c, hh, ww = self.target_feature_sizes[t]
-                    p = torch.empty((B, hh * ww, c), dtype=torch.float32, device=images.device)
+                    size = tuple(self.target_feature_sizes[t])
+                    shape = (B, size[0]) if (len(size) == 1 or "_cls" in t) else (B, size[1] * size[2], size[0])
+                    p = torch.empty(shape, dtype=torch.float32, device=images.device)
                     preds.append(p)
                     ptrs[i] = p.data_ptr()
         self._fwd_id += 1
