@@ -45,12 +45,12 @@ enum {
 };
 
 enum {
-  THEIA_EPI_GELU = 1 << 1,      /* out2 = bf16(v) (pre-activation), v = gelu(v)                     */
+  THEIA_EPI_GELU = 1 << 1,      /* out2 = bf16(gelu'(v)) (saved for backward), v = gelu(v)          */
   THEIA_EPI_RELU = 1 << 2,      /* v = max(v, 0)                                                    */
   THEIA_EPI_RESID = 1 << 3,     /* v += aux[m,n]        (aux may alias out: accumulate)             */
   THEIA_EPI_OUT_F32 = 1 << 4,   /* store fp32 instead of bf16                                       */
   THEIA_EPI_ATOMIC = 1 << 5,    /* fp32 atomicAdd into out (split-K wgrad)                          */
-  THEIA_EPI_MUL_DGELU = 1 << 6, /* v *= gelu'(aux[m,n])                                             */
+  THEIA_EPI_MUL_AUX = 1 << 6,   /* v *= aux[m,n]   (backward of GELU with the saved derivative)      */
   THEIA_EPI_MUL_RELUMASK = 1 << 7, /* v = aux[m,n] > 0 ? v : 0                                      */
   THEIA_EPI_POSCLS = 1 << 8,    /* token t = m % tokens: t==0 ? cls[n]+pos[0,n] : v + pos[t,n]      */
   THEIA_EPI_STATS = 1 << 9,     /* per-image sum / sum-of-squares of the stored values -> stats     */
@@ -85,7 +85,7 @@ typedef struct theia_gemm_desc {
   int epi;          /* THEIA_EPI_* flags */
   void* out;        /* bf16 (default) or fp32 */
   long long ldo;
-  void* out2;       /* GELU: pre-activation, bf16, same shape as out */
+  void* out2;       /* GELU: gelu'(pre-activation), bf16, same shape as out */
   const float* bias;/* [N] or NULL */
   const void* aux;  /* bf16, indexed like out */
   const float* pos; /* POSCLS: [tokens, N] */

@@ -29,7 +29,8 @@ def fetch_all(m, cfg, B):
     D = cfg.hidden
     out = {("x", 0): fetch(m, "x", 0, (B, 197, D)), ("tokens", 0): fetch(m, "tokens", 0, (B, 197, D))}
     for l in range(cfg.layers):
-        for name, w in (("ln1", D), ("qkv", 3 * D), ("attn", D), ("xmid", D), ("ln2", D), ("h", 4 * D), ("a", 4 * D)):
+        # ("h" holds gelu'(pre-activation) in the CUDA path, not the pre-activation: it is not forced)
+        for name, w in (("ln1", D), ("qkv", 3 * D), ("attn", D), ("xmid", D), ("ln2", D), ("a", 4 * D)):
             out[(name, l)] = fetch(m, name, l, (B, 197, w))
         out[("x", l + 1)] = fetch(m, "x", l + 1, (B, 197, D))
     for i, (t, size) in enumerate(cfg.teachers.items()):

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_PKG, "libtheia_b200.so")
 
 OP_K2D, OP_MN2D, OP_CONV_K, OP_CONV_MN = 0, 1, 2, 3
 EPI_GELU, EPI_RELU, EPI_RESID, EPI_OUT_F32, EPI_ATOMIC = 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5
-EPI_MUL_DGELU, EPI_MUL_RELUMASK, EPI_POSCLS, EPI_STATS, EPI_COLSUM = 1 << 6, 1 << 7, 1 << 8, 1 << 9, 1 << 10
+EPI_MUL_AUX, EPI_MUL_RELUMASK, EPI_POSCLS, EPI_STATS, EPI_COLSUM = 1 << 6, 1 << 7, 1 << 8, 1 << 9, 1 << 10
 MAX_TEACHERS = 8
 
 

@@ -64,7 +64,7 @@ constexpr int SMEM_LIMIT = 232448;  // 227 KB
 
 constexpr int AUX_SLOTS = 3;                                  // per-warp ring depth (32x32 bf16 chunks)
 constexpr int AUX_RING_BYTES = EPI_WARPS * AUX_SLOTS * 2048;  // 48 KB
-constexpr int AUXF = THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK;
+constexpr int AUXF = THEIA_EPI_RESID | THEIA_EPI_MUL_AUX | THEIA_EPI_MUL_RELUMASK;
 
 template <int BN, bool RING>
 struct Cfg {
@@ -428,16 +428,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if (epi & THEIA_EPI_GELU) {
+            // gelu(x) = x Phi(x); its derivative Phi(x) + x phi(x) is stored (bf16) for the backward pass, so
+            // the dgrad epilogue is a plain multiply instead of a second erf/exp evaluation
+            float cdf[16], pdf[16];
+            normal_cdf_pdf<16, true>(xv, cdf, pdf);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int i = half * 4 + j;
-              uint2 pre;
-              pre.x = pack_bf16x2(xv[4 * j + 0], xv[4 * j + 1]);
-              pre.y = pack_bf16x2(xv[4 * j + 2], xv[4 * j + 3]);
-              if ((ok >> i) & 1u) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + rowoff[i] + n) = pre;
+              uint2 dg;
+              dg.x = pack_bf16x2(fmaf(xv[4 * j + 0], pdf[4 * j + 0], cdf[4 * j + 0]),
+                                 fmaf(xv[4 * j + 1], pdf[4 * j + 1], cdf[4 * j + 1]));
+              dg.y = pack_bf16x2(fmaf(xv[4 * j + 2], pdf[4 * j + 2], cdf[4 * j + 2]),
+                                 fmaf(xv[4 * j + 3], pdf[4 * j + 3], cdf[4 * j + 3]));
+              if ((ok >> i) & 1u) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + rowoff[i] + n) = dg;
             }
-            float cdf[16], pdf[16];
-            normal_cdf_pdf<16, false>(xv, cdf, pdf);
 #pragma unroll
             for (int k = 0; k < 16; ++k) xv[k] *= cdf[k];
           }
@@ -452,11 +456,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float2 a01 = unpack_bf16x2(aux[half * 4 + j].x), a23 = unpack_bf16x2(aux[half * 4 + j].y);
               av[4 * j + 0] = a01.x, av[4 * j + 1] = a01.y, av[4 * j + 2] = a23.x, av[4 * j + 3] = a23.y;
             }
-            if (epi & THEIA_EPI_MUL_DGELU) {
-              float cdf[16], pdf[16];
-              normal_cdf_pdf<16, true>(av, cdf, pdf);
+            if (epi & THEIA_EPI_MUL_AUX) {
 #pragma unroll
-              for (int k = 0; k < 16; ++k) xv[k] *= fmaf(av[k], pdf[k], cdf[k]);
+              for (int k = 0; k < 16; ++k) xv[k] *= av[k];
             } else if (epi & THEIA_EPI_MUL_RELUMASK) {
 #pragma unroll
               for (int k = 0; k < 16; ++k) xv[k] = av[k] > 0.f ? xv[k] : 0.f;
@@ -597,8 +599,8 @@ static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK&
     THEIA_EPI_CASE(THEIA_EPI_RESID)
     THEIA_EPI_CASE(THEIA_EPI_OUT_F32)
     THEIA_EPI_CASE(THEIA_EPI_ATOMIC)
-    THEIA_EPI_CASE(THEIA_EPI_MUL_DGELU)
-    THEIA_EPI_CASE(THEIA_EPI_MUL_DGELU | THEIA_EPI_COLSUM)
+    THEIA_EPI_CASE(THEIA_EPI_MUL_AUX)
+    THEIA_EPI_CASE(THEIA_EPI_MUL_AUX | THEIA_EPI_COLSUM)
     THEIA_EPI_CASE(THEIA_EPI_POSCLS)
     THEIA_EPI_CASE(THEIA_EPI_STATS)
     THEIA_EPI_CASE(THEIA_EPI_RELU | THEIA_EPI_STATS)
@@ -700,7 +702,7 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   k.splits = d->splits > 0 ? d->splits : 1;
   if (k.splits > 1 && !(d->epi & THEIA_EPI_ATOMIC)) return set_error(THEIA_ERR_ARG, "split-K needs EPI_ATOMIC");
   if ((d->epi & THEIA_EPI_GELU) && !d->out2) return set_error(THEIA_ERR_ARG, "EPI_GELU needs out2");
-  if ((d->epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_DGELU | THEIA_EPI_MUL_RELUMASK)) && !d->aux)
+  if ((d->epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_AUX | THEIA_EPI_MUL_RELUMASK)) && !d->aux)
     return set_error(THEIA_ERR_ARG, "epilogue needs aux");
   if ((d->epi & THEIA_EPI_POSCLS) && (!d->pos || !d->cls)) return set_error(THEIA_ERR_ARG, "POSCLS needs pos/cls");
   if ((d->epi & THEIA_EPI_COLSUM) && !d->colsum) return set_error(THEIA_ERR_ARG, "COLSUM needs colsum");

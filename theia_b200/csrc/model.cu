@@ -44,7 +44,7 @@ struct HeadW {
 };
 
 struct LayerA {
-  long long ln1, qkv, attn, xmid, ln2, h, a;  // bf16 element offsets
+  long long ln1, qkv, attn, xmid, ln2, h, a;  // bf16 element offsets (h holds gelu'(pre-activation))
   long long mean1, rstd1, mean2, rstd2, lse;  // fp32 element offsets
 };
 struct HeadA {
@@ -414,12 +414,22 @@ int linear(const Ctx& c, const bf16* x, const bf16* w, const float* bias, void* 
   return theia_gemm(&d, c.s);
 }
 
+// split-K factor for a wgrad GEMM: fill whole waves of the persistent grid (tiles*splits close to a multiple of
+// the SM count) with at least 8 K-blocks per split; fewer splits win ties (each split adds a tile of atomics)
 int pick_splits(int tiles, int num_kb) {
-  int s = (2 * num_sms() + tiles - 1) / tiles;
+  const int sms = num_sms();
   const int maxs = num_kb / 8 > 0 ? num_kb / 8 : 1;
-  if (s > maxs) s = maxs;
-  if (s < 1) s = 1;
-  return s;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= maxs && s <= 64; ++s) {
+    const long long items = 1LL * tiles * s;
+    const long long waves = (items + sms - 1) / sms;
+    const double eff = static_cast<double>(items) / (waves * sms);
+    if (items < sms && s < maxs) continue;  // do not leave SMs idle when more splits are possible
+    if (eff > best_eff + 0.02) best_eff = eff, best = s;
+    if (items >= 4LL * sms && eff > 0.9) break;
+  }
+  return best;
 }
 
 // dW[Nout,Kin] += dY[Mtok,Nout]^T * X[Mtok,Kin]   (fp32 atomics, split-K over tokens)
@@ -818,7 +828,7 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     const LayerA& a = m->la[l];
     // MLP
     TRY(wgrad(c, dx, c.AB(a.a), c.G(p.f2w), M, D, 4 * D));
-    TRY(linear(c, dx, c.PB(w.w2T), nullptr, c.AB(m->dh), M, 4 * D, D, THEIA_EPI_MUL_DGELU | THEIA_EPI_COLSUM,
+    TRY(linear(c, dx, c.PB(w.w2T), nullptr, c.AB(m->dh), M, 4 * D, D, THEIA_EPI_MUL_AUX | THEIA_EPI_COLSUM,
                c.AB(a.h), nullptr, c.G(p.f1b)));
     TRY(wgrad(c, c.AB(m->dh), c.AB(a.ln2), c.G(p.f1w), M, 4 * D, D));
     TRY(linear(c, c.AB(m->dh), c.PB(w.w1T), nullptr, c.AB(m->dln), M, D, 4 * D, 0));

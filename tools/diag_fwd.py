@@ -52,7 +52,7 @@ D = cfg.hidden
 print(f"{'stage':16s} vs_fp32    vs_bf16emu   (fp32 vs emu)")
 rows = [("x", 0)]
 for l in (0, 1, 5, 11):
-    rows += [("ln1", l), ("qkv", l), ("attn", l), ("xmid", l), ("ln2", l), ("h", l), ("a", l), ("x", l + 1)]
+    rows += [("ln1", l), ("qkv", l), ("attn", l), ("xmid", l), ("ln2", l), ("a", l), ("x", l + 1)]
 for name, l in rows:
     width = {"qkv": 3 * D, "h": 4 * D, "a": 4 * D}.get(name, D)
     mine = fetch(name, l, (B, 197, width))
