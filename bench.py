@@ -139,7 +139,9 @@ def workload_config(args, B):
             "global_batch": B * args.gpus, "main_loss": "cos_l1",
             "preprocess": "rescale+normalize in-kernel, do_resize=False on both arms",
             "l2_policy": "per-step working set (>10 GB of activations at batch 256) far exceeds the 126 MB L2",
-            "parallelism": f"dp{args.gpus}"}
+            "parallelism": f"dp{args.gpus}" + ("" if args.gpus == 1 else
+                                               (" (one flat-buffer NCCL all-reduce per step)" if getattr(args, "dp_mode", "flat") == "flat"
+                                                else " (torch DDP wrapper, bucketed all-reduce)"))}
 
 
 def main():
@@ -154,6 +156,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dp-mode", default="flat", choices=["flat", "ddp"],
+                    help="N>1: one flat-buffer NCCL all-reduce issued by the module (default) or the reference's DDP wrapper")
     ap.add_argument("--gemm-csv", default=None, help="dump per-launch GEMM timings of the timed region")
     args = ap.parse_args()
 
@@ -175,6 +179,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
 
@@ -185,9 +191,12 @@ def main():
                           max_batch=B).to(dev)
     model.train()
     net = model
-    if world > 1:
+    if world > 1 and args.dp_mode == "ddp":
         from torch.nn.parallel import DistributedDataParallel as DDP
         net = DDP(model, device_ids=[local], find_unused_parameters=False)  # train_rvfm.py:258
+    elif world > 1:
+        dist.broadcast(model._flat, 0)  # what DDP's constructor does: rank 0's parameters everywhere
+        model.sync_gradients(True)      # single all-reduce (avg) over the flat gradient buffer inside backward()
     # lr rule of train_rvfm.py:299-301
     lr = 2e-3 * (B * world) / (64 * 8)
     decay, no_decay = [], []

@@ -45,6 +45,15 @@ def main():
     g_ref = torch.cat([p.grad.flatten() for p in ref.parameters()])
     rel = ((g_ddp - g_ref).norm() / g_ref.norm()).item()
     assert rel < 2e-2, f"rank {rank}: DDP grads differ from the {world}x batch run: rel {rel}"
+    # the module's own single flat all-reduce (no DDP wrapper) gives the same gradients
+    m2 = make()
+    m2.sync_gradients(True)
+    p2 = m2(images, do_resize=False)
+    l2 = m2.get_loss(p2, targets)
+    (0.9 * l2["cos_loss"] + 0.1 * l2["l1_loss"]).backward()
+    g_flat = torch.cat([p.grad.flatten() for p in m2.parameters()])
+    rel2 = ((g_flat - g_ref).norm() / g_ref.norm()).item()
+    assert rel2 < 2e-2, f"rank {rank}: flat all-reduce grads differ: rel {rel2}"
     # optimizer steps keep ranks bit-identical
     opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0.01, fused=True)
     for _ in range(3):

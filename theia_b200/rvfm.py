@@ -164,6 +164,7 @@ class RobotVisionFM(nn.Module):
         self._packed_version = None
         self._fwd_id = 0
         self._dpred_bf16 = {}
+        self._grad_sync = None  # (process group,) when the module all-reduces its own flat gradient buffer
 
         # layout comes from the library (host-only call; works without a GPU)
         h = self._create_handle(1)
@@ -283,6 +284,13 @@ class RobotVisionFM(nn.Module):
             pretrained_dict = {k: v for k, v in weights_dict.items() if k in self.state_dict()}
             self.load_state_dict(pretrained_dict, strict=False)
 
+    def sync_gradients(self, enabled: bool = True, group=None) -> None:
+        """Data-parallel alternative to wrapping the module in DistributedDataParallel (train_rvfm.py:258): every
+        gradient lives in ONE flat fp32 buffer, so backward() finishes with a single NCCL all-reduce (average) over it
+        -- no bucket copies, one collective.  Do not combine with a DDP wrapper (the reduction would happen twice).
+        Parameters must already be identical on all ranks (same seed / checkpoint, or broadcast `self._flat`)."""
+        self._grad_sync = (group,) if enabled else None
+
     def freeze_translator(self) -> None:
         """rvfm.py:89-92."""
         for param in self.translator.parameters():
@@ -381,6 +389,10 @@ class RobotVisionFM(nn.Module):
             ptrs[i] = buf.data_ptr()
         L.check(lib.theia_model_backward(self._handle, ptrs, L.stream_ptr()), "theia_model_backward")
         flat_g = self._grads.clone()  # autograd may keep what we return as .grad; the internal buffer is reused
+        if self._grad_sync is not None:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self._grad_sync[0]) > 1:
+                dist.all_reduce(flat_g, op=dist.ReduceOp.AVG, group=self._grad_sync[0])
         return [flat_g[o:o + math.prod(shape)].view(shape) for (_, shape, o) in self._param_meta]
 
     def forward_feature(self, x: torch.Tensor, **kwargs: Any) -> torch.Tensor:
