@@ -145,6 +145,17 @@ int theia_attention_tc_bwd(const void* qkv, const void* out, const void* dout, c
 /* parameter packing helpers */
 int theia_gather4(const void* in, void* out, int in_is_f32, int out_is_f32, int n0, int n1, int n2, int n3,
                   long long s0, long long s1, long long s2, long long s3, long long base, void* stream);
+/* Fused optimizer tail (train_rvfm.py:126-133; optimizers/utils.py:8-35): torch.optim.AdamW arithmetic over the
+ * flat fp32 parameter / gradient / moment buffers in one pass.  decay_flag64[i] != 0 = elements [64 i, 64 i + 64)
+ * belong to the weight-decay group; max_grad_norm > 0 applies clip_grad_norm_ first (scratch2: 2 floats). */
+int theia_adamw_flat(float* p, const float* g, float* m, float* v, const uint8_t* decay_flag64, long long n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int step, float max_grad_norm,
+                     float* scratch2, void* stream);
+/* Target ingest (src/theia/dataset/data_utils.py:152-153,342-355): teacher embeddings [B,C,H*W] bf16 ->
+ * [B,H*W,C] bf16, z-scored with per-channel bf16 mean/std (NULL = no normalisation); bit-exact with the
+ * reference's bf16 `(x - mean) / std` */
+int theia_target_ingest(const void* emb_chw, const void* mean_c, const void* std_c, void* out_hwc, int B, int C,
+                        int HW, void* stream);
 /* LayerNorm[C,H,W] affine layouts: reference [C][Hv][Wv] <-> NHWC zero-padded [Hp][Wp][C] (fp32) */
 int theia_chw_to_hwc(const float* in, float* out, int C, int Hv, int Wv, int Hp, int Wp, void* stream);
 int theia_hwc_to_chw(const float* in, float* out, int C, int Hv, int Wv, int Hp, int Wp, void* stream);

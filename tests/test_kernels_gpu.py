@@ -527,3 +527,17 @@ def test_ln3d_padded_31_in_32(lib):
     assert torch.all(dx[:, Wv:] == 0) and torch.all(dx[:, :, Wv:] == 0)
     assert relerr(dg.view(Wp, Wp, Cc)[:Wv, :Wv], gr.grad.permute(1, 2, 0)) < 1e-3
     assert relerr(db.view(Wp, Wp, Cc)[:Wv, :Wv], br.grad.permute(1, 2, 0)) < 1e-3
+
+
+@pytest.mark.parametrize("C_,H_", [(1024, 16), (256, 64), (32, 64), (1280, 16)])
+def test_target_ingest_bit_exact_with_reference_bf16_math(lib, C_, H_):
+    """dataset/data_utils.py:152-153 (rearrange 'c h w -> (h w) c') + :342-355 ((x - mean) / std in bf16)."""
+    from theia_b200.data import ingest_targets
+    Bn = 3
+    emb = rnd(Bn, C_, H_, H_, seed=1, scale=3.0)
+    mean, std = rnd(C_, seed=2), (rnd(C_, seed=3).float().abs() + 0.5).to(torch.bfloat16)
+    got = ingest_targets(emb, mean, std)
+    want = (emb.flatten(2).transpose(1, 2) - mean) / std  # torch bf16 arithmetic, exactly the reference's
+    assert got.dtype == torch.bfloat16 and tuple(got.shape) == (Bn, H_ * H_, C_)
+    assert torch.equal(got, want)
+    assert torch.equal(ingest_targets(emb), emb.flatten(2).transpose(1, 2))

@@ -217,6 +217,37 @@ def test_training_reduces_loss_and_repacks_weights():
     assert hist[-1] < hist[0] - 1e-3, hist
 
 
+def test_flat_adamw_matches_torch_adamw():
+    """the fused optimizer tail (two weight-decay groups of optimizers/utils.py:26-33, optional
+    clip_grad_norm_) against torch.optim.AdamW on identical gradients."""
+    from theia_b200.optim import FlatAdamW
+    cfg, P, m = build("facebook/deit-tiny-patch16-224", "dinov2")
+    cfg2, P2, m2 = build("facebook/deit-tiny-patch16-224", "dinov2")
+    images, targets = O.synthetic_batch(cfg, 4, seed=3, device=DEV)
+    decay, no_decay = [], []
+    for n, p in m2.named_parameters():
+        (no_decay if (p.ndim <= 1 or n.endswith(".bias")) else decay).append(p)
+    ref = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.05}],
+                            lr=2e-3, betas=(0.9, 0.999), eps=1e-8)
+    opt = FlatAdamW(m, lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, max_grad_norm=0.5)
+    for it in range(3):
+        for mod, o in ((m, opt), (m2, ref)):
+            pred = mod(images, do_resize=False)
+            losses = mod.get_loss(pred, targets)
+            o.zero_grad(set_to_none=True)
+            (0.9 * losses["cos_loss"] + 0.1 * losses["l1_loss"]).backward()
+        # same gradients on both sides (the forward/backward kernels are deterministic up to atomics order):
+        # copy m's gradients into m2 so the comparison isolates the optimizer arithmetic
+        for pa, pb in zip(m.parameters(), m2.parameters()):
+            pb.grad.copy_(pa.grad)
+        torch.nn.utils.clip_grad_norm_(m2.parameters(), 0.5)
+        opt.step()
+        ref.step()
+        assert relerr(m._flat, m2._flat) < 1e-6, it
+    worst = max((a - b).abs().max().item() for a, b in zip(m.parameters(), m2.parameters()))
+    assert worst < 1e-5, worst
+
+
 def test_full_batch_properties():
     """BASELINE-size batch (256) on deit-tiny/cdiv: per-image independence (no cross-sample statistic on
     the path): the first 4 predictions equal those of a 4-image batch."""

@@ -58,6 +58,8 @@ SYMBOLS = {
     "theia_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "theia_ln3d_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _vp]),
     "theia_ln3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp]),
+    "theia_adamw_flat": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),
+    "theia_target_ingest": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_chw_to_hwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "theia_hwc_to_chw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "theia_loss_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),

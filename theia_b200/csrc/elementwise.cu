@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // register partials over the rows a warp visits, block-reduced in shared memory, one atomic per column
 // per block.  NCH = 16-byte chunks per lane (D <= 256*NCH); dy/x stay packed in registers between passes.
 template <int NCH>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in,
@@ -580,6 +580,94 @@ __global__ void __launch_bounds__(256) gather4_kernel(const TI* __restrict__ in,
   out[t] = static_cast<TO>(v);
 }
 
+// Fused optimizer tail (train_rvfm.py:126-133, optimizers/utils.py:8-35): AdamW over the flat fp32
+// buffers in ONE pass (torch.optim.AdamW arithmetic: decoupled weight decay, bias correction), two weight-decay
+// groups through a per-64-element flag table, optional global-norm clipping through a device-side coefficient.
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(g + i);
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    } else {
+      for (long long k = i; k < n; ++k) acc += g[k] * g[k];
+    }
+  }
+  acc = warp_sum(acc);
+  __shared__ float sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sh[i];
+    atomicAdd(out, t);
+  }
+}
+// coef[0] = min(1, max_norm / (sqrt(sumsq) + 1e-6))  (torch.nn.utils.clip_grad_norm_)
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef) {
+  const float c = max_norm / (sqrtf(sumsq[0]) + 1e-6f);
+  coef[0] = c < 1.f ? c : 1.f;
+}
+__global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                         float* __restrict__ m, float* __restrict__ v,
+                                                         const uint8_t* __restrict__ decay_flag, long long n, float lr,
+                                                         float beta1, float beta2, float eps, float wd, float bc1,
+                                                         float sqrt_bc2, const float* __restrict__ gscale) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const float gs = gscale ? gscale[0] : 1.f;
+  const float decay = decay_flag[i >> 6] ? 1.f - lr * wd : 1.f;
+  const float step = lr / bc1;
+  float4 P = *reinterpret_cast<float4*>(p + i), G = *reinterpret_cast<const float4*>(g + i);
+  float4 M = *reinterpret_cast<float4*>(m + i), V = *reinterpret_cast<float4*>(v + i);
+  float* pp = &P.x;
+  float* mm = &M.x;
+  float* vv = &V.x;
+  const float* gg = &G.x;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float gk = gg[k] * gs;
+    float pk = pp[k] * decay;
+    const float mk = mm[k] + (gk - mm[k]) * (1.f - beta1);  // lerp_
+    const float vk = vv[k] * beta2 + gk * gk * (1.f - beta2);
+    const float denom = sqrtf(vk) / sqrt_bc2 + eps;
+    pk -= step * (mk / denom);
+    pp[k] = pk, mm[k] = mk, vv[k] = vk;
+  }
+  *reinterpret_cast<float4*>(p + i) = P;
+  *reinterpret_cast<float4*>(m + i) = M;
+  *reinterpret_cast<float4*>(v + i) = V;
+}
+
+// Target ingest (src/theia/dataset/data_utils.py:152-153,342-355): teacher embedding stored
+// [C,H,W] bf16 -> "(h w) c" and z-scored with the per-channel bf16 mean / std, on the GPU instead of in the
+// dataloader workers.  Arithmetic reproduces torch's bf16 ops bit for bit: r = bf16(x - mean); y = bf16(r / std).
+__global__ void target_ingest_kernel(const bf16* __restrict__ in, const bf16* __restrict__ mean,
+                                     const bf16* __restrict__ stdv, bf16* __restrict__ out, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16* src = in + static_cast<long long>(b) * C * HW;
+  bf16* dst = out + static_cast<long long>(b) * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? __bfloat162float(src[static_cast<long long>(c) * HW + p]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) {
+      float v = tile[threadIdx.x][i];
+      if (mean != nullptr && stdv != nullptr) {
+        const float r = __bfloat162float(__float2bfloat16_rn(v - __bfloat162float(mean[c])));
+        v = r / __bfloat162float(stdv[c]);
+      }
+      dst[static_cast<long long>(p) * C + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 // LayerNorm[C,H,W] affine: [C][Hv][Wv] (reference layout) <-> [Hp][Wp][C] (NHWC, zero padded)
 __global__ void __launch_bounds__(256) chw_to_hwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
                                                          int Hv, int Wv, int Hp, int Wp) {
@@ -870,6 +958,40 @@ extern "C" int theia_gather4(const void* in, void* out, int in_is_f32, int out_i
   else
     return set_error(THEIA_ERR_UNSUPPORTED, "gather4: unsupported dtype combination");
   THEIA_CHECK_LAUNCH("gather4");
+  return THEIA_OK;
+}
+
+extern "C" int theia_adamw_flat(float* p, const float* g, float* m, float* v, const uint8_t* decay_flag64, long long n,
+                                float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                float max_grad_norm, float* scratch2, void* stream) {
+  if (n <= 0) return THEIA_OK;
+  if (n % 4 != 0) return set_error(THEIA_ERR_ARG, "adamw: n %% 4 != 0");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  const float* gscale = nullptr;
+  if (max_grad_norm > 0.f) {
+    if (!scratch2) return set_error(THEIA_ERR_ARG, "adamw: clipping needs scratch2");
+    cudaError_t e = cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), S(stream));
+    if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    sumsq_kernel<<<num_sms() * 4, 256, 0, S(stream)>>>(g, n, scratch2);
+    THEIA_CHECK_LAUNCH("sumsq");
+    clip_coef_kernel<<<1, 1, 0, S(stream)>>>(scratch2, max_grad_norm, scratch2 + 1);
+    THEIA_CHECK_LAUNCH("clip_coef");
+    gscale = scratch2 + 1;
+  }
+  adamw_flat_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, S(stream)>>>(
+      p, g, m, v, decay_flag64, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), gscale);
+  THEIA_CHECK_LAUNCH("adamw_flat");
+  return THEIA_OK;
+}
+
+extern "C" int theia_target_ingest(const void* emb_chw, const void* mean_c, const void* std_c, void* out_hwc, int B,
+                                   int C, int HW, void* stream) {
+  if (B <= 0) return THEIA_OK;
+  dim3 g((HW + 31) / 32, (C + 31) / 32, B), blk(32, 8);
+  target_ingest_kernel<<<g, blk, 0, S(stream)>>>(static_cast<const bf16*>(emb_chw), static_cast<const bf16*>(mean_c),
+                                                 static_cast<const bf16*>(std_c), static_cast<bf16*>(out_hwc), C, HW);
+  THEIA_CHECK_LAUNCH("target_ingest");
   return THEIA_OK;
 }
 
