@@ -136,7 +136,7 @@ def workload_config(args, B):
     return {"workload": f"theia-{args.backbone} {args.teachers} distill step (fwd+loss+bwd+AdamW), per-GPU batch {B}, "
                         f"224x224x3 uint8 -> {args.teachers} teacher targets",
             "backbone": BACKBONES[args.backbone], "teachers": args.teachers, "per_gpu_batch": B,
-            "global_batch": B * args.gpus, "main_loss": "cos_l1",
+            "global_batch": B * args.gpus, "main_loss": "cos_l1", "optimizer": "AdamW (" + getattr(args, "optimizer", "flat") + ")",
             "preprocess": "rescale+normalize in-kernel, do_resize=False on both arms",
             "l2_policy": "per-step working set (>10 GB of activations at batch 256) far exceeds the 126 MB L2",
             "parallelism": f"dp{args.gpus}" + ("" if args.gpus == 1 else
@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dp-mode", default="flat", choices=["flat", "ddp"],
                     help="N>1: one flat-buffer NCCL all-reduce issued by the module (default) or the reference's DDP wrapper")
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
+                    help="flat = theia_b200.optim.FlatAdamW (one fused pass over the flat buffers); torch = torch.optim.AdamW(fused=True)")
     ap.add_argument("--gemm-csv", default=None, help="dump per-launch GEMM timings of the timed region")
     args = ap.parse_args()
 
@@ -202,8 +204,12 @@ def main():
     decay, no_decay = [], []
     for n, p in model.named_parameters():  # optimizers/utils.py:26-33
         (no_decay if (p.ndim <= 1 or n.endswith(".bias")) else decay).append(p)
-    opt = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.01}],
-                            lr=lr, betas=(0.9, 0.999), fused=True)
+    if args.optimizer == "flat":
+        from theia_b200.optim import FlatAdamW
+        opt = FlatAdamW(model, lr=lr, betas=(0.9, 0.999), weight_decay=0.01)  # same two decay groups, fused pass
+    else:
+        opt = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.01}],
+                                lr=lr, betas=(0.9, 0.999), fused=True)
 
     # synthetic data: pinned host copies for the e2e leg, device copies for `value`
     g = torch.Generator().manual_seed(1000 + rank)

@@ -74,4 +74,4 @@ class FlatAdamW:
                                          float(self.eps), float(self.weight_decay), int(self.step_count),
                                          float(self.max_grad_norm), self.scratch.data_ptr(), L.stream_ptr()),
                 "theia_adamw_flat")
-        flat.add_(0)  # bump the version counter: the bf16 operand copies are re-packed at the next forward
+        self.model._packed_version = None  # the bf16 operand copies are re-packed at the next forward
