@@ -52,7 +52,8 @@ enum {
   THEIA_EPI_ATOMIC = 1 << 5,    /* fp32 atomicAdd into out (split-K wgrad)                          */
   THEIA_EPI_MUL_AUX = 1 << 6,   /* v *= aux[m,n]   (backward of GELU with the saved derivative)      */
   THEIA_EPI_MUL_RELUMASK = 1 << 7, /* v = aux[m,n] > 0 ? v : 0                                      */
-  THEIA_EPI_POSCLS = 1 << 8,    /* token t = m % tokens: t==0 ? cls[n]+pos[0,n] : v + pos[t,n]      */
+  THEIA_EPI_POSCLS = 1 << 8,    /* token t = m % tokens: patch token (tok_p0 <= t < tok_p1) ? v + pos[t,n]
+                                   : pos[t,n]   (pos = per-token table incl. CLS / register tokens)      */
   THEIA_EPI_STATS = 1 << 9,     /* per-image sum / sum-of-squares of the stored values -> stats     */
   THEIA_EPI_COLSUM = 1 << 10    /* colsum[n] += sum over rows of the stored (bf16) values           */
 };
@@ -98,6 +99,7 @@ typedef struct theia_gemm_desc {
   long long out_z_stride;
   int bn;           /* N tile: 0 = auto, else 128 / 192 / 256 */
   float* colsum;    /* COLSUM: [N] fp32, accumulated */
+  int tok_p0, tok_p1; /* POSCLS: token range of the patch tokens */
 } theia_gemm_desc;
 
 int theia_gemm(const theia_gemm_desc* d, void* stream);
@@ -133,7 +135,9 @@ int theia_loss_bwd(const float* pred, const void* target, int target_is_bf16, co
  * 224x224 -> [bicubic-antialias resize to 256 + centre crop 224 when do_resize] -> rescale/normalise ->
  * bf16 patch rows [B*197, 768] (row b*197 is the zero CLS slot; column = c*256 + i*16 + j) */
 int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_resize, int do_rescale,
-                     int do_normalize, const float* mean3, const float* std3, void* stream);
+                     int do_normalize, const float* mean3, const float* std3, int tokens, int patch_off, void* stream);
+/* tokens / patch_off: rows per image of the patch matrix and the row of the first patch (197 / 1 for DeiT, 196 / 0
+ * for DeiTNoCLS, 204 / 1 for DeiTReg); rows of non-patch tokens are zero */
 /* attention (hf:modeling_vit.py:171-196,232-246): qkv [B*N,3*H*64] bf16 -> out [B*N,H*64]; lse [B,H,N] */
 int theia_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream);
 int theia_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N,
@@ -163,6 +167,8 @@ int theia_cast_bf16(const float* in, void* out, long long n, void* stream);
 int theia_transpose_cast_bf16(const float* in, void* out, int R, int C, void* stream);
 /* out[n] += sum_m x[m,n] (rows with m % skip_mod == 0 skipped when skip_mod > 0) */
 int theia_colsum(const void* x, float* out, int M, int N, long long ld, int skip_mod, void* stream);
+/* same, keeping only rows whose token index (m % period) lies in [t0, t1) */
+int theia_colsum_tokens(const void* x, float* out, int M, int N, long long ld, int period, int t0, int t1, void* stream);
 /* out[j] = sum_b x[b*n + j] */
 int theia_batchsum(const void* x, float* out, int B, int n, void* stream);
 
@@ -174,6 +180,9 @@ int theia_batchsum(const void* x, float* out, int B, int n, void* stream);
 typedef struct theia_model_config {
   int hidden, heads, layers, image, patch, max_batch;
   float ln_eps;
+  int variant;        /* 0 = DeiT (CLS + patches), 1 = DeiTNoCLS (patches only), 2 = DeiTReg (CLS + patches + registers);
+                         src/theia/models/backbones.py:506-526 */
+  int num_reg_tokens; /* DeiTReg: 7 */
   int num_teachers;
   const char* teacher_names[THEIA_MAX_TEACHERS];
   int teacher_c[THEIA_MAX_TEACHERS];

@@ -42,11 +42,16 @@ def import_reference():
         d, h = O.BACKBONES[name]
         return ViTModel(ViTConfig(hidden_size=d, num_attention_heads=h, intermediate_size=4 * d))
 
+    def config_factory(name, *a, **k):
+        d, h = O.BACKBONES[name]
+        return ViTConfig(hidden_size=d, num_attention_heads=h, intermediate_size=4 * d)
+
     def proc_factory(name, *a, **k):
         return DeiTImageProcessor(image_mean=list(O.IMAGE_MEAN), image_std=list(O.IMAGE_STD))
 
     transformers.AutoModel.from_pretrained = staticmethod(model_factory)
     transformers.AutoProcessor.from_pretrained = staticmethod(proc_factory)
+    transformers.AutoConfig.from_pretrained = staticmethod(config_factory)
     sys.path.insert(0, REF_SRC)
     from theia.models.rvfm import RobotVisionFM
     return RobotVisionFM
@@ -70,6 +75,8 @@ CASES = [
     ("tiny_cdiv_b2_resize", "facebook/deit-tiny-patch16-224", "cdiv", 2, True),
     ("tiny_cddsv_b1", "facebook/deit-tiny-patch16-224", "cddsv", 1, False),
     ("tiny_dinov2_cls_b3", "facebook/deit-tiny-patch16-224", "dinov2+cls", 3, False),  # distill_cls (train_rvfm.py:239-246)
+    ("tiny_nocls_dinov2_b2", "nocls-facebook/deit-tiny-patch16-224", "dinov2", 2, False),  # DeiTNoCLS (backbones.py:344)
+    ("tiny_reg_dinov2_b2", "reg-facebook/deit-tiny-patch16-224", "dinov2", 2, False),      # DeiTReg (backbones.py:424)
 ]
 
 

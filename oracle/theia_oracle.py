@@ -76,15 +76,30 @@ class OracleConfig:
     # tests to separate kernel bugs from the precision effect of bf16 storage (ReLU-mask flips make
     # the gradient a discontinuous function of the forward activations).
     emulate_bf16: bool = False
+    # backbone variant (backbones.py:506-526): "deit" (CLS + 196 patches), "nocls" (DeiTNoCLS: 196 patches),
+    # "reg" (DeiTReg: CLS + 196 patches + num_reg register tokens, stripped before the translator)
+    variant: str = "deit"
+    num_reg: int = 0
 
     @property
     def tokens(self) -> int:
+        """rows of position_embeddings (always 197: ViTEmbeddings keeps the CLS slot even in the no-CLS variant)"""
         return (self.image // self.patch) ** 2 + 1
+
+    @property
+    def seq(self) -> int:
+        n = (self.image // self.patch) ** 2
+        return n + (0 if self.variant == "nocls" else 1) + self.num_reg
 
 
 def make_config(backbone: str, teachers, distill_cls: bool = False) -> OracleConfig:
     """distill_cls: train_rvfm.py:239-246 -- ViT / DINOv2 / CLIP teachers also get a '<name>_cls' target of size
     (C_t,) predicted by a LinearAdapterHead on the CLS token."""
+    variant, num_reg = "deit", 0
+    if backbone.startswith("nocls-"):
+        variant, backbone = "nocls", backbone[len("nocls-"):]
+    elif backbone.startswith("reg-"):
+        variant, num_reg, backbone = "reg", 7, backbone[len("reg-"):]
     d, h = BACKBONES[backbone]
     if isinstance(teachers, str):
         teachers = TEACHER_SETS[teachers]
@@ -95,7 +110,7 @@ def make_config(backbone: str, teachers, distill_cls: bool = False) -> OracleCon
         for t in list(teachers):
             if "google/vit" in t or "facebook/dino" in t or "openai/clip" in t:
                 sizes[t + "_cls"] = MODEL_FEATURE_SIZES[t][:1]
-    return OracleConfig(hidden=d, heads=h, teachers=sizes)
+    return OracleConfig(hidden=d, heads=h, teachers=sizes, variant=variant, num_reg=num_reg)
 
 
 def _r(x: torch.Tensor, cfg: "OracleConfig") -> torch.Tensor:
@@ -116,8 +131,12 @@ def param_shapes(cfg: OracleConfig) -> dict:
     D = cfg.hidden
     s = {}
     e = "backbone.model.embeddings."
-    s[e + "cls_token"] = (1, 1, D)
+    if cfg.variant != "nocls":
+        s[e + "cls_token"] = (1, 1, D)
     s[e + "position_embeddings"] = (1, cfg.tokens, D)
+    if cfg.variant == "reg":
+        s[e + "reg_token"] = (1, cfg.num_reg, D)
+        s[e + "reg_pos_embed"] = (1, cfg.num_reg, D)
     s[e + "patch_embeddings.projection.weight"] = (D, 3, cfg.patch, cfg.patch)
     s[e + "patch_embeddings.projection.bias"] = (D,)
     for l in range(cfg.layers):
@@ -233,7 +252,13 @@ def vit_forward(P: dict, pix: torch.Tensor, cfg: OracleConfig, taps: Optional[di
                  P[e + "patch_embeddings.projection.bias"], stride=cfg.patch)
     x = x.flatten(2).transpose(1, 2)  # [B,196,D]
     B = x.shape[0]
-    x = _r(torch.cat([P[e + "cls_token"].expand(B, -1, -1), x], dim=1) + P[e + "position_embeddings"], cfg)
+    if cfg.variant == "nocls":  # ViTEmbeddingsNoCLS.forward (backbones.py:70-93)
+        x = _r(x + P[e + "position_embeddings"][:, 1:], cfg)
+    elif cfg.variant == "reg":  # ViTEmbeddingsReg.forward (backbones.py:186-217)
+        x = torch.cat([P[e + "cls_token"].expand(B, -1, -1), x, P[e + "reg_token"].expand(B, -1, -1)], dim=1)
+        x = _r(x + torch.cat([P[e + "position_embeddings"], P[e + "reg_pos_embed"]], dim=1), cfg)
+    else:
+        x = _r(torch.cat([P[e + "cls_token"].expand(B, -1, -1), x], dim=1) + P[e + "position_embeddings"], cfg)
 
     def tap(name, l, v):
         """record an intermediate (taps) and/or teacher-force it (force): the VALUE becomes the given tensor,
@@ -287,7 +312,9 @@ def lconv_head_forward(P: dict, t: str, x: torch.Tensor, cfg: OracleConfig, taps
     ct, ht, wt = cfg.teachers[t]
     B, C = x.shape[0], x.shape[2]
     g = cfg.image // cfg.patch
-    y = x[:, 1:].reshape(B, g, g, C).permute(0, 3, 1, 2)  # drop CLS; b (h w) c -> b c h w
+    if cfg.variant != "nocls":
+        x = x[:, 1:]  # drop CLS (adapter_heads.py:355-356, backbone_no_cls False)
+    y = x.reshape(B, g, g, C).permute(0, 3, 1, 2)  # b (h w) c -> b c h w
     y = _r(F.conv_transpose2d(y, _r(P[p + "pad.1.weight"], cfg), P[p + "pad.1.bias"], stride=1), cfg)  # 14 -> 16
 
     def tap(name, v):  # NHWC like the CUDA path stores it
@@ -346,7 +373,7 @@ def backbone_forward(P, images, cfg, taps=None, force=None, **kw):
 
 def forward_feature(P, images, cfg, feature_reduce_method=None, **kw):
     """RobotVisionFM.forward_feature (rvfm.py:94-113)."""
-    return handle_feature_output(backbone_forward(P, images, cfg, **kw), feature_reduce_method)
+    return handle_feature_output(backbone_forward(P, images, cfg, **kw), feature_reduce_method, cfg.num_reg)
 
 
 def forward(P, images, cfg, target_model_names=None, taps=None, force=None, **kw) -> dict:
@@ -356,6 +383,8 @@ def forward(P, images, cfg, target_model_names=None, taps=None, force=None, **kw
         x = x + (force[("tokens", 0)].to(x.dtype).view_as(x) - x).detach()
     if taps is not None:
         taps[("tokens", 0)] = x.detach()
+    if cfg.num_reg > 0:
+        x = x[:, :-cfg.num_reg]  # rvfm.py:133-134
     names = target_model_names if target_model_names is not None else list(cfg.teachers)
     return {t: lconv_head_forward(P, t, x, cfg, taps, force) for t in names}
 

@@ -26,13 +26,13 @@ def fetch(m, name, i, shape):
 
 def fetch_all(m, cfg, B):
     """every stored forward activation of the last forward, keyed like the oracle's taps"""
-    D = cfg.hidden
-    out = {("x", 0): fetch(m, "x", 0, (B, 197, D)), ("tokens", 0): fetch(m, "tokens", 0, (B, 197, D))}
+    D, NT = cfg.hidden, cfg.seq
+    out = {("x", 0): fetch(m, "x", 0, (B, NT, D)), ("tokens", 0): fetch(m, "tokens", 0, (B, NT, D))}
     for l in range(cfg.layers):
         # ("h" holds gelu'(pre-activation) in the CUDA path, not the pre-activation: it is not forced)
         for name, w in (("ln1", D), ("qkv", 3 * D), ("attn", D), ("xmid", D), ("ln2", D), ("a", 4 * D)):
-            out[(name, l)] = fetch(m, name, l, (B, 197, w))
-        out[("x", l + 1)] = fetch(m, "x", l + 1, (B, 197, D))
+            out[(name, l)] = fetch(m, name, l, (B, NT, w))
+        out[("x", l + 1)] = fetch(m, "x", l + 1, (B, NT, D))
     for i, (t, size) in enumerate(cfg.teachers.items()):
         if len(size) == 1:
             continue  # CLS head: a single Linear, nothing stored

@@ -37,7 +37,9 @@ def test_model_layout_matches_reference_state_dict(lib):
     """state_dict keys / shapes == the reference's, as restated by the oracle."""
     from oracle import theia_oracle as O
     from theia_b200 import RobotVisionFM
-    for backbone, tset in (("facebook/deit-tiny-patch16-224", "cdiv"), ("facebook/deit-base-patch16-224", "dinov2")):
+    for backbone, tset in (("facebook/deit-tiny-patch16-224", "cdiv"), ("facebook/deit-base-patch16-224", "dinov2"),
+                           ("facebook/deit-tiny-patch16-224", "cddsv"), ("nocls-facebook/deit-tiny-patch16-224", "dinov2"),
+                           ("reg-facebook/deit-small-patch16-224", "cdiv")):
         cfg = O.make_config(backbone, tset)
         m = RobotVisionFM(backbone=backbone, translator="lconv", target_feature_sizes=dict(cfg.teachers),
                           translator_kwargs={"hidden_size_factor": 1.0})
@@ -49,6 +51,8 @@ def test_model_layout_matches_reference_state_dict(lib):
         # weight-decay grouping of optimizers/utils.py:26-33 depends on ndim / '.bias'
         nd = {k: p.ndim for k, p in m.named_parameters()}
         assert nd["backbone.model.embeddings.position_embeddings"] == 3
+        assert ("backbone.model.embeddings.cls_token" in nd) == (not backbone.startswith("nocls-"))
+        assert ("backbone.model.embeddings.reg_token" in nd) == backbone.startswith("reg-")
         # q/k/v weights are adjacent in the flat buffer (single fused QKV GEMM, no copies)
         lay = {n: o for n, _, o in m._param_meta}
         p = "backbone.model.encoder.layer.0.attention.attention."

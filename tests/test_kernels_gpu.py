@@ -99,8 +99,10 @@ def test_gemm_poscls(lib):
     bias, pos, cls = (rnd(D, seed=3, dtype=torch.float32), rnd(197, D, seed=4, dtype=torch.float32),
                       rnd(D, seed=5, dtype=torch.float32))
     out = torch.zeros(M, D, dtype=torch.bfloat16, device=DEV)
-    gemm(lib, M=M, N=D, K=K, A=a, lda=K, B=w, ldb=K, out=out, ldo=D, bias=bias, pos=pos, cls=cls, tokens=197,
-         epi=L.EPI_POSCLS)
+    table = pos.clone()
+    table[0] += cls  # per-token table: CLS row holds cls_token + pos[0]
+    gemm(lib, M=M, N=D, K=K, A=a, lda=K, B=w, ldb=K, out=out, ldo=D, bias=bias, pos=table, tokens=197, tok_p0=1,
+         tok_p1=197, epi=L.EPI_POSCLS)
     ref = (a.float() @ w.float().t() + bias).view(Bn, 197, D) + pos
     ref[:, 0] = cls + pos[0]
     assert relerr(out.float().view(Bn, 197, D), ref) < 6e-3
@@ -318,7 +320,7 @@ def test_preprocess(lib, chw):
     out = torch.empty(Bn * 197, 768, dtype=torch.bfloat16, device=DEV)
     mean, std = (C.c_float * 3)(*O.IMAGE_MEAN), (C.c_float * 3)(*O.IMAGE_STD)
     d = img.to(DEV)
-    L.check(lib.theia_preprocess(d.data_ptr(), out.data_ptr(), Bn, chw, 0, 1, 1, mean, std, S()))
+    L.check(lib.theia_preprocess(d.data_ptr(), out.data_ptr(), Bn, chw, 0, 1, 1, mean, std, 197, 1, S()))
     pix = O.preprocess(img, do_resize=False)  # [B,3,224,224]
     ref = F.unfold(pix, 16, stride=16).transpose(1, 2)  # [B,196, c*256+i*16+j]
     o = out.float().view(Bn, 197, 768).cpu()
@@ -342,7 +344,7 @@ def test_preprocess_with_bicubic_resize(lib, chw):
     d = img.to(DEV)
     out = torch.empty(Bn * 197, 768, dtype=torch.bfloat16, device=DEV)
     mean, std = (C.c_float * 3)(*O.IMAGE_MEAN), (C.c_float * 3)(*O.IMAGE_STD)
-    L.check(lib.theia_preprocess(d.data_ptr(), out.data_ptr(), Bn, chw, 1, 1, 1, mean, std, S()))
+    L.check(lib.theia_preprocess(d.data_ptr(), out.data_ptr(), Bn, chw, 1, 1, 1, mean, std, 197, 1, S()))
     pix = O.preprocess(d, do_resize=True)  # device tensor -> torchvision float path + round
     ref = F.unfold(pix, 16, stride=16).transpose(1, 2)
     o = out.float().view(Bn, 197, 768)

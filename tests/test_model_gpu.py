@@ -72,7 +72,9 @@ def test_readme_quickstart_zeros():
                                              ("facebook/deit-tiny-patch16-224", "cdiv", 3),
                                              ("facebook/deit-small-patch16-224", "dinov2", 5),
                                              ("facebook/deit-tiny-patch16-224", "cddsv", 2),
-                                             ("facebook/deit-tiny-patch16-224", "cdiv+cls", 3)])
+                                             ("facebook/deit-tiny-patch16-224", "cdiv+cls", 3),
+                                             ("nocls-facebook/deit-tiny-patch16-224", "dinov2", 2),
+                                             ("reg-facebook/deit-tiny-patch16-224", "cdiv", 2)])
 def test_distill_step_parity_vs_oracle(backbone, tset, B):
     cfg, P, m = build(backbone, tset)
     images, targets = O.synthetic_batch(cfg, B, seed=0, device=DEV)
@@ -191,6 +193,25 @@ def test_cls_distillation_heads_against_reference_golden():
     images, targets = O.synthetic_batch(cfg, fx["B"], seed=fx["seed"], device=DEV)
     pred = m(images, **fx["kwargs"])
     assert tuple(pred["facebook/dinov2-large_cls"].shape) == (fx["B"], 1024)
+    for t, gq in fx["pred"].items():
+        assert relerr(_sl(pred[t]).cpu(), gq["sample"]) < 3e-2, t
+    losses = m.get_loss(pred, targets)
+    for k, v in fx["losses"].items():
+        assert abs(float(losses[k]) - v) <= 1e-3 * abs(v), k
+
+
+@pytest.mark.parametrize("fixture", ["tiny_nocls_dinov2_b2", "tiny_reg_dinov2_b2"])
+def test_backbone_variants_against_reference_golden(fixture):
+    """DeiTNoCLS (196 tokens, no CLS) and DeiTReg (CLS + 196 + 7 register tokens): backbones.py:344-503."""
+    fx = torch.load(os.path.join(GOLDEN, fixture + ".pt"), weights_only=False)
+    cfg, P, m = build(fx["backbone"], fx["teachers"], seed=fx["seed"])
+    assert m.no_cls == (cfg.variant == "nocls") and m.num_reg_tokens == cfg.num_reg
+    images, targets = O.synthetic_batch(cfg, fx["B"], seed=fx["seed"], device=DEV)
+    with torch.no_grad():
+        feat = m.forward_feature(images, **fx["kwargs"])
+    assert tuple(feat.shape) == fx["feature"]["shape"]
+    assert relerr(_sl(feat).cpu(), fx["feature"]["sample"]) < 2e-2
+    pred = m(images, **fx["kwargs"])
     for t, gq in fx["pred"].items():
         assert relerr(_sl(pred[t]).cpu(), gq["sample"]) < 3e-2, t
     losses = m.get_loss(pred, targets)

@@ -33,12 +33,14 @@ class GemmDesc(C.Structure):
                 ("conv", ConvGeom), ("epi", C.c_int), ("out", C.c_void_p), ("ldo", C.c_longlong),
                 ("out2", C.c_void_p), ("bias", C.c_void_p), ("aux", C.c_void_p), ("pos", C.c_void_p),
                 ("cls", C.c_void_p), ("tokens", C.c_int), ("stats", C.c_void_p), ("rows_per_image", C.c_int),
-                ("splits", C.c_int), ("batch_z", C.c_int), ("out_z_stride", C.c_longlong), ("bn", C.c_int), ("colsum", C.c_void_p)]
+                ("splits", C.c_int), ("batch_z", C.c_int), ("out_z_stride", C.c_longlong), ("bn", C.c_int), ("colsum", C.c_void_p),
+                ("tok_p0", C.c_int), ("tok_p1", C.c_int)]
 
 
 class ModelConfig(C.Structure):
     _fields_ = [("hidden", C.c_int), ("heads", C.c_int), ("layers", C.c_int), ("image", C.c_int),
-                ("patch", C.c_int), ("max_batch", C.c_int), ("ln_eps", C.c_float), ("num_teachers", C.c_int),
+                ("patch", C.c_int), ("max_batch", C.c_int), ("ln_eps", C.c_float), ("variant", C.c_int),
+                ("num_reg_tokens", C.c_int), ("num_teachers", C.c_int),
                 ("teacher_names", C.c_char_p * MAX_TEACHERS), ("teacher_c", C.c_int * MAX_TEACHERS),
                 ("teacher_hw", C.c_int * MAX_TEACHERS)]
 
@@ -64,7 +66,7 @@ SYMBOLS = {
     "theia_hwc_to_chw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "theia_loss_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "theia_loss_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "theia_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp]),
+    "theia_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _vp]),
     "theia_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_attention_tc_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_attention_tc_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -72,6 +74,7 @@ SYMBOLS = {
     "theia_gather4": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _vp]),
     "theia_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "theia_transpose_cast_bf16": (_i, [_vp, _vp, _i, _i, _vp]),
+    "theia_colsum_tokens": (_i, [_vp, _vp, _i, _i, _ll, _i, _i, _i, _vp]),
     "theia_colsum": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
     "theia_batchsum": (_i, [_vp, _vp, _i, _i, _vp]),
     "theia_model_create": (_i, [C.POINTER(ModelConfig), C.POINTER(_vp)]),

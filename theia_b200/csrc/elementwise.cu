@@ -463,23 +463,23 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict_
 // Image pre-processing (DeiT processor without resize): uint8 -> normalised bf16 patch rows.
 // out[b*197 + 0][:] = 0 (CLS slot), out[b*197 + 1 + p][c*256 + i*16 + j] = norm(img[b, py*16+i, px*16+j, c])
 // ============================================================================================
-__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int B,
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int NT, int P0, int B,
                                                          int chw, float s0, float s1, float s2, float o0, float o1,
                                                          float o2) {
   // one thread per 8 consecutive k of one patch row
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * 197 * 96;
+  const long long total = static_cast<long long>(B) * NT * 96;
   if (t >= total) return;
   const int k8 = static_cast<int>(t % 96);
   const long long row = t / 96;
-  const int tok = static_cast<int>(row % 197);
-  const int b = static_cast<int>(row / 197);
+  const int tok = static_cast<int>(row % NT);
+  const int b = static_cast<int>(row / NT);
   float o[8];
-  if (tok == 0) {
+  if (tok < P0 || tok >= P0 + 196) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = 0.f;
   } else {
-    const int p = tok - 1, py = p / 14, px = p % 14;
+    const int p = tok - P0, py = p / 14, px = p % 14;
     const int k = k8 * 8;
     const int c = k >> 8, i = (k >> 4) & 15, j = k & 15;
     const int yy = py * 16 + i, xx = px * 16 + j;
@@ -513,22 +513,22 @@ struct ResizeTable {
 };
 __constant__ ResizeTable c_rt;
 
-__global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out,
+__global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int NT, int P0,
                                                                 int B, int chw, float s0, float s1, float s2, float o0,
                                                                 float o1, float o2) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * 197 * 96;
+  const long long total = static_cast<long long>(B) * NT * 96;
   if (t >= total) return;
   const int k8 = static_cast<int>(t % 96);
   const long long row = t / 96;
-  const int tok = static_cast<int>(row % 197);
-  const int b = static_cast<int>(row / 197);
+  const int tok = static_cast<int>(row % NT);
+  const int b = static_cast<int>(row / NT);
   float o[8];
-  if (tok == 0) {
+  if (tok < P0 || tok >= P0 + 196) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = 0.f;
   } else {
-    const int p = tok - 1, py = p / 14, px = p % 14;
+    const int p = tok - P0, py = p / 14, px = p % 14;
     const int k = k8 * 8;
     const int c = k >> 8, i = (k >> 4) & 15, j = k & 15;
     const int oy = py * 16 + i + 16;
@@ -721,7 +721,7 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
 // period > 0: out has `period*N` entries and row m adds into out[(m % period)*N + n] (pos-emb grad).
 // ============================================================================================
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int M, int N,
-                                                     long long ld, int skip_mod, int rows_per_block) {
+                                                     long long ld, int skip_mod, int rows_per_block, int t0, int t1) {
   __shared__ float sh[8][256];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = (blockIdx.x * 32 + tx) * 8;
@@ -732,7 +732,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   for (int e = 0; e < 8; ++e) a[e] = 0.f;
   if (n < N) {
     for (int r = r0 + ty; r < r1; r += 8) {
-      if (skip_mod > 0 && (r % skip_mod) == 0) continue;
+      if (skip_mod > 0) {
+        const int tk = r % skip_mod;
+        if (tk < t0 || tk >= t1) continue;
+      }
       float v[8];
       load8(x + static_cast<long long>(r) * ld + n, v);
 #pragma unroll
@@ -914,8 +917,9 @@ static int upload_resize_table() {
 }
 
 extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_resize,
-                                int do_rescale, int do_normalize, const float* mean3, const float* std3,
-                                void* stream) {
+                                int do_rescale, int do_normalize, const float* mean3, const float* std3, int tokens,
+                                int patch_off, void* stream) {
+  if (tokens < patch_off + 196 || patch_off < 0) return set_error(THEIA_ERR_ARG, "preprocess: bad token layout");
   // out = (x - off) * scale  per channel
   float sc[3], of[3];
   for (int c = 0; c < 3; ++c) {
@@ -929,15 +933,17 @@ extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int
       sc[c] = do_rescale ? (1.f / 255.f) : 1.f;
     }
   }
-  const long long total = static_cast<long long>(B) * 197 * 96;
+  const long long total = static_cast<long long>(B) * tokens * 96;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   if (do_resize) {
     int rc = upload_resize_table();
     if (rc) return rc;
-    preprocess_resize_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), B, channels_first,
+    preprocess_resize_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), tokens, patch_off, B,
+                                                          channels_first,
                                                           sc[0], sc[1], sc[2], of[0], of[1], of[2]);
   } else {
-    preprocess_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), B, channels_first, sc[0],
+    preprocess_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), tokens, patch_off, B,
+                                                   channels_first, sc[0],
                                                    sc[1], sc[2], of[0], of[1], of[2]);
   }
   THEIA_CHECK_LAUNCH("preprocess");
@@ -1026,8 +1032,20 @@ extern "C" int theia_colsum(const void* x, float* out, int M, int N, long long l
   if (N % 8 != 0) return set_error(THEIA_ERR_ARG, "colsum: N %% 8 != 0");
   const int rows_per_block = 512;
   dim3 g((N + 255) / 256, (M + rows_per_block - 1) / rows_per_block);
-  colsum_kernel<<<g, 256, 0, S(stream)>>>(static_cast<const bf16*>(x), out, M, N, ld, skip_mod, rows_per_block);
+  // skip_mod > 0: rows with (m % skip_mod) == 0 are skipped (legacy form: CLS rows)
+  colsum_kernel<<<g, 256, 0, S(stream)>>>(static_cast<const bf16*>(x), out, M, N, ld, skip_mod, rows_per_block, 1,
+                                          skip_mod > 0 ? skip_mod : 1);
   THEIA_CHECK_LAUNCH("colsum");
+  return THEIA_OK;
+}
+
+extern "C" int theia_colsum_tokens(const void* x, float* out, int M, int N, long long ld, int period, int t0, int t1,
+                                   void* stream) {
+  if (N % 8 != 0 || period < 1) return set_error(THEIA_ERR_ARG, "colsum_tokens: bad arguments");
+  const int rows_per_block = 512;
+  dim3 g((N + 255) / 256, (M + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<<<g, 256, 0, S(stream)>>>(static_cast<const bf16*>(x), out, M, N, ld, period, rows_per_block, t0, t1);
+  THEIA_CHECK_LAUNCH("colsum_tokens");
   return THEIA_OK;
 }
 

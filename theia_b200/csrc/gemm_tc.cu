@@ -46,7 +46,7 @@ struct GemmK {
   const bf16* aux;
   const float* pos;
   const float* cls;
-  int tokens;
+  int tokens, tok_p0, tok_p1;
   float* stats;
   float* colsum;
   long long out_z_stride;
@@ -418,10 +418,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int m = it.m_blk * BM + wq * 32 + i * 4 + rsub;
               const int t = m % p.tokens;
               const float4 ps = *reinterpret_cast<const float4*>(p.pos + static_cast<long long>(t) * p.N + n);
-              if (t == 0) {
-                const float4 cl = *reinterpret_cast<const float4*>(p.cls + n);
-                xv[4 * j + 0] = cl.x + ps.x, xv[4 * j + 1] = cl.y + ps.y;
-                xv[4 * j + 2] = cl.z + ps.z, xv[4 * j + 3] = cl.w + ps.w;
+              if (t < p.tok_p0 || t >= p.tok_p1) {  // CLS / register token: the table holds the whole value
+                xv[4 * j + 0] = ps.x, xv[4 * j + 1] = ps.y, xv[4 * j + 2] = ps.z, xv[4 * j + 3] = ps.w;
               } else {
                 xv[4 * j + 0] += ps.x, xv[4 * j + 1] += ps.y, xv[4 * j + 2] += ps.z, xv[4 * j + 3] += ps.w;
               }
@@ -695,6 +693,7 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   k.pos = d->pos;
   k.cls = d->cls;
   k.tokens = d->tokens > 0 ? d->tokens : 1;
+  k.tok_p0 = d->tok_p0, k.tok_p1 = d->tok_p1;
   k.stats = d->stats;
   k.colsum = d->colsum;
   k.out_z_stride = d->out_z_stride;
@@ -704,7 +703,7 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   if ((d->epi & THEIA_EPI_GELU) && !d->out2) return set_error(THEIA_ERR_ARG, "EPI_GELU needs out2");
   if ((d->epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_AUX | THEIA_EPI_MUL_RELUMASK)) && !d->aux)
     return set_error(THEIA_ERR_ARG, "epilogue needs aux");
-  if ((d->epi & THEIA_EPI_POSCLS) && (!d->pos || !d->cls)) return set_error(THEIA_ERR_ARG, "POSCLS needs pos/cls");
+  if ((d->epi & THEIA_EPI_POSCLS) && !d->pos) return set_error(THEIA_ERR_ARG, "POSCLS needs the token table (pos)");
   if ((d->epi & THEIA_EPI_COLSUM) && !d->colsum) return set_error(THEIA_ERR_ARG, "COLSUM needs colsum");
   if ((d->epi & THEIA_EPI_STATS) && (!d->stats || d->a_mode != THEIA_OP_CONV_K))
     return set_error(THEIA_ERR_ARG, "STATS needs stats and a CONV_K A operand");

@@ -59,6 +59,9 @@ using namespace theia;
 struct theia_model {
   theia_model_config cfg;
   int D, H, L, T, Bmax;
+  int N, p0, R;            // tokens per image, index of the first patch token, register tokens
+  int regt, regp;          // DeiTReg parameters (indices), -1 otherwise
+  long long tokt, tgrad;   // token table (fp32 pack) / its gradient scratch
   std::vector<PInfo> params;
   long long n_params_total;  // floats in the flat buffer
   int cls, pos, pew, peb, lnfw, lnfb;
@@ -132,7 +135,12 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
     return set_error(THEIA_ERR_UNSUPPORTED, "hidden must be heads*64");
   if (cfg->image != 224 || cfg->patch != 16) return set_error(THEIA_ERR_UNSUPPORTED, "only 224/16 ViT geometry");
   if (cfg->num_teachers < 0 || cfg->num_teachers > THEIA_MAX_TEACHERS) return set_error(THEIA_ERR_ARG, "num_teachers");
+  if (cfg->variant < 0 || cfg->variant > 2) return set_error(THEIA_ERR_ARG, "variant must be 0 (DeiT), 1 (NoCLS) or 2 (Reg)");
+  if (cfg->variant == 2 && (cfg->num_reg_tokens < 1 || cfg->num_reg_tokens > 11))
+    return set_error(THEIA_ERR_UNSUPPORTED, "DeiTReg: 1..11 register tokens (sequence <= 208)");
   for (int t = 0; t < cfg->num_teachers; ++t) {
+    if (cfg->teacher_hw[t] == 1 && cfg->variant == 1)
+      return set_error(THEIA_ERR_UNSUPPORTED, "CLS-token heads need a backbone with a CLS token");
     if (cfg->teacher_hw[t] != 16 && cfg->teacher_hw[t] != 64 && cfg->teacher_hw[t] != 1)
       return set_error(THEIA_ERR_UNSUPPORTED, "teacher %s: target maps must be 16x16, 64x64 or a CLS vector (got %d)",
                        cfg->teacher_names[t], cfg->teacher_hw[t]);
@@ -146,9 +154,17 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   const int T = m->T = cfg->num_teachers;
   const int B = m->Bmax = cfg->max_batch;
   m->n_params_total = 0;
+  m->R = cfg->variant == 2 ? cfg->num_reg_tokens : 0;
+  m->p0 = cfg->variant == 1 ? 0 : 1;
+  m->N = 196 + m->p0 + m->R;
   const std::string e = "backbone.model.embeddings.";
-  m->cls = add_param(m, e + "cls_token", {1, 1, D});
+  m->cls = m->regt = m->regp = -1;
+  if (cfg->variant != 1) m->cls = add_param(m, e + "cls_token", {1, 1, D});
   m->pos = add_param(m, e + "position_embeddings", {1, 197, D});
+  if (cfg->variant == 2) {
+    m->regt = add_param(m, e + "reg_token", {1, m->R, D});
+    m->regp = add_param(m, e + "reg_pos_embed", {1, m->R, D});
+  }
   m->pew = add_param(m, e + "patch_embeddings.projection.weight", {D, 3, 16, 16});
   m->peb = add_param(m, e + "patch_embeddings.projection.bias", {D});
   for (int l = 0; l < L; ++l) {
@@ -208,10 +224,12 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   }
 
   // ---- workspace carving ----
-  const long long M = static_cast<long long>(B) * 197, P = static_cast<long long>(B) * 256;
+  const long long M = static_cast<long long>(B) * m->N, P = static_cast<long long>(B) * 256;
   Carver pb, pf, ab, af;
   const long long AL = 128;  // 256-byte alignment for bf16, 512 for fp32: fine for TMA (16 B) and vectors
   m->wpe = pb.take(static_cast<long long>(D) * 768, AL);
+  m->tokt = pf.take(static_cast<long long>(m->N) * D, AL);
+  m->tgrad = af.take(static_cast<long long>(m->N) * D, AL);
   for (int l = 0; l < L; ++l) {
     LayerW w;
     const long long DD = static_cast<long long>(D) * D;
@@ -264,7 +282,7 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
     a.rstd1 = af.take(M, AL);
     a.mean2 = af.take(M, AL);
     a.rstd2 = af.take(M, AL);
-    a.lse = af.take(static_cast<long long>(B) * m->H * 197, AL);
+    a.lse = af.take(static_cast<long long>(B) * m->H * m->N, AL);
     m->la.push_back(a);
   }
   m->tokens = ab.take(M * D, AL);
@@ -336,7 +354,7 @@ extern "C" int theia_model_debug_ptr(theia_model* m, const char* name, int i, vo
                                      int* is_f32) {
   if (!m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
   const std::string n(name);
-  const long long M = static_cast<long long>(m->last_B) * 197, P = static_cast<long long>(m->last_B) * 256;
+  const long long M = static_cast<long long>(m->last_B) * m->N, P = static_cast<long long>(m->last_B) * 256;
   const int D = m->D;
   auto AB = [&](long long off) { return static_cast<void*>(reinterpret_cast<bf16*>(m->ws + m->o_actbf) + off); };
   *is_f32 = 0;
@@ -374,6 +392,39 @@ extern "C" int theia_model_bind(theia_model* m, float* master, float* grads, voi
   m->ws = static_cast<uint8_t*>(workspace);
   return THEIA_OK;
 }
+
+namespace theia {
+// Per-token additive table of the embedding stage (hf:modeling_vit.py:116-126; backbones.py:70-93,186-217):
+//   patch token t: position embedding of its slot;  CLS: cls_token + pos[0];  register r: reg_token[r] + reg_pos[r]
+__global__ void token_table_kernel(float* __restrict__ tab, const float* __restrict__ pos, const float* __restrict__ cls,
+                                   const float* __restrict__ regt, const float* __restrict__ regp, int N, int D, int p0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * D) return;
+  const int t = i / D, d = i - t * D;
+  float v;
+  if (t < p0) v = cls[d] + pos[d];
+  else if (t < p0 + 196) v = pos[(t - p0 + 1) * D + d];
+  else v = regt[(t - p0 - 196) * D + d] + regp[(t - p0 - 196) * D + d];
+  tab[i] = v;
+}
+// gradient of the table -> gradients of position_embeddings / cls_token / reg_token / reg_pos_embed
+__global__ void token_table_grad_kernel(const float* __restrict__ tg, float* __restrict__ gpos, float* __restrict__ gcls,
+                                        float* __restrict__ gregt, float* __restrict__ gregp, int N, int D, int p0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * D) return;
+  const int t = i / D, d = i - t * D;
+  const float v = tg[i];
+  if (t < p0) {
+    gcls[d] = v;
+    gpos[d] = v;
+  } else if (t < p0 + 196) {
+    gpos[(t - p0 + 1) * D + d] = v;
+  } else {
+    gregt[(t - p0 - 196) * D + d] = v;
+    gregp[(t - p0 - 196) * D + d] = v;
+  }
+}
+}  // namespace theia
 
 namespace {
 
@@ -587,6 +638,10 @@ extern "C" int theia_model_pack(theia_model* m, void* stream) {
   Ctx c{m, static_cast<cudaStream_t>(stream)};
   const int D = m->D, C = m->D;
   TRY(theia_cast_bf16(c.W(m->pew), c.PB(m->wpe), 768LL * D, c.s));
+  token_table_kernel<<<(m->N * D + 255) / 256, 256, 0, c.s>>>(c.PF(m->tokt), c.W(m->pos), m->cls >= 0 ? c.W(m->cls) : nullptr,
+                                                             m->regt >= 0 ? c.W(m->regt) : nullptr,
+                                                             m->regp >= 0 ? c.W(m->regp) : nullptr, m->N, D, m->p0);
+  THEIA_CHECK_LAUNCH("token_table");
   for (int l = 0; l < m->L; ++l) {
     const LayerP& p = m->lp[l];
     const LayerW& w = m->lw[l];
@@ -647,15 +702,16 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
   if (B < 1 || B > m->Bmax) return set_error(THEIA_ERR_ARG, "batch %d outside [1,%d]", B, m->Bmax);
   Ctx c{m, static_cast<cudaStream_t>(stream)};
   const int D = m->D, C = m->D, H = m->H, L = m->L;
-  const int M = B * 197, P = B * 256;
+  const int NT = m->N;
+  const int M = B * NT, P = B * 256;
   m->last_B = B;
   TRY(theia_preprocess(images, c.AB(m->patches), B, channels_first, do_resize, do_rescale, do_normalize, mean3, std3,
-                       c.s));
+                       NT, m->p0, c.s));
   {  // patch embedding + CLS + position embeddings (hf:modeling_vit.py:100-128,153-168)
     theia_gemm_desc d = gemm_base(M, D, 768);
     d.A = c.AB(m->patches), d.lda = 768, d.B = c.PB(m->wpe), d.ldb = 768;
     d.out = c.AB(m->x[0]), d.ldo = D, d.bias = c.W(m->peb);
-    d.epi = THEIA_EPI_POSCLS, d.pos = c.W(m->pos), d.cls = c.W(m->cls), d.tokens = 197;
+    d.epi = THEIA_EPI_POSCLS, d.pos = c.PF(m->tokt), d.tokens = NT, d.tok_p0 = m->p0, d.tok_p1 = m->p0 + 196;
     TRY(theia_gemm(&d, c.s));
   }
   for (int l = 0; l < L; ++l) {  // hf:modeling_vit.py:328-346
@@ -665,7 +721,7 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
     TRY(theia_layernorm_fwd(c.AB(m->x[l]), c.W(p.ln1w), c.W(p.ln1b), c.AB(a.ln1), c.AF(a.mean1), c.AF(a.rstd1), M, D,
                             m->cfg.ln_eps, c.s));
     TRY(linear(c, c.AB(a.ln1), c.PB(w.wqkv), c.W(p.qb), c.AB(a.qkv), M, 3 * D, D, 0));
-    TRY(theia_attention_tc_fwd(c.AB(a.qkv), c.AB(a.attn), c.AF(a.lse), B, 197, H, c.s));
+    TRY(theia_attention_tc_fwd(c.AB(a.qkv), c.AB(a.attn), c.AF(a.lse), B, NT, H, c.s));
     TRY(linear(c, c.AB(a.attn), c.PB(w.wo), c.W(p.ob), c.AB(a.xmid), M, D, D, THEIA_EPI_RESID, c.AB(m->x[l])));
     TRY(theia_layernorm_fwd(c.AB(a.xmid), c.W(p.ln2w), c.W(p.ln2b), c.AB(a.ln2), c.AF(a.mean2), c.AF(a.rstd2), M, D,
                             m->cfg.ln_eps, c.s));
@@ -686,7 +742,7 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
     const HeadA& a = m->ha[t];
     if (p.hw == 1) {  // pred[B, C_t] = tokens[:, 0] W^T + b : rows of A are the CLS rows (pitch 197*D)
       theia_gemm_desc d = gemm_base(B, p.ct, C);
-      d.A = c.AB(m->tokens), d.lda = 197LL * D, d.B = c.PB(w.l), d.ldb = C;
+      d.A = c.AB(m->tokens), d.lda = 1LL * NT * D, d.B = c.PB(w.l), d.ldb = C;
       d.out = preds[t], d.ldo = p.ct, d.bias = c.W(p.lb), d.epi = THEIA_EPI_OUT_F32;
       TRY(theia_gemm(&d, c.s));
       continue;
@@ -697,8 +753,8 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
     TRY(zero_f32(c, st0, 6LL * B));
     theia_conv_geom g;
     // pad: ConvTranspose2d(3x3, s1) 14 -> 16 over the spatial tokens (CLS skipped by the base offset)
-    conv_geom_16(g, C, 14, B, D, 14LL * D, 197LL * D, -2);
-    TRY(conv3x3(c, c.AB(m->tokens) + D, g, c.PB(w.padF), c.W(p.padb), c.AB(a.padout), C, C, THEIA_EPI_STATS, st0, nullptr));
+    conv_geom_16(g, C, 14, B, D, 14LL * D, 1LL * NT * D, -2);
+    TRY(conv3x3(c, c.AB(m->tokens) + 1LL * m->p0 * D, g, c.PB(w.padF), c.W(p.padb), c.AB(a.padout), C, C, THEIA_EPI_STATS, st0, nullptr));
     TRY(theia_ln3d_apply(c.AB(a.padout), st0, c.PF(w.gb[0][0]), c.PF(w.gb[0][1]), c.AB(a.ln0), B, 256 * C, 1e-5f, C, 0,
                          0, c.s));
     if (p.hw == 16) {
@@ -729,7 +785,8 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
   const int B = m->last_B;
   if (B < 1) return set_error(THEIA_ERR_ARG, "backward before forward");
   const int D = m->D, C = m->D, H = m->H, L = m->L;
-  const int M = B * 197, P = B * 256;
+  const int NT = m->N;
+  const int M = B * NT, P = B * 256;
   TRY(zero_f32(c, m->grads, m->n_params_total));
   cudaError_t e = cudaMemsetAsync(c.AB(m->dtok), 0, sizeof(bf16) * M * D, c.s);
   if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
@@ -748,7 +805,7 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
       {  // dW[C_t, C] = dp^T cls_tokens
         theia_gemm_desc d = gemm_base(p.ct, C, B);
         d.a_mode = THEIA_OP_MN2D, d.b_mode = THEIA_OP_MN2D;
-        d.A = dp, d.lda = p.ct, d.B = c.AB(m->tokens), d.ldb = 197LL * D;
+        d.A = dp, d.lda = p.ct, d.B = c.AB(m->tokens), d.ldb = 1LL * NT * D;
         d.out = c.G(p.lw), d.ldo = C, d.epi = THEIA_EPI_ATOMIC;
         TRY(theia_gemm(&d, c.s));
       }
@@ -756,7 +813,7 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
       {  // d tokens[:, 0] += dp W
         theia_gemm_desc d = gemm_base(B, C, p.ct);
         d.A = dp, d.lda = p.ct, d.B = c.PB(w.lT), d.ldb = p.ct;
-        d.out = c.AB(m->dtok), d.ldo = 197LL * D, d.epi = THEIA_EPI_RESID, d.aux = c.AB(m->dtok);
+        d.out = c.AB(m->dtok), d.ldo = 1LL * NT * D, d.epi = THEIA_EPI_RESID, d.aux = c.AB(m->dtok);
         TRY(theia_gemm(&d, c.s));
       }
       continue;
@@ -804,13 +861,13 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
         TRY(theia_gather4(wsc, c.G(convw[i]), 1, 1, C, C, 9, 1, C, 1, 1LL * C * C, 0, 0, c.s));
         TRY(convT2x_dgrad(c, dA1, c.PB(convD[i]), dA0, C, B, vv[i - 1], pp[i - 1], vv[i], pp[i], pad));
       } else {
-        conv_geom_16(g, C, 14, B, D, 14LL * D, 197LL * D, -2);
-        TRY(conv_wgrad(c, dA1, c.AB(m->tokens) + D, g, wsc, C));
+        conv_geom_16(g, C, 14, B, D, 14LL * D, 1LL * NT * D, -2);
+        TRY(conv_wgrad(c, dA1, c.AB(m->tokens) + 1LL * m->p0 * D, g, wsc, C));
         // grad Wt[ci][co][t] = ws[8-t][co][ci]
         TRY(theia_gather4(wsc, c.G(convw[i]), 1, 1, C, C, 9, 1, 1, C, -1LL * C * C, 0, 8LL * C * C, c.s));
         // dgrad onto the 14x14 token grid, accumulated over heads
         conv_geom_16(g, C, 16, B, C, 16LL * C, 256LL * C, 0);
-        g.out_h = 14, g.out_w = 14, g.out_img_rows = 197, g.out_row_off = 1, g.out_wpitch = 14;
+        g.out_h = 14, g.out_w = 14, g.out_img_rows = NT, g.out_row_off = m->p0, g.out_wpitch = 14;
         TRY(conv3x3(c, dA1, g, c.PB(convD[i]), nullptr, c.AB(m->dtok), D, C, THEIA_EPI_RESID, nullptr, c.AB(m->dtok)));
       }
     }
@@ -837,7 +894,7 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     // attention
     TRY(wgrad(c, dx2, c.AB(a.attn), c.G(p.ow), M, D, D));
     TRY(linear(c, dx2, c.PB(w.woT), nullptr, c.AB(m->dattn), M, D, D, 0));
-    TRY(theia_attention_tc_bwd(c.AB(a.qkv), c.AB(a.attn), c.AB(m->dattn), c.AF(a.lse), c.AB(m->dqkv), B, 197, H, c.s));
+    TRY(theia_attention_tc_bwd(c.AB(a.qkv), c.AB(a.attn), c.AB(m->dattn), c.AF(a.lse), c.AB(m->dqkv), B, NT, H, c.s));
     TRY(wgrad(c, c.AB(m->dqkv), c.AB(a.ln1), c.G(p.qw), M, 3 * D, D));
     TRY(theia_colsum(c.AB(m->dqkv), c.G(p.qb), M, 3 * D, 3 * D, 0, c.s));
     TRY(linear(c, c.AB(m->dqkv), c.PB(w.wqkvT), nullptr, c.AB(m->dln), M, D, 3 * D, 0));
@@ -845,10 +902,12 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
                             c.G(p.ln1w), c.G(p.ln1b), l > 0 ? c.G(m->lp[l - 1].f2b) : nullptr, M, D, c.s));
   }
   // embeddings: position / cls / patch projection
-  TRY(theia_batchsum(dx, c.G(m->pos), B, 197 * D, c.s));
-  e = cudaMemcpyAsync(c.G(m->cls), c.G(m->pos), sizeof(float) * D, cudaMemcpyDeviceToDevice, c.s);
-  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memcpy: %s", cudaGetErrorString(e));
+  TRY(theia_batchsum(dx, c.AF(m->tgrad), B, NT * D, c.s));
+  token_table_grad_kernel<<<(NT * D + 255) / 256, 256, 0, c.s>>>(c.AF(m->tgrad), c.G(m->pos), m->cls >= 0 ? c.G(m->cls) : nullptr,
+                                                                 m->regt >= 0 ? c.G(m->regt) : nullptr,
+                                                                 m->regp >= 0 ? c.G(m->regp) : nullptr, NT, D, m->p0);
+  THEIA_CHECK_LAUNCH("token_table_grad");
   TRY(wgrad(c, dx, c.AB(m->patches), c.G(m->pew), M, D, 768));
-  TRY(theia_colsum(dx, c.G(m->peb), M, D, D, 197, c.s));
+  TRY(theia_colsum_tokens(dx, c.G(m->peb), M, D, D, NT, m->p0, m->p0 + 196, c.s));
   return THEIA_OK;
 }

@@ -130,8 +130,15 @@ class RobotVisionFM(nn.Module):
         **kwargs: Any,
     ) -> None:
         super().__init__()
-        if not isinstance(backbone, str) or backbone not in BACKBONES:
+        # build_backbone (backbones.py:506-526): "reg" -> DeiTReg, "nocls" -> DeiTNoCLS, "deit" -> DeiT
+        self._variant, base_name = 0, backbone
+        if isinstance(backbone, str) and backbone.startswith("reg-"):
+            self._variant, base_name = 2, backbone[len("reg-"):]
+        elif isinstance(backbone, str) and backbone.startswith("nocls-"):
+            self._variant, base_name = 1, backbone[len("nocls-"):]
+        if not isinstance(backbone, str) or base_name not in BACKBONES:
             raise NotImplementedError(f"Requested {backbone} is not implemented.")  # backbones.py:526
+        self._num_reg = int(kwargs.pop("num_reg_tokens", 7)) if self._variant == 2 else 0
         if pretrained:
             raise NotImplementedError("pretrained hub weights need network access; use load_pretrained_weights()")
         if translator != "lconv":
@@ -149,11 +156,12 @@ class RobotVisionFM(nn.Module):
         self.image_size = image_size
         self.final_spatial = None
         self.feature_reduce_method = feature_reduce_method
-        self.no_cls = False
-        self.num_reg_tokens = 0
+        self.no_cls = self._variant == 1            # rvfm.py:59 hasattr(backbone, "no_cls")
+        self.num_reg_tokens = self._num_reg         # rvfm.py:60
+        self._seq = 196 + (0 if self._variant == 1 else 1) + self._num_reg
         self.target_loss_weights = target_loss_weights
         self.backbone_name = backbone
-        self.hidden, self.heads = BACKBONES[backbone]
+        self.hidden, self.heads = BACKBONES[base_name]
         self.image_mean, self.image_std = IMAGE_MEAN, IMAGE_STD
         self._teachers = list(target_feature_sizes.keys()) if target_feature_sizes else []
         self._max_batch = int(kwargs.pop("max_batch", 0))
@@ -199,6 +207,7 @@ class RobotVisionFM(nn.Module):
         cfg.hidden, cfg.heads, cfg.layers, cfg.image, cfg.patch = self.hidden, self.heads, 12, 224, 16
         cfg.max_batch = max_batch
         cfg.ln_eps = 1e-12
+        cfg.variant, cfg.num_reg_tokens = self._variant, self._num_reg
         cfg.num_teachers = len(self._teachers)
         if cfg.num_teachers > L.MAX_TEACHERS:
             raise NotImplementedError("too many teachers")
@@ -398,7 +407,7 @@ class RobotVisionFM(nn.Module):
     def forward_feature(self, x: torch.Tensor, **kwargs: Any) -> torch.Tensor:
         """rvfm.py:94-113.  Returns fp32 like the reference; not differentiable (inference API)."""
         B = len(x) if isinstance(x, (list, tuple)) else (1 if getattr(x, "ndim", 4) == 3 else x.shape[0])
-        tok = torch.empty((B, 197, self.hidden), dtype=torch.bfloat16, device=self._flat.device)
+        tok = torch.empty((B, self._seq, self.hidden), dtype=torch.bfloat16, device=self._flat.device)
         self._run_backbone(x, kwargs, False, (), tokens_out=tok)
         return handle_feature_output(tok.float(), self.feature_reduce_method, self.num_reg_tokens)
 
