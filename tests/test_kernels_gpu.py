@@ -39,11 +39,20 @@ def gemm(lib, **kw):
     L.check(lib.theia_gemm(C.byref(d), S()), "theia_gemm")
 
 
+# Every GEMM / implicit-GEMM test runs three ways: the launcher's own choice, single-CTA kernels only
+# (cta_group::1), and CTA pairs wherever the tile allows (cta_group::2, including the conv gathers).
+@pytest.fixture(params=["auto", "single", "pair"])
+def cta_mode(request, lib):
+    lib.theia_debug_set(8, {"auto": 0, "single": 1, "pair": 2}[request.param])
+    yield request.param
+    lib.theia_debug_set(8, 0)
+
+
 # ----------------------------------------------------------------------------- GEMM, K-major
 @pytest.mark.parametrize("M,N,K,bn", [(256, 256, 128, 0), (591, 192, 192, 0), (394, 1280, 768, 0),
-                                      (128, 128, 64, 128), (1000, 576, 192, 192), (300, 768, 3072, 256),
+                                      (128, 128, 64, 128), (1000, 576, 192, 192), (300, 768, 3072, 256), (591, 512, 192, 256),
                                       (197, 32, 192, 0)])
-def test_gemm_k2d_bias(lib, M, N, K, bn):
+def test_gemm_k2d_bias(lib, M, N, K, bn, cta_mode):
     a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.05)
     bias = rnd(N, seed=3, dtype=torch.float32)
     out = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
@@ -53,7 +62,7 @@ def test_gemm_k2d_bias(lib, M, N, K, bn):
     assert relerr(out.float(), ref) < 6e-3
 
 
-def test_gemm_epilogues(lib):
+def test_gemm_epilogues(lib, cta_mode):
     M, N, K = 394, 768, 192
     a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.08)
     bias = rnd(N, seed=3, dtype=torch.float32)
@@ -90,7 +99,7 @@ def test_gemm_epilogues(lib):
     assert relerr(out.float(), acc.clamp_min(0)) < 6e-3
 
 
-def test_gemm_poscls(lib):
+def test_gemm_poscls(lib, cta_mode):
     Bn, D, K = 3, 192, 768
     M = Bn * 197
     a = rnd(M, K, seed=1)
@@ -112,7 +121,7 @@ def test_gemm_poscls(lib):
 @pytest.mark.parametrize("Mtok,Nout,Kin,splits,bn", [(512, 256, 256, 1, 256), (1000, 320, 192, 3, 192),
                                                      (788, 768, 768, 4, 256), (640, 32, 192, 2, 0),
                                                      (985, 576, 192, 5, 128)])
-def test_gemm_wgrad_mn_major(lib, Mtok, Nout, Kin, splits, bn):
+def test_gemm_wgrad_mn_major(lib, Mtok, Nout, Kin, splits, bn, cta_mode):
     dy, x = rnd(Mtok, Nout, seed=1), rnd(Mtok, Kin, seed=2)
     dw = torch.zeros(Nout, Kin, dtype=torch.float32, device=DEV)
     gemm(lib, M=Nout, N=Kin, K=Mtok, a_mode=L.OP_MN2D, b_mode=L.OP_MN2D, A=dy, lda=Nout, B=x, ldb=Kin, out=dw,
@@ -121,7 +130,7 @@ def test_gemm_wgrad_mn_major(lib, Mtok, Nout, Kin, splits, bn):
     assert relerr(dw, ref) < 1e-4
 
 
-def test_gemm_mixed_major_b(lib):
+def test_gemm_mixed_major_b(lib, cta_mode):
     """dgrad without a transposed weight copy: B operand MN-major (W stored [K_gemm][N_gemm])."""
     M, Nout, Kin = 300, 320, 256  # y = dy[M,Nout] @ W[Nout,Kin]
     dy, w = rnd(M, Nout, seed=1), rnd(Nout, Kin, seed=2, scale=0.05)
@@ -144,8 +153,8 @@ def geom16(Cc, Hin, Bn, sw, sh, sb, shift0):
     return g
 
 
-@pytest.mark.parametrize("Cc,Bn", [(128, 3), (192, 2)])
-def test_conv3x3_fwd_relu_stats(lib, Cc, Bn):
+@pytest.mark.parametrize("Cc,Bn", [(128, 3), (192, 2), (256, 3)])
+def test_conv3x3_fwd_relu_stats(lib, Cc, Bn, cta_mode):
     x = rnd(Bn, 16, 16, Cc, seed=1)  # NHWC
     w = rnd(Cc, Cc, 3, 3, seed=2, scale=0.05, dtype=torch.float32)  # Conv2d [co,ci,kh,kw]
     bias = rnd(Cc, seed=3, dtype=torch.float32)
@@ -163,7 +172,7 @@ def test_conv3x3_fwd_relu_stats(lib, Cc, Bn):
     torch.testing.assert_close(stats[:, 1], (o * o).sum(1), rtol=2e-4, atol=1e-2)
 
 
-def test_pad_convtranspose_fwd_and_dgrad(lib):
+def test_pad_convtranspose_fwd_and_dgrad(lib, cta_mode):
     Cc, Bn, D = 128, 2, 128
     tok = rnd(Bn, 197, D, seed=1)
     wt = rnd(Cc, Cc, 3, 3, seed=2, scale=0.05, dtype=torch.float32).to(torch.bfloat16).float()  # [ci,co,kh,kw]
@@ -195,14 +204,15 @@ def test_pad_convtranspose_fwd_and_dgrad(lib):
     assert torch.equal(dtok[:, 0], dtok0[:, 0])  # CLS rows untouched
 
 
-def test_conv_wgrad(lib):
-    Cc, Bn = 128, 3
+@pytest.mark.parametrize("Cc", [128, 256])
+def test_conv_wgrad(lib, Cc, cta_mode):
+    Bn = 3
     x = rnd(Bn, 16, 16, Cc, seed=1)
     dy = rnd(Bn * 256, Cc, seed=2)
     ws = torch.zeros(9, Cc, Cc, dtype=torch.float32, device=DEV)
     g = geom16(Cc, 16, Bn, Cc, 16 * Cc, 256 * Cc, -1)
     gemm(lib, M=Cc, N=Cc, K=Bn * 256, a_mode=L.OP_MN2D, b_mode=L.OP_CONV_MN, A=dy, lda=Cc, B=x, conv=g, out=ws,
-         ldo=Cc, epi=L.EPI_ATOMIC, batch_z=9, out_z_stride=Cc * Cc, splits=2, bn=128)
+         ldo=Cc, epi=L.EPI_ATOMIC, batch_z=9, out_z_stride=Cc * Cc, splits=2, bn=Cc)
     w = torch.zeros(Cc, Cc, 3, 3, device=DEV, requires_grad=True)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, padding=1)
     (y * dy.float().view(Bn, 16, 16, Cc).permute(0, 3, 1, 2)).sum().backward()
@@ -210,7 +220,7 @@ def test_conv_wgrad(lib):
     assert relerr(ws, ref) < 1e-4
 
 
-def test_pad_conv_wgrad(lib):
+def test_pad_conv_wgrad(lib, cta_mode):
     Cc, Bn, D = 128, 2, 128
     tok = rnd(Bn, 197, D, seed=1)
     dy = rnd(Bn * 256, Cc, seed=2)
@@ -434,7 +444,7 @@ def _convt_geom(Cc, Bn, Hin, pitch_in, tile_w, tile_h, sub_h, sub_w, Hout_pitch,
 
 
 @pytest.mark.parametrize("which", ["t1_16to31", "t2_31to64"])
-def test_convtranspose_stride2_fwd_dgrad_wgrad(lib, which):
+def test_convtranspose_stride2_fwd_dgrad_wgrad(lib, which, cta_mode):
     Cc, Bn = 128, 2
     if which == "t1_16to31":
         Hin, pin, Hout, pout, pad, opad, tw, th = 16, 16, 31, 32, 1, 0, 16, 8

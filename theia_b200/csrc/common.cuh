@@ -46,6 +46,16 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// explicit shared-space accesses (pointer arithmetic on the dynamic smem base otherwise compiles to generic LD/ST)
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -122,6 +132,120 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// G = CTAs per MMA.  G == 1 forwards to the single-CTA forms above.  With G == 2 the kernel runs as clusters of
+// two CTAs on one TPC: rank 0 issues the MMAs for both, every CTA's TMA loads complete on rank 0's barrier, and
+// commits are multicast to the same barrier offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of both CTAs
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier given by its shared::cluster address (own or peer CTA)
+// Relaxed: the callers order their TMEM reads with tcgen05.wait::ld + tcgen05.fence::before_thread_sync; a
+// release at cluster scope would drain every outstanding global store of the warp (MEMBAR) on each tile.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <int G>
+__device__ __forceinline__ void tma_load_2d_g(const void* tmap, void* smem_dst, uint32_t bar_cluster_addr, int c0,
+                                              int c1) {
+  if (G == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+template <int G>
+__device__ __forceinline__ void tma_load_4d_g(const void* tmap, void* smem_dst, uint32_t bar_cluster_addr, int c0,
+                                              int c1, int c2, int c3) {
+  if (G == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+        "%5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
+template <int G>
+__device__ __forceinline__ void tmem_alloc_g(uint32_t* smem_slot, uint32_t ncols) {
+  if (G == 1) {
+    tmem_alloc(smem_slot, ncols);
+  } else {  // issued by the same warp of BOTH CTAs; each CTA gets the (identical) address in its own slot
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(ncols)
+                 : "memory");
+  }
+}
+template <int G>
+__device__ __forceinline__ void tmem_relinquish_g() {
+  if (G == 1) {
+    tmem_relinquish();
+  } else {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int G>
+__device__ __forceinline__ void tmem_dealloc_g(uint32_t taddr, uint32_t ncols) {
+  if (G == 1) {
+    tmem_dealloc(taddr, ncols);
+  } else {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  }
+}
+// G == 2: D[256 x N] over the TMEM of both CTAs; A = each CTA's 128 rows, B = each CTA's N/2 rows, the
+// descriptors name the same shared-memory offsets in both CTAs.  Issued by ONE thread of the leader CTA.
+template <int G>
+__device__ __forceinline__ void tc_mma_bf16_g(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if (G == 1) {
+    tc_mma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// G == 2: the arrive lands on the barrier at this offset in BOTH CTAs of the pair
+template <int G>
+__device__ __forceinline__ void tc_commit_g(uint64_t* bar) {
+  if (G == 1) {
+    tc_commit(bar);
+  } else {
+    const uint16_t mask = 3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+  }
+}
 
 // Shared-memory matrix descriptor for tcgen05.mma (SWIZZLE_128B, version 1).
 //   K-major operand tile  [rows][64 bf16]  (128-byte rows, 8-row swizzle atoms): SBO = 1024

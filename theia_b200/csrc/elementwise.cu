@@ -787,12 +787,18 @@ extern "C" int theia_layernorm_fwd(const void* x, const float* gamma, const floa
   return THEIA_OK;
 }
 
+static int g_ln_bwd_grid_mult = 2;
+extern "C" int theia_debug_ln_grid(int mult) {
+  if (mult >= 1 && mult <= 16) g_ln_bwd_grid_mult = mult;
+  return 0;
+}
+
 extern "C" int theia_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                                    const float* rstd, const void* dadd, void* dx, float* dgamma, float* dbeta,
                                    float* dxsum, int M, int D, void* stream) {
   if (D % 8 != 0 || D > 1024) return set_error(THEIA_ERR_ARG, "layernorm: D %% 8 == 0 and D <= 1024 required");
   if (M <= 0) return THEIA_OK;
-  int grid = num_sms() * 4;
+  int grid = num_sms() * g_ln_bwd_grid_mult;
   if (grid > (M + 7) / 8) grid = (M + 7) / 8;
   const size_t sm = 3 * D * sizeof(float);
 #define LNB(N)                                                                                                      \

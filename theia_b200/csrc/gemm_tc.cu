@@ -7,15 +7,17 @@
 //                            = the convolution padding)
 //   warp 1   MMA issuer     (one thread, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
 //   warp 2   TMEM allocator
-//   warps 4-11 epilogue     (tcgen05.ld -> registers -> swizzled smem transpose -> coalesced
-//                            global stores with the fused epilogue; two warps per TMEM lane quarter,
-//                            alternating 32-column chunks; epilogue flags are compile-time)
+//   warps 4-11 epilogue     (tcgen05.ld 32x32b: every thread owns one output row and 32 consecutive columns
+//                            of a chunk; the fused epilogue runs on that layout and stores with 256-bit
+//                            st.global (one full 32-byte sector per lane); two warps per TMEM lane quarter,
+//                            alternating chunks; epilogue flags are compile-time)
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring
 // (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Operand modes (include/theia_b200.h): K-major 2-D, MN-major 2-D (wgrad), K-major NHWC
 // gather with the taps folded into K (forward / dgrad convolutions), MN-major NHWC gather of
 // one tap (convolution wgrad, tap = z slice).
+#include <stdlib.h>
 #include <cuda.h>
 
 #include "common.cuh"
@@ -28,6 +30,7 @@ struct GemmK {
   int M, N;
   int num_kb, kb_per_split, splits, batch_z;
   int m_tiles, n_tiles, total_items;
+  int m_units;  // m_tiles / CTAs per MMA (rounded up): the M extent of the tile scheduler
   int a_mode, b_mode;
   int cchunks;  // CONV_K: 64-channel chunks per tap
   int es;       // gather stride of the NHWC operand
@@ -52,6 +55,7 @@ struct GemmK {
   long long out_z_stride;
   uint32_t idesc;
   uint32_t a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep;
+  int dbg;  // diagnostics (theia_debug_set key 7): 1 = no TMA loads after the first ring fill, 2 = skip the epilogue
 };
 
 constexpr int BM = 128;
@@ -59,16 +63,20 @@ constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
-constexpr int STAGING_BYTES = EPI_WARPS * 32 * 32 * 4;
+constexpr int STAGING_BYTES = EPI_WARPS * 4 * 32 * 4;  // per-warp bias slice of the current tile (<= 4 chunks x 32 floats)
 constexpr int SMEM_LIMIT = 232448;  // 227 KB
 
 constexpr int AUX_SLOTS = 3;                                  // per-warp ring depth (32x32 bf16 chunks)
 constexpr int AUX_RING_BYTES = EPI_WARPS * AUX_SLOTS * 2048;  // 48 KB
 constexpr int AUXF = THEIA_EPI_RESID | THEIA_EPI_MUL_AUX | THEIA_EPI_MUL_RELUMASK;
 
-template <int BN, bool RING>
+// PAIR = CTAs per MMA: 1 = cta_group::1 (128 x BN tile per CTA), 2 = cta_group::2 (a cluster of two CTAs on
+// one TPC computes a 256 x BN tile; each CTA stages its own 128 A rows and HALF of the B tile, so the operand
+// traffic per CTA -- L2 -> SM and shared-memory writes -- drops from 48 to 32 KB per 64-deep K block).
+template <int BN, bool RING, int PAIR>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / PAIR;  // B rows (K-major) / columns (MN-major) staged by one CTA
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EXTRA = STAGING_BYTES + (RING ? AUX_RING_BYTES : 0);
   static constexpr int STAGES = (SMEM_LIMIT - EXTRA - 1024 - 256) / STAGE_BYTES;
@@ -80,12 +88,13 @@ struct Item {
   int m_blk, n_blk, z, kb0, kb1;
 };
 
+// m_blk is returned in scheduling units (CTA pairs under cta_group::2): the caller adds its cluster rank
 __device__ __forceinline__ Item decode_item(const GemmK& p, int item) {
   Item it;
   it.n_blk = item % p.n_tiles;
   int t = item / p.n_tiles;
-  it.m_blk = t % p.m_tiles;
-  t /= p.m_tiles;
+  it.m_blk = t % p.m_units;
+  t /= p.m_units;
   it.z = t % p.batch_z;
   const int s = t / p.batch_z;
   it.kb0 = s * p.kb_per_split;
@@ -130,16 +139,16 @@ __device__ __forceinline__ void normal_cdf_pdf(const float (&x)[NV], float (&cdf
 }
 
 // EPI_CT >= 0: epilogue flags are a compile-time constant (hot combinations); -1: read p.epi.
-template <int BN, int EPI_CT>
+template <int BN, int EPI_CT, int PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmK p) {
   // compile-time specialised kernels that read an aux operand stage it through a cp.async ring in shared
   // memory (48 KB in flight per SM: registers alone cannot keep enough HBM reads outstanding)
   constexpr bool RING = (EPI_CT >= 0) && ((EPI_CT & AUXF) != 0);
-  using C = Cfg<BN, RING>;
+  using C = Cfg<BN, RING, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* staging_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
+  float* bias_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
   uint8_t* aux_ring_all = smem + C::STAGES * C::STAGE_BYTES + STAGING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EXTRA);
   uint64_t* full = bars;
@@ -150,6 +159,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // scheduling unit = the CTA (PAIR 1) or the two-CTA cluster (PAIR 2); rank 0 of a pair is the MMA leader:
+  // it owns the full / tempty barriers both CTAs signal, and its commits are multicast to both CTAs
+  const int cta_rank = (PAIR == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int unit0 = (PAIR == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int nunits = (PAIR == 2) ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -162,16 +176,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], EPI_WARPS);
+      mbar_init(&tempty[s], EPI_WARPS * PAIR);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_g<PAIR>(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish_g<PAIR>();
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR == 2) cluster_sync_all();  // the peer's barriers are initialised before anything remote touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -180,42 +195,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int filled = 0;
+      for (int item = unit0; item < p.total_items; item += nunits) {
         const Item it = decode_item(p, item);
-        const int m0 = it.m_blk * BM, n0 = it.n_blk * BN;
+        const int m_blk = it.m_blk * PAIR + cta_rank;
+        const int m0 = m_blk * BM, n0 = it.n_blk * BN + cta_rank * C::B_ROWS;  // this CTA's share of the operands
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if ((p.dbg & 1) && filled >= C::STAGES) {  // diagnostic: MMA rate without operand traffic
+            if (cta_rank == 0) mbar_arrive(&full[stage]);
+            if (++stage == C::STAGES) stage = 0, phase ^= 1;
+            continue;
+          }
+          ++filled;
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          // both CTAs of a pair complete their bytes on the LEADER's barrier, which expects the sum
+          if (cta_rank == 0) mbar_expect_tx(&full[stage], C::STAGE_BYTES * PAIR);
+          const uint32_t fb = (PAIR == 2) ? mapa_u32(smem_u32(&full[stage]), 0) : smem_u32(&full[stage]);
           // ---- A ----
           if (p.a_mode == THEIA_OP_K2D) {
-            tma_load_2d(&tmA, sa, &full[stage], kb * BK, m0);
+            tma_load_2d_g<PAIR>(&tmA, sa, fb, kb * BK, m0);
           } else if (p.a_mode == THEIA_OP_MN2D) {
-            tma_load_2d(&tmA, sa, &full[stage], m0, kb * BK);
-            tma_load_2d(&tmA, sa + 8192, &full[stage], m0 + 64, kb * BK);
+            tma_load_2d_g<PAIR>(&tmA, sa, fb, m0, kb * BK);
+            tma_load_2d_g<PAIR>(&tmA, sa + 8192, fb, m0 + 64, kb * BK);
           } else {  // CONV_K
             const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
-            const int b = it.m_blk / p.tiles_per_img, ht = it.m_blk - b * p.tiles_per_img;
-            tma_load_4d(&tmA, sa, &full[stage], cc * 64, p.dw[tap], p.es * ht * p.tile_h + p.dh[tap], b);
+            const int b = m_blk / p.tiles_per_img, ht = m_blk - b * p.tiles_per_img;
+            tma_load_4d_g<PAIR>(&tmA, sa, fb, cc * 64, p.dw[tap], p.es * ht * p.tile_h + p.dh[tap], b);
           }
           // ---- B ----
           if (p.b_mode == THEIA_OP_K2D) {
             if (p.b_tap_rows > 0) {  // tap-major weight pack [tap][rows][C]
               const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
-              tma_load_2d(&tmB, sb, &full[stage], cc * 64, p.wtap[tap] * p.b_tap_rows + n0);
+              tma_load_2d_g<PAIR>(&tmB, sb, fb, cc * 64, p.wtap[tap] * p.b_tap_rows + n0);
             } else {
-              tma_load_2d(&tmB, sb, &full[stage], kb * BK, n0);
+              tma_load_2d_g<PAIR>(&tmB, sb, fb, kb * BK, n0);
             }
           } else if (p.b_mode == THEIA_OP_MN2D) {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(&tmB, sb + i * 8192, &full[stage], n0 + 64 * i, kb * BK);
+            for (int i = 0; i < C::B_ROWS / 64; ++i) tma_load_2d_g<PAIR>(&tmB, sb + i * 8192, fb, n0 + 64 * i, kb * BK);
           } else {  // CONV_MN: tap = z
             const int b = kb / p.kb_per_img, hb = kb - b * p.kb_per_img;
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_4d(&tmB, sb + i * 8192, &full[stage], n0 + 64 * i, p.dw[it.z],
-                          p.es * hb * p.rows_per_kb + p.dh[it.z], b);
+            for (int i = 0; i < C::B_ROWS / 64; ++i)
+              tma_load_4d_g<PAIR>(&tmB, sb + i * 8192, fb, n0 + 64 * i, p.dw[it.z],
+                                  p.es * hb * p.rows_per_kb + p.dh[it.z], b);
           }
           if (++stage == C::STAGES) {
             stage = 0;
@@ -226,12 +251,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int item = unit0; item < p.total_items; item += nunits) {
         const Item it = decode_item(p, item);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -245,68 +270,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
             const uint64_t db = make_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
-            tc_mma_bf16(d_tmem, da, db, p.idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16_g<PAIR>(d_tmem, da, db, p.idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          tc_commit_g<PAIR>(&empty[stage]);  // smem slot (of both CTAs) reusable once these MMAs have read it
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tfull[acc]);  // accumulator complete
+        tc_commit_g<PAIR>(&tfull[acc]);  // accumulator complete (each CTA drains its own 128 TMEM lanes)
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {
     // ============================== epilogue ==============================
+    // Row-per-thread layout straight out of TMEM: lane l of the warp owns tile row 32*wq + l and the 32
+    // consecutive columns of the current chunk.  No shared-memory transpose: a lane's 32 outputs are 64
+    // contiguous bytes (bf16) written as two 256-bit stores (full sectors); per-row addressing is computed
+    // once per tile.  Aux operands arrive through a per-warp cp.async ring in the same layout.
     const int ew = warp - 4;      // 0..7
     const int wq = ew & 3;        // TMEM lane quarter == warp % 4
     const int hsel = ew >> 2;     // this warp takes the 32-column chunks with (chunk & 1) == hsel
-    float* stg = staging_all + ew * (32 * 32);
+    const int r = wq * 32 + lane; // tile row of this lane
     int acc = 0;
     uint32_t acc_phase = 0;
     const int epi = (EPI_CT >= 0) ? EPI_CT : p.epi;
-    const int c = lane & 7;
-    const int rsub = lane >> 3;
     constexpr int NCHUNK = BN / 32;
-    // ---- aux ring (RING kernels): chunk q of this warp lives in slot q % AUX_SLOTS; the prefetch cursor
-    // (pitem, pch) runs AUX_SLOTS chunks ahead of the processing position, across tile boundaries ----
+    const bool wide = (p.ldo & 15) == 0;  // rows start 32-byte aligned: 256-bit accesses allowed
+    auto map_row = [&](int m_blk, long long& off, bool& ok, int& img) {
+      if (p.conv_out) {
+        img = m_blk / p.tiles_per_img;
+        const int ht = m_blk - img * p.tiles_per_img;
+        const int hh = r / p.tile_w, ww = r - hh * p.tile_w;
+        const int h = ht * p.tile_h + hh;
+        ok = (h < p.out_h) && (ww < p.out_w) && (m_blk < p.m_tiles);
+        off = (static_cast<long long>(img) * p.out_img_rows + p.out_row_off +
+               static_cast<long long>(h * p.sy + p.py) * p.out_wpitch + (ww * p.sx + p.px)) * p.ldo;
+      } else {
+        img = 0;
+        const long long m = static_cast<long long>(m_blk) * BM + r;
+        ok = m < p.M;
+        off = m * p.ldo;
+      }
+    };
+    // ---- aux ring (RING kernels): chunk q of this warp lives in slot q % AUX_SLOTS ([lane][4 x 16 B], the
+    // 16-byte index XOR-swizzled against bank conflicts); the prefetch cursor (pitem, pch) runs AUX_SLOTS chunks
+    // ahead of the processing position, across tile boundaries ----
     uint8_t* ring = aux_ring_all + ew * (AUX_SLOTS * 2048);
-    int pitem = blockIdx.x, pch = hsel, slot = 0;
+    const int rsw = (lane >> 1) & 3;
+    int pitem = unit0, pch = hsel, slot = 0;
     auto ring_issue = [&](int sl) {
       if (pitem < p.total_items) {
         const Item pit = decode_item(p, pitem);
-        const int nn = pit.n_blk * BN + pch * 32 + c * 4;
-        const int pimg = p.conv_out ? pit.m_blk / p.tiles_per_img : 0;
+        long long poff;
+        bool pok;
+        int pimg;
+        map_row(pit.m_blk * PAIR + cta_rank, poff, pok, pimg);
+        const int nn = pit.n_blk * BN + pch * 32;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = wq * 32 + i * 4 + rsub;
-          long long orow;
-          bool okr;
-          if (p.conv_out) {
-            const int ht = pit.m_blk - pimg * p.tiles_per_img;
-            const int hh = r / p.tile_w, ww = r - hh * p.tile_w;
-            const int h = ht * p.tile_h + hh;
-            okr = (h < p.out_h) && (ww < p.out_w);
-            orow = static_cast<long long>(pimg) * p.out_img_rows + p.out_row_off +
-                   static_cast<long long>(h * p.sy + p.py) * p.out_wpitch + (ww * p.sx + p.px);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t dst = smem_u32(ring + sl * 2048 + lane * 64 + ((j ^ rsw) << 4));
+          if (pok && nn + 8 * j < p.N) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p.aux + poff + nn + 8 * j) : "memory");
           } else {
-            orow = pit.m_blk * BM + r;
-            okr = orow < p.M;
-          }
-          const uint32_t dst = smem_u32(ring + sl * 2048 + (i * 32 + lane) * 8);
-          if (okr && nn < p.N) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p.aux + orow * p.ldo + nn)
-                         : "memory");
-          } else {
-            asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(dst), "r"(0u) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
           }
         }
         pch += 2;
         if (pch >= NCHUNK) {
           pch = hsel;
-          pitem += gridDim.x;
+          pitem += nunits;
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -315,185 +349,161 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int sidx = 0; sidx < AUX_SLOTS; ++sidx) ring_issue(sidx);
     }
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      const Item it = decode_item(p, item);
-      // ---- per-tile row bookkeeping: this lane touches rows rr = 4*i + rsub of its warp's slab ----
-      long long rowoff[8];
-      uint32_t okmask = 0;
-      int img = 0;
-      if (p.conv_out) img = it.m_blk / p.tiles_per_img;
+    const uint32_t te0 = (PAIR == 2) ? mapa_u32(smem_u32(&tempty[0]), 0) : smem_u32(&tempty[0]);
+    const uint32_t te1 = (PAIR == 2) ? mapa_u32(smem_u32(&tempty[1]), 0) : smem_u32(&tempty[1]);
+    // per-warp bias slice of the current tile ([chunk][32] floats)
+    const uint32_t sbias = smem_u32(bias_all + ew * 128);
+    if (unit0 < p.total_items) {
+      const int n_blk0 = unit0 % p.n_tiles;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = wq * 32 + i * 4 + rsub;
-        const int m = it.m_blk * BM + r;
-        long long orow;
-        bool ok;
-        if (p.conv_out) {
-          const int ht = it.m_blk - img * p.tiles_per_img;
-          const int hh = r / p.tile_w, ww = r - hh * p.tile_w;
-          const int h = ht * p.tile_h + hh;
-          ok = (h < p.out_h) && (ww < p.out_w);
-          orow = static_cast<long long>(img) * p.out_img_rows + p.out_row_off +
-                 static_cast<long long>(h * p.sy + p.py) * p.out_wpitch + (ww * p.sx + p.px);
-        } else {
-          ok = m < p.M;
-          orow = m;
+      for (int ci = 0; ci < NCHUNK / 2; ++ci) {
+        const int n = n_blk0 * BN + (hsel + 2 * ci) * 32 + lane;
+        sts32(sbias + (ci * 32 + lane) * 4, __float_as_uint((p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f));
+      }
+      __syncwarp();
+    }
+    for (int item = unit0; item < p.total_items; item += nunits) {
+      Item it = decode_item(p, item);
+      it.m_blk = it.m_blk * PAIR + cta_rank;
+      long long rowoff;
+      bool rok;
+      int img;
+      map_row(it.m_blk, rowoff, rok, img);
+      // the NEXT tile's bias slice is fetched now (one value per lane and chunk) and parked in shared memory
+      // after this tile's chunks are done: its global-load latency hides behind a whole tile of work
+      float nbias[NCHUNK / 2];
+      {
+        const int nitem = item + nunits;
+        const int nn_blk = (nitem < p.total_items) ? nitem % p.n_tiles : 0;
+#pragma unroll
+        for (int ci = 0; ci < NCHUNK / 2; ++ci) {
+          const int n = nn_blk * BN + (hsel + 2 * ci) * 32 + lane;
+          nbias[ci] = (p.bias != nullptr && n < p.N) ? p.bias[n] : 0.f;
         }
-        rowoff[i] = orow * p.ldo;
-        okmask |= (ok ? 1u : 0u) << i;
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (p.dbg & 2) {  // diagnostic: mainloop rate without an epilogue
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc ? te1 : te0);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       float st_s = 0.f, st_ss = 0.f;
-#pragma unroll 1
-      for (int ch = hsel; ch < NCHUNK; ch += 2) {
-        const bool last = (ch + 2 >= NCHUNK);
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
+      uint32_t vbuf[2][32];  // TMEM loads are software pipelined: chunk ci+1 is in flight while ci is processed
+      tmem_ld32(tacc + hsel * 32, vbuf[0]);
+#pragma unroll
+      for (int ci = 0; ci < NCHUNK / 2; ++ci) {
+        const int ch = hsel + 2 * ci;
+        const bool last = (ci + 1 == NCHUNK / 2);
         const int nbase = it.n_blk * BN + ch * 32;
-        if (RING) asm volatile("cp.async.wait_group %0;" ::"n"(AUX_SLOTS - 1) : "memory");  // this chunk's aux landed
-        if (nbase >= p.N) {  // nothing to store; still release the accumulator
-          if (last) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-          }
-          if (RING) {
-            ring_issue(slot);
-            slot = (slot + 1 == AUX_SLOTS) ? 0 : slot + 1;
-          }
-          continue;
-        }
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN + ch * 32, v);
+        uint32_t(&v)[32] = vbuf[ci & 1];
         tmem_ld_wait();
-        if (last) {  // all TMEM reads of this warp for this accumulator are done
+        if (!last) {
+          tmem_ld32(tacc + (ch + 2) * 32, vbuf[(ci + 1) & 1]);
+        } else {  // all TMEM reads of this warp for this accumulator are done
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) mbar_arrive_cluster(acc ? te1 : te0);
         }
-        // phase 1: row-per-thread -> swizzled staging (conflict-free float4 stores)
-        {
-          float4* row = reinterpret_cast<float4*>(stg + lane * 32);
+        if (RING) asm volatile("cp.async.wait_group %0;" ::"n"(AUX_SLOTS - 1) : "memory");  // this chunk's aux landed
+        const int ncols = max(0, min(32, p.N - nbase));  // multiple of 8; 0 = nothing to store in this chunk
+        float xv[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) xv[k] = __uint_as_float(v[k]);
+        if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 f;
-            f.x = __uint_as_float(v[4 * j + 0]);
-            f.y = __uint_as_float(v[4 * j + 1]);
-            f.z = __uint_as_float(v[4 * j + 2]);
-            f.w = __uint_as_float(v[4 * j + 3]);
-            row[j ^ (lane & 7)] = f;
+            const uint4 b4 = lds128(sbias + (ci * 32 + 4 * j) * 4);  // smem broadcast
+            xv[4 * j + 0] += __uint_as_float(b4.x), xv[4 * j + 1] += __uint_as_float(b4.y);
+            xv[4 * j + 2] += __uint_as_float(b4.z), xv[4 * j + 3] += __uint_as_float(b4.w);
           }
         }
-        __syncwarp();
-        // phase 2: 4 rows x 128 B per warp instruction, coalesced global access; two passes of 4 rows
-        // (16 values per lane) so the per-element math runs as 16 interleaved chains
-        const int n = nbase + c * 4;
-        const uint32_t ok = (n < p.N) ? okmask : 0u;
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && ok) bias4 = *reinterpret_cast<const float4*>(p.bias + n);
-        float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
-        uint2 aux[8];
-        if (RING) {
+        if (epi & THEIA_EPI_POSCLS) {
+          if (rok) {
+            const int t = static_cast<int>((static_cast<long long>(it.m_blk) * BM + r) % p.tokens);
+            const bool patch = (t >= p.tok_p0) && (t < p.tok_p1);
+            const float* tab = p.pos + static_cast<long long>(t) * p.N + nbase;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) aux[i] = *reinterpret_cast<const uint2*>(ring + slot * 2048 + (i * 32 + lane) * 8);
-        } else if (epi & AUXF) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            aux[i] = ((ok >> i) & 1u) ? *reinterpret_cast<const uint2*>(p.aux + rowoff[i] + n) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float xv[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int rr = (half * 4 + j) * 4 + rsub;
-            const float4 f = reinterpret_cast<const float4*>(stg + rr * 32)[c ^ (rr & 7)];
-            xv[4 * j + 0] = f.x + bias4.x, xv[4 * j + 1] = f.y + bias4.y;
-            xv[4 * j + 2] = f.z + bias4.z, xv[4 * j + 3] = f.w + bias4.w;
-          }
-          if (epi & THEIA_EPI_POSCLS) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = half * 4 + j;
-              if (!((ok >> i) & 1u)) continue;
-              const int m = it.m_blk * BM + wq * 32 + i * 4 + rsub;
-              const int t = m % p.tokens;
-              const float4 ps = *reinterpret_cast<const float4*>(p.pos + static_cast<long long>(t) * p.N + n);
-              if (t < p.tok_p0 || t >= p.tok_p1) {  // CLS / register token: the table holds the whole value
-                xv[4 * j + 0] = ps.x, xv[4 * j + 1] = ps.y, xv[4 * j + 2] = ps.z, xv[4 * j + 3] = ps.w;
-              } else {
-                xv[4 * j + 0] += ps.x, xv[4 * j + 1] += ps.y, xv[4 * j + 2] += ps.z, xv[4 * j + 3] += ps.w;
-              }
-            }
-          }
-          if (epi & THEIA_EPI_GELU) {
-            // gelu(x) = x Phi(x); its derivative Phi(x) + x phi(x) is stored (bf16) for the backward pass, so
-            // the dgrad epilogue is a plain multiply instead of a second erf/exp evaluation
-            float cdf[16], pdf[16];
-            normal_cdf_pdf<16, true>(xv, cdf, pdf);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = half * 4 + j;
-              uint2 dg;
-              dg.x = pack_bf16x2(fmaf(xv[4 * j + 0], pdf[4 * j + 0], cdf[4 * j + 0]),
-                                 fmaf(xv[4 * j + 1], pdf[4 * j + 1], cdf[4 * j + 1]));
-              dg.y = pack_bf16x2(fmaf(xv[4 * j + 2], pdf[4 * j + 2], cdf[4 * j + 2]),
-                                 fmaf(xv[4 * j + 3], pdf[4 * j + 3], cdf[4 * j + 3]));
-              if ((ok >> i) & 1u) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + rowoff[i] + n) = dg;
-            }
-#pragma unroll
-            for (int k = 0; k < 16; ++k) xv[k] *= cdf[k];
-          }
-          if (epi & THEIA_EPI_RELU) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) xv[k] = fmaxf(xv[k], 0.f);
-          }
-          if (epi & AUXF) {
-            float av[16];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a01 = unpack_bf16x2(aux[half * 4 + j].x), a23 = unpack_bf16x2(aux[half * 4 + j].y);
-              av[4 * j + 0] = a01.x, av[4 * j + 1] = a01.y, av[4 * j + 2] = a23.x, av[4 * j + 3] = a23.y;
-            }
-            if (epi & THEIA_EPI_MUL_AUX) {
-#pragma unroll
-              for (int k = 0; k < 16; ++k) xv[k] *= av[k];
-            } else if (epi & THEIA_EPI_MUL_RELUMASK) {
-#pragma unroll
-              for (int k = 0; k < 16; ++k) xv[k] = av[k] > 0.f ? xv[k] : 0.f;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 16; ++k) xv[k] += av[k];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int i = half * 4 + j;
-            const bool rok = (ok >> i) & 1u;
-            const long long off = rowoff[i] + n;
-            const float x0 = xv[4 * j + 0], x1 = xv[4 * j + 1], x2 = xv[4 * j + 2], x3 = xv[4 * j + 3];
-            if (epi & THEIA_EPI_ATOMIC) {
-              float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(it.z) * p.out_z_stride + off;
-              if (rok)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(x0), "f"(x1), "f"(x2),
-                             "f"(x3)
-                             : "memory");
-            } else if (epi & THEIA_EPI_OUT_F32) {
-              if (rok) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = make_float4(x0, x1, x2, x3);
-            } else {
-              uint2 o;
-              o.x = pack_bf16x2(x0, x1);
-              o.y = pack_bf16x2(x2, x3);
-              if (rok) *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + off) = o;
-              if (epi & (THEIA_EPI_STATS | THEIA_EPI_COLSUM)) {
-                const float msk = rok ? 1.f : 0.f;
-                const float2 q01 = unpack_bf16x2(o.x), q23 = unpack_bf16x2(o.y);
-                if (epi & THEIA_EPI_STATS) {
-                  st_s += msk * ((q01.x + q01.y) + (q23.x + q23.y));
-                  st_ss += msk * ((q01.x * q01.x + q01.y * q01.y) + (q23.x * q23.x + q23.y * q23.y));
+            for (int j = 0; j < 8; ++j) {
+              if (4 * j < ncols) {
+                const float4 ps = *reinterpret_cast<const float4*>(tab + 4 * j);
+                if (patch) {
+                  xv[4 * j + 0] += ps.x, xv[4 * j + 1] += ps.y, xv[4 * j + 2] += ps.z, xv[4 * j + 3] += ps.w;
+                } else {  // CLS / register token: the table holds the whole value
+                  xv[4 * j + 0] = ps.x, xv[4 * j + 1] = ps.y, xv[4 * j + 2] = ps.z, xv[4 * j + 3] = ps.w;
                 }
-                if (epi & THEIA_EPI_COLSUM)
-                  cs0 += msk * q01.x, cs1 += msk * q01.y, cs2 += msk * q23.x, cs3 += msk * q23.y;
               }
+            }
+          }
+        }
+        uint32_t pk[16];
+        auto store_bf16_row = [&](bf16* base) {  // pk[16] = this lane's 32 bf16 outputs
+          if (!rok) return;
+          bf16* dst = base + rowoff + nbase;
+          if (wide && ncols == 32) {
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(pk[0]), "r"(pk[1]),
+                         "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                         : "memory");
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16), "r"(pk[8]),
+                         "r"(pk[9]), "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
+                         : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (4 * j < ncols) *reinterpret_cast<uint2*>(dst + 4 * j) = make_uint2(pk[2 * j], pk[2 * j + 1]);
+          }
+        };
+        if (epi & THEIA_EPI_GELU) {
+          // gelu(x) = x Phi(x); its derivative Phi(x) + x phi(x) is stored (bf16) for the backward pass, so
+          // the dgrad epilogue is a plain multiply instead of a second erf/exp evaluation
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float xs[16], cdf[16], pdf[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) xs[k] = xv[16 * hh + k];
+            normal_cdf_pdf<16, true>(xs, cdf, pdf);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              pk[8 * hh + k] = pack_bf16x2(fmaf(xs[2 * k], pdf[2 * k], cdf[2 * k]),
+                                           fmaf(xs[2 * k + 1], pdf[2 * k + 1], cdf[2 * k + 1]));
+#pragma unroll
+            for (int k = 0; k < 16; ++k) xv[16 * hh + k] = xs[k] * cdf[k];
+          }
+          store_bf16_row(reinterpret_cast<bf16*>(p.out2));
+        }
+        if (epi & THEIA_EPI_RELU) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) xv[k] = fmaxf(xv[k], 0.f);
+        }
+        if (epi & AUXF) {
+          uint32_t au[16];
+          if (RING) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = lds128(smem_u32(ring + slot * 2048 + lane * 64 + ((j ^ rsw) << 4)));
+              au[4 * j + 0] = q.x, au[4 * j + 1] = q.y, au[4 * j + 2] = q.z, au[4 * j + 3] = q.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint2 q = make_uint2(0u, 0u);
+              if (rok && 4 * j < ncols) q = *reinterpret_cast<const uint2*>(p.aux + rowoff + nbase + 4 * j);
+              au[2 * j] = q.x, au[2 * j + 1] = q.y;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float2 a2 = unpack_bf16x2(au[k]);
+            if (epi & THEIA_EPI_MUL_AUX) {
+              xv[2 * k] *= a2.x, xv[2 * k + 1] *= a2.y;
+            } else if (epi & THEIA_EPI_MUL_RELUMASK) {
+              xv[2 * k] = a2.x > 0.f ? xv[2 * k] : 0.f, xv[2 * k + 1] = a2.y > 0.f ? xv[2 * k + 1] : 0.f;
+            } else {
+              xv[2 * k] += a2.x, xv[2 * k + 1] += a2.y;
             }
           }
         }
@@ -501,22 +511,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ring_issue(slot);
           slot = (slot + 1 == AUX_SLOTS) ? 0 : slot + 1;
         }
-        if (epi & THEIA_EPI_COLSUM) {  // column sums of the stored tile rows (bias gradient of the consumer)
-          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8), cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
-          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8), cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
-          cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16), cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
-          cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16), cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
-          if (rsub == 0 && n < p.N)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.colsum + n), "f"(cs0), "f"(cs1),
-                         "f"(cs2), "f"(cs3)
-                         : "memory");
+        if (epi & THEIA_EPI_ATOMIC) {
+          if (rok) {
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(it.z) * p.out_z_stride + rowoff + nbase;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (4 * j < ncols)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(xv[4 * j]),
+                             "f"(xv[4 * j + 1]), "f"(xv[4 * j + 2]), "f"(xv[4 * j + 3])
+                             : "memory");
+          }
+        } else if (epi & THEIA_EPI_OUT_F32) {
+          if (rok) {
+            float* o = reinterpret_cast<float*>(p.out) + rowoff + nbase;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (8 * j < ncols) {
+                if (wide) {
+                  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + 8 * j), "f"(xv[8 * j]),
+                               "f"(xv[8 * j + 1]), "f"(xv[8 * j + 2]), "f"(xv[8 * j + 3]), "f"(xv[8 * j + 4]),
+                               "f"(xv[8 * j + 5]), "f"(xv[8 * j + 6]), "f"(xv[8 * j + 7])
+                               : "memory");
+                } else {
+                  *reinterpret_cast<float4*>(o + 8 * j) = make_float4(xv[8 * j], xv[8 * j + 1], xv[8 * j + 2], xv[8 * j + 3]);
+                  *reinterpret_cast<float4*>(o + 8 * j + 4) =
+                      make_float4(xv[8 * j + 4], xv[8 * j + 5], xv[8 * j + 6], xv[8 * j + 7]);
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) pk[k] = pack_bf16x2(xv[2 * k], xv[2 * k + 1]);
+          store_bf16_row(reinterpret_cast<bf16*>(p.out));
+          if (epi & (THEIA_EPI_STATS | THEIA_EPI_COLSUM)) {
+            float q[32];  // the stored (rounded) values; rows / columns that are not stored count as zero
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float2 q2 = unpack_bf16x2(pk[k]);
+              const bool cok = rok && (2 * k < ncols);
+              q[2 * k] = cok ? q2.x : 0.f, q[2 * k + 1] = cok ? q2.y : 0.f;
+            }
+            if (epi & THEIA_EPI_STATS) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) st_s += q[k], st_ss += q[k] * q[k];
+            }
+            if (epi & THEIA_EPI_COLSUM) {
+              // warp reduce-scatter: after the butterfly lane l holds the sum over the warp's 32 rows of
+              // column l of the chunk (bias gradient of the consumer), one coalesced red per warp and chunk
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) {
+                const bool upper = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; ++i) {
+                  const float send = upper ? q[i] : q[i + off];
+                  const float keep = upper ? q[i + off] : q[i];
+                  q[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+              if (lane < ncols) atomicAdd(p.colsum + nbase + lane, q[0]);
+            }
+          }
         }
-        __syncwarp();
       }
+      __syncwarp();  // every lane has read this tile's bias slice
+#pragma unroll
+      for (int ci = 0; ci < NCHUNK / 2; ++ci) sts32(sbias + (ci * 32 + lane) * 4, __float_as_uint(nbias[ci]));
+      __syncwarp();
       if (epi & THEIA_EPI_STATS) {
         st_s = warp_sum(st_s);
         st_ss = warp_sum(st_ss);
-        if (lane == 0) {
+        if (lane == 0 && it.m_blk < p.m_tiles) {
           atomicAdd(p.stats + 2 * img, st_s);
           atomicAdd(p.stats + 2 * img + 1, st_ss);
         }
@@ -529,16 +594,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR == 2) cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer can still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    tmem_dealloc_g<PAIR>(tmem_base, C::TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static long long g_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static long long g_dbg[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 // ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----
 constexpr int PROF_RING = 8192;
@@ -557,26 +623,39 @@ static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
   return encode_tensor_map(tm, ptr, 2, dims, strides, box);
 }
 
-template <int BN, int EPI_CT>
+template <int BN, int EPI_CT, int PAIR>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k, cudaStream_t stream) {
-  using C = Cfg<BN, (EPI_CT >= 0) && ((EPI_CT & AUXF) != 0)>;
+  using C = Cfg<BN, (EPI_CT >= 0) && ((EPI_CT & AUXF) != 0), PAIR>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_CT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
     attr_done = true;
   }
-  int grid = k.total_items < num_sms() ? k.total_items : num_sms();
+  const int max_units = num_sms() / PAIR;
+  const int grid = (k.total_items < max_units ? k.total_items : max_units) * PAIR;
   const bool prof = g_prof_on && g_prof_n < PROF_RING;
   if (prof) cudaEventRecord(g_ev0[g_prof_n], stream);
-  gemm_tc_kernel<BN, EPI_CT><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, k);
+  if (PAIR == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = C::SMEM_BYTES, cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI_CT, PAIR>, tmA, tmB, k);
+    if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "gemm cluster launch: %s", cudaGetErrorString(e));
+  } else {
+    gemm_tc_kernel<BN, EPI_CT, PAIR><<<grid, NTHREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, k);
+  }
   if (prof) {
     cudaEventRecord(g_ev1[g_prof_n], stream);
     g_prof_flops[g_prof_n] = 2.0 * k.M * (double)k.N * (double)k.num_kb * BK * k.batch_z;
     int* mt = g_prof_meta[g_prof_n];
     mt[0] = k.M, mt[1] = k.N, mt[2] = k.num_kb * BK, mt[3] = k.a_mode, mt[4] = k.b_mode, mt[5] = k.epi;
-    mt[6] = k.splits * 1000 + k.batch_z, mt[7] = BN;
+    mt[6] = k.splits * 1000 + k.batch_z, mt[7] = BN + (PAIR == 2 ? 1 : 0);  // odd BN = CTA-pair kernel
     ++g_prof_n;
   }
   count_launch();
@@ -586,12 +665,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k
 }
 
 // hot epilogue combinations get a compile-time specialisation; anything else runs the generic kernel
-template <int BN>
+template <int BN, int PAIR>
 static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k, cudaStream_t stream) {
   switch (k.epi) {
 #define THEIA_EPI_CASE(E) \
   case (E):               \
-    return launch<BN, (E)>(tmA, tmB, k, stream);
+    return launch<BN, (E), PAIR>(tmA, tmB, k, stream);
     THEIA_EPI_CASE(0)
     THEIA_EPI_CASE(THEIA_EPI_GELU)
     THEIA_EPI_CASE(THEIA_EPI_RESID)
@@ -604,7 +683,7 @@ static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK&
     THEIA_EPI_CASE(THEIA_EPI_RELU | THEIA_EPI_STATS)
 #undef THEIA_EPI_CASE
     default:
-      return launch<BN, -1>(tmA, tmB, k, stream);
+      return launch<BN, -1, PAIR>(tmA, tmB, k, stream);
   }
 }
 
@@ -612,12 +691,24 @@ static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK&
 
 using namespace theia;
 
+// CTAs per MMA for a GEMM with this N tile and M extent: the 256-wide tile runs as a CTA pair (cta_group::2)
+// whenever there are two M tiles to pair up.  theia_debug_set(8, 1) or the
+// environment variable THEIA_GEMM_SINGLE_CTA forces single-CTA kernels, theia_debug_set(8, 2) pairs everywhere (A/B timing).
+int theia::gemm_pair_mode(int bn, int m_tiles, int a_mode) {
+  static const bool env_single = getenv("THEIA_GEMM_SINGLE_CTA") != nullptr;
+  // measured (r01, B200): the pair wins 2-14 % on every 2-D operand shape of the step, but loses ~8 % on the
+  // implicit-GEMM convolutions whose A operand is the 4-D TMA gather -- the two gathers of a pair have to
+  // finish in lockstep -- so those keep the single-CTA kernel
+  if (a_mode == THEIA_OP_CONV_K && g_dbg[8] != 2) return 1;
+  return (bn == 256 && m_tiles >= 2 && g_dbg[8] != 1 && !env_single) ? 2 : 1;
+}
+
 extern "C" int theia_debug_set(int key, long long value) {
   if (key == 0) {
     for (auto& v : g_dbg) v = 0;
     return 0;
   }
-  if (key < 0 || key >= 8) return THEIA_ERR_ARG;
+  if (key < 0 || key >= 16) return THEIA_ERR_ARG;
   g_dbg[key] = value;
   return 0;
 }
@@ -677,6 +768,9 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
     else bn = d->N > 192 ? 256 : (d->N > 128 ? 192 : 128);
   }
   if (bn != 128 && bn != 192 && bn != 256) return set_error(THEIA_ERR_ARG, "theia_gemm: bn must be 128/192/256");
+
+  const int pair = gemm_pair_mode(bn, (d->M + BM - 1) / BM, d->a_mode);
+  const int bbox = bn / pair;  // B rows / columns one CTA stages
 
   GemmK k;
   memset(&k, 0, sizeof(k));
@@ -744,11 +838,11 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   // ---- B ----
   if (d->b_mode == THEIA_OP_K2D && d->a_mode == THEIA_OP_CONV_K && g.b_tap_rows > 0) {
     // tap-major weight pack [9][b_tap_rows][C]: one 2-D map over all taps
-    rc = encode_2d(&tmB, d->B, (uint64_t)g.C, (uint64_t)9 * g.b_tap_rows, (uint64_t)g.C, 64, bn);
+    rc = encode_2d(&tmB, d->B, (uint64_t)g.C, (uint64_t)9 * g.b_tap_rows, (uint64_t)g.C, 64, bbox);
     k.b_tap_rows = g.b_tap_rows;
     for (int i = 0; i < 9; ++i) k.wtap[i] = g.wtap[i];
   } else if (d->b_mode == THEIA_OP_K2D) {
-    rc = encode_2d(&tmB, d->B, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, 64, bn);
+    rc = encode_2d(&tmB, d->B, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, 64, bbox);
   } else if (d->b_mode == THEIA_OP_MN2D) {
     rc = encode_2d(&tmB, d->B, (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, 64);
   } else if (d->b_mode == THEIA_OP_CONV_MN) {
@@ -779,8 +873,9 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   k.splits = (k.num_kb + k.kb_per_split - 1) / k.kb_per_split;  // no empty split
   k.m_tiles = (d->M + BM - 1) / BM;
   k.n_tiles = (d->N + bn - 1) / bn;
-  k.total_items = k.m_tiles * k.n_tiles * k.batch_z * k.splits;
-  k.idesc = make_idesc_bf16(BM, bn, a_mn, b_mn);
+  k.m_units = (k.m_tiles + pair - 1) / pair;
+  k.total_items = k.m_units * k.n_tiles * k.batch_z * k.splits;
+  k.idesc = make_idesc_bf16(BM * pair, bn, a_mn, b_mn);
   k.a_lbo = a_mn ? 8192 : 16;
   k.a_sbo = 1024;
   k.a_kstep = a_mn ? 2048 : 32;
@@ -788,6 +883,7 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   k.b_sbo = 1024;
   k.b_kstep = b_mn ? 2048 : 32;
   // bring-up overrides
+  k.dbg = (int)g_dbg[7];
   if (g_dbg[1]) k.a_lbo = (uint32_t)g_dbg[1];
   if (g_dbg[2]) k.a_sbo = (uint32_t)g_dbg[2];
   if (g_dbg[3]) k.b_lbo = (uint32_t)g_dbg[3];
@@ -795,7 +891,8 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   if (g_dbg[5]) k.a_kstep = (uint32_t)g_dbg[5];
   if (g_dbg[6]) k.b_kstep = (uint32_t)g_dbg[6];
 
-  if (bn == 128) return dispatch<128>(tmA, tmB, k, stream);
-  if (bn == 192) return dispatch<192>(tmA, tmB, k, stream);
-  return dispatch<256>(tmA, tmB, k, stream);
+  if (bn == 128) return dispatch<128, 1>(tmA, tmB, k, stream);
+  if (bn == 192) return dispatch<192, 1>(tmA, tmB, k, stream);
+  if (pair == 2) return dispatch<256, 2>(tmA, tmB, k, stream);
+  return dispatch<256, 1>(tmA, tmB, k, stream);
 }

@@ -465,10 +465,13 @@ int linear(const Ctx& c, const bf16* x, const bf16* w, const float* bias, void* 
   return theia_gemm(&d, c.s);
 }
 
-// split-K factor for a wgrad GEMM: fill whole waves of the persistent grid (tiles*splits close to a multiple of
-// the SM count) with at least 8 K-blocks per split; fewer splits win ties (each split adds a tile of atomics)
-int pick_splits(int tiles, int num_kb) {
-  const int sms = num_sms();
+// split-K factor for a wgrad GEMM: fill whole waves of the persistent grid (units*splits close to a multiple of
+// the resident scheduling units) with at least 8 K-blocks per split; fewer splits win ties (each split adds a
+// tile of atomics).  A scheduling unit is one CTA tile, or one 256-row CTA-pair tile when the launcher pairs.
+int pick_splits(int m_tiles, int nz_tiles, int bn, int num_kb) {
+  const int pair = gemm_pair_mode(bn, m_tiles, THEIA_OP_MN2D);  // wgrads: A = dY, MN-major
+  const int tiles = ((m_tiles + pair - 1) / pair) * nz_tiles;
+  const int sms = num_sms() / pair;
   const int maxs = num_kb / 8 > 0 ? num_kb / 8 : 1;
   int best = 1;
   double best_eff = 0.0;
@@ -491,8 +494,7 @@ int wgrad(const Ctx& c, const bf16* dy, const bf16* x, float* dw, int Mtok, int 
   d.out = dw, d.ldo = Kin, d.epi = THEIA_EPI_ATOMIC;
   const int bn = (Kin % 256 == 0) ? 256 : (Kin % 192 == 0 ? 192 : (Kin > 192 ? 256 : (Kin > 128 ? 192 : 128)));
   d.bn = bn;
-  const int tiles = ((Nout + 127) / 128) * ((Kin + bn - 1) / bn);
-  d.splits = pick_splits(tiles, (Mtok + 63) / 64);
+  d.splits = pick_splits((Nout + 127) / 128, (Kin + bn - 1) / bn, bn, (Mtok + 63) / 64);
   return theia_gemm(&d, c.s);
 }
 
@@ -591,8 +593,7 @@ int convT2x_wgrad(const Ctx& c, const bf16* x, const bf16* dy, float* wsout, int
   d.batch_z = 9, d.out_z_stride = 1LL * C * C;
   const int bn = (C % 256 == 0) ? 256 : (C % 192 == 0 ? 192 : 128);
   d.bn = bn;
-  const int tiles = 9 * ((C + 127) / 128) * ((C + bn - 1) / bn);
-  d.splits = pick_splits(tiles, Ppix / 64);
+  d.splits = pick_splits((C + 127) / 128, 9 * ((C + bn - 1) / bn), bn, Ppix / 64);
   return theia_gemm(&d, c.s);
 }
 
@@ -619,8 +620,7 @@ int conv_wgrad(const Ctx& c, const bf16* dy, const bf16* x, const theia_conv_geo
   d.batch_z = 9, d.out_z_stride = static_cast<long long>(Cout) * g.C;
   const int bn = (g.C % 256 == 0) ? 256 : (g.C % 192 == 0 ? 192 : 128);
   d.bn = bn;
-  const int tiles = 9 * ((Cout + 127) / 128) * ((g.C + bn - 1) / bn);
-  d.splits = pick_splits(tiles, P / 64);
+  d.splits = pick_splits((Cout + 127) / 128, 9 * ((g.C + bn - 1) / bn), bn, P / 64);
   return theia_gemm(&d, c.s);
 }
 

@@ -7,6 +7,10 @@ from theia_b200 import _lib as L
 M, N, K, epi = (int(v) for v in sys.argv[1:5])
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 5
 lib = L.lib()
+if len(sys.argv) > 6:
+    lib.theia_debug_set(7, int(sys.argv[6]))  # 1 = no loads, 2 = no epilogue
+if len(sys.argv) > 7:
+    lib.theia_debug_set(8, int(sys.argv[7]))  # 1 = single-CTA kernels only
 dev = "cuda"
 a = torch.randn(M, K, device=dev).to(torch.bfloat16)
 b = (0.05 * torch.randn(N, K, device=dev)).to(torch.bfloat16)
