@@ -214,7 +214,6 @@ int theia_prof_record(int i, double* ms, int* meta8);
 
 /* debug knobs for bring-up (descriptor field overrides); key 0 clears all */
 int theia_debug_set(int key, long long value);
-int theia_debug_ln_grid(int mult); /* LayerNorm-backward blocks per SM (tuning knob) */
 
 #ifdef __cplusplus
 }

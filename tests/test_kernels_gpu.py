@@ -260,7 +260,10 @@ def test_layernorm_fwd_bwd(lib, M, D):
     assert relerr(dx.float(), xr.grad + dadd.float()) < 6e-3
     assert relerr(dg, gr.grad) < 1e-3
     assert relerr(db, br.grad) < 1e-3
-    assert relerr(dxs, dx.float().sum(0)) < 1e-4  # fused column sums of the produced dx (bias gradient)
+    # fused column sums of dx (bias gradient of the producer Linear): accumulated in fp32 before the bf16
+    # rounding of dx, so they follow the fp32 reference more closely than a sum over the stored tensor
+    assert relerr(dxs, (xr.grad + dadd.float()).sum(0)) < 2e-4
+    assert relerr(dxs, dx.float().sum(0)) < 5e-3
 
 
 def test_ln3d_apply_and_bwd(lib):

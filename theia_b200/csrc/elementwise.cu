@@ -88,21 +88,60 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  optional + dadd (residual grad).
 // dgamma/dbeta (and optionally the column sums of dx = bias gradient of the producer Linear): per-lane
 // register partials over the rows a warp visits, block-reduced in shared memory, one atomic per column
-// per block.  NCH = 16-byte chunks per lane (D <= 256*NCH); dy/x stay packed in registers between passes.
-template <int NCH>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ mean_in,
-                                                            const float* __restrict__ rstd_in,
-                                                            const bf16* __restrict__ dadd, bf16* __restrict__ dx,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            float* __restrict__ dxsum, int M, int D) {
-  extern __shared__ float red[];  // [3][D]
+// per block.
+// HBM-bound (3 reads + 1 write of [M, D] bf16), so the rows are staged through shared memory by the bulk
+// async-copy engine: every warp owns a ring of STAGES row slots (dy | x | dadd, contiguous 2*D bytes each)
+// filled by cp.async.bulk with mbarrier completion -- the bytes in flight per SM (~100 KB) no longer depend on
+// registers, which are left to the 9*NCH*8 fp32 column accumulators.  One warp per row, NCH = 16-byte chunks
+// per lane (D <= 256*NCH).
+constexpr int LNB_WARPS = 12;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NCH, int LNB_STAGES>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
+layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                     const bf16* __restrict__ dadd, bf16* __restrict__ dx, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dxsum, int M, int D) {
+  extern __shared__ __align__(128) uint8_t lnb_smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int nch = D >> 3;
+  const uint32_t rowb = static_cast<uint32_t>(D) * 2;  // bytes of one bf16 row
+  const uint32_t slotb = 3 * rowb;
+  float* red = reinterpret_cast<float*>(lnb_smem);  // [3][D]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lnb_smem + 3 * D * sizeof(float)) + wib * LNB_STAGES;
+  const uint32_t ring = smem_u32(lnb_smem) + 3 * D * sizeof(float) + LNB_WARPS * LNB_STAGES * 8 +
+                        wib * LNB_STAGES * slotb;
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) red[i] = 0.f;
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < LNB_STAGES; ++st) mbar_init(&bars[st], 1);
+    fence_barrier_init();
+  }
   __syncthreads();
+
+  const int stride = gridDim.x * LNB_WARPS;
+  const int row0 = blockIdx.x * LNB_WARPS + wib;
+  auto issue = [&](int row, int st) {  // lane 0: stage one row
+    if (row < M) {
+      const long long off = static_cast<long long>(row) * D;
+      mbar_expect_tx(&bars[st], dadd ? 3 * rowb : 2 * rowb);
+      bulk_g2s(ring + st * slotb, dy + off, rowb, &bars[st]);
+      bulk_g2s(ring + st * slotb + rowb, x + off, rowb, &bars[st]);
+      if (dadd) bulk_g2s(ring + st * slotb + 2 * rowb, dadd + off, rowb, &bars[st]);
+    }
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < LNB_STAGES; ++st) issue(row0 + st * stride, st);
+  }
+
   float ag[NCH][8], ab[NCH][8], ax[NCH][8], gm[NCH][8];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
@@ -111,69 +150,67 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const bf16* __res
     for (int e = 0; e < 8; ++e) ag[c][e] = 0.f, ab[c][e] = 0.f, ax[c][e] = 0.f, gm[c][e] = 0.f;
     if (ch < nch) load8f(gamma + ch * 8, gm[c]);
   }
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
-  for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < M; row += warps_total) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const long long base = static_cast<long long>(row) * D;
-    uint4 pd[NCH], px[NCH], pa[NCH];
+  float mean_n = 0.f, rstd_n = 0.f;  // statistics of the row about to be processed (fetched one row ahead)
+  if (row0 < M) mean_n = mean_in[row0], rstd_n = rstd_in[row0];
+  int st = 0;
+  uint32_t parity = 0;
+  const float invD = 1.0f / D;
+  for (int row = row0; row < M; row += stride) {
+    const float rstd = rstd_n, nmr = -mean_n * rstd_n;
+    if (row + stride < M) mean_n = mean_in[row + stride], rstd_n = rstd_in[row + stride];
+    mbar_wait(&bars[st], parity);
+    const uint32_t slot = ring + st * slotb;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
-        pd[c] = *reinterpret_cast<const uint4*>(dy + base + ch * 8);
-        px[c] = *reinterpret_cast<const uint4*>(x + base + ch * 8);
-        if (dadd) pa[c] = *reinterpret_cast<const uint4*>(dadd + base + ch * 8);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int ch = lane + 32 * c;
-      if (ch < nch) {
-        const uint32_t* ud = reinterpret_cast<const uint32_t*>(&pd[c]);
-        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&px[c]);
+        const uint4 pd = lds128(slot + ch * 16), px = lds128(slot + rowb + ch * 16);
+        const uint32_t* ud = reinterpret_cast<const uint32_t*>(&pd);
+        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&px);
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
           const float2 d = unpack_bf16x2(ud[e2]), xv = unpack_bf16x2(ux[e2]);
-          const float xh0 = (xv.x - mean) * rstd, xh1 = (xv.y - mean) * rstd;
+          const float xh0 = fmaf(xv.x, rstd, nmr), xh1 = fmaf(xv.y, rstd, nmr);
           const float g0 = d.x * gm[c][2 * e2], g1 = d.y * gm[c][2 * e2 + 1];
           s1 += g0 + g1;
-          s2 += g0 * xh0 + g1 * xh1;
-          ag[c][2 * e2] += d.x * xh0, ag[c][2 * e2 + 1] += d.y * xh1;
+          s2 = fmaf(g0, xh0, fmaf(g1, xh1, s2));
+          ag[c][2 * e2] = fmaf(d.x, xh0, ag[c][2 * e2]), ag[c][2 * e2 + 1] = fmaf(d.y, xh1, ag[c][2 * e2 + 1]);
           ab[c][2 * e2] += d.x, ab[c][2 * e2 + 1] += d.y;
         }
       }
     }
-    s1 = warp_sum(s1) / D;
-    s2 = warp_sum(s2) / D;
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    const float ns2 = -s2;
+    const long long base = static_cast<long long>(row) * D;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
-        const uint32_t* ud = reinterpret_cast<const uint32_t*>(&pd[c]);
-        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&px[c]);
-        const uint32_t* ua = reinterpret_cast<const uint32_t*>(&pa[c]);
+        const uint4 pd = lds128(slot + ch * 16), px = lds128(slot + rowb + ch * 16);
+        uint4 pa = make_uint4(0u, 0u, 0u, 0u);
+        if (dadd) pa = lds128(slot + 2 * rowb + ch * 16);
+        const uint32_t* ud = reinterpret_cast<const uint32_t*>(&pd);
+        const uint32_t* ux = reinterpret_cast<const uint32_t*>(&px);
+        const uint32_t* ua = reinterpret_cast<const uint32_t*>(&pa);
         uint4 outp;
         uint32_t* uo = reinterpret_cast<uint32_t*>(&outp);
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
-          const float2 d = unpack_bf16x2(ud[e2]), xv = unpack_bf16x2(ux[e2]);
-          const float xh0 = (xv.x - mean) * rstd, xh1 = (xv.y - mean) * rstd;
-          float o0 = rstd * (d.x * gm[c][2 * e2] - s1 - xh0 * s2);
-          float o1 = rstd * (d.y * gm[c][2 * e2 + 1] - s1 - xh1 * s2);
-          if (dadd) {
-            const float2 a = unpack_bf16x2(ua[e2]);
-            o0 += a.x, o1 += a.y;
-          }
+          const float2 d = unpack_bf16x2(ud[e2]), xv = unpack_bf16x2(ux[e2]), a = unpack_bf16x2(ua[e2]);
+          const float xh0 = fmaf(xv.x, rstd, nmr), xh1 = fmaf(xv.y, rstd, nmr);
+          const float o0 = fmaf(rstd, fmaf(xh0, ns2, fmaf(d.x, gm[c][2 * e2], -s1)), a.x);
+          const float o1 = fmaf(rstd, fmaf(xh1, ns2, fmaf(d.y, gm[c][2 * e2 + 1], -s1)), a.y);
           uo[e2] = pack_bf16x2(o0, o1);
-          if (dxsum) {
-            const float2 q = unpack_bf16x2(uo[e2]);
-            ax[c][2 * e2] += q.x, ax[c][2 * e2 + 1] += q.y;
-          }
+          if (dxsum) ax[c][2 * e2] += o0, ax[c][2 * e2 + 1] += o1;
         }
         *reinterpret_cast<uint4*>(dx + base + ch * 8) = outp;
       }
     }
+    __syncwarp();  // every lane is done reading the slot
+    if (lane == 0) issue(row + LNB_STAGES * stride, st);
+    if (++st == LNB_STAGES) st = 0, parity ^= 1;
   }
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
@@ -787,28 +824,31 @@ extern "C" int theia_layernorm_fwd(const void* x, const float* gamma, const floa
   return THEIA_OK;
 }
 
-static int g_ln_bwd_grid_mult = 2;
-extern "C" int theia_debug_ln_grid(int mult) {
-  if (mult >= 1 && mult <= 16) g_ln_bwd_grid_mult = mult;
-  return 0;
-}
-
 extern "C" int theia_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
                                    const float* rstd, const void* dadd, void* dx, float* dgamma, float* dbeta,
                                    float* dxsum, int M, int D, void* stream) {
   if (D % 8 != 0 || D > 1024) return set_error(THEIA_ERR_ARG, "layernorm: D %% 8 == 0 and D <= 1024 required");
   if (M <= 0) return THEIA_OK;
-  int grid = num_sms() * g_ln_bwd_grid_mult;
-  if (grid > (M + 7) / 8) grid = (M + 7) / 8;
-  const size_t sm = 3 * D * sizeof(float);
-#define LNB(N)                                                                                                      \
-  layernorm_bwd_kernel<N><<<grid, 256, sm, S(stream)>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), \
-                                                        gamma, mean, rstd, static_cast<const bf16*>(dadd),          \
-                                                        static_cast<bf16*>(dx), dgamma, dbeta, dxsum, M, D)
-  if (D <= 256) LNB(1);
-  else if (D <= 512) LNB(2);
-  else if (D <= 768) LNB(3);
-  else LNB(4);
+  int grid = num_sms();  // one persistent block per SM
+  if (grid > (M + LNB_WARPS - 1) / LNB_WARPS) grid = (M + LNB_WARPS - 1) / LNB_WARPS;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dadd)) & 15)
+    return set_error(THEIA_ERR_ARG, "layernorm_bwd: dy / x / dadd must be 16-byte aligned");
+#define LNB(N, ST)                                                                                                   \
+  do {                                                                                                               \
+    const size_t sm = 3 * D * sizeof(float) + LNB_WARPS * ST * 8 + static_cast<size_t>(LNB_WARPS) * ST * 6 * D;      \
+    static bool attr_done = false;                                                                                   \
+    if (!attr_done) {                                                                                                \
+      cudaFuncSetAttribute(layernorm_bwd_kernel<N, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);    \
+      attr_done = true;                                                                                              \
+    }                                                                                                                \
+    layernorm_bwd_kernel<N, ST><<<grid, LNB_WARPS * 32, sm, S(stream)>>>(                                            \
+        static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd, static_cast<const bf16*>(dadd), \
+        static_cast<bf16*>(dx), dgamma, dbeta, dxsum, M, D);                                                         \
+  } while (0)
+  if (D <= 256) LNB(1, 4);
+  else if (D <= 512) LNB(2, 4);
+  else if (D <= 768) LNB(3, 3);
+  else LNB(4, 2);
 #undef LNB
   THEIA_CHECK_LAUNCH("layernorm_bwd");
   return THEIA_OK;

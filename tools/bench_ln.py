@@ -22,9 +22,5 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n
 f = lambda: L.check(lib.theia_layernorm_fwd(x.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), M, D, 1e-12, s))
 bw = lambda: L.check(lib.theia_layernorm_bwd(dy.data_ptr(), x.data_ptr(), g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dadd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dxs.data_ptr(), M, D, s))
-for mult in (1, 2, 3, 4, 8):
-    lib.theia_debug_ln_grid(mult)
-    print("grid mult", mult, f"LN bwd {timeit(bw)*1e3:.1f} us")
-lib.theia_debug_ln_grid(2)
 tf, tb = timeit(f), timeit(bw)
 print(f"LN fwd {tf*1e3:.1f} us  {M*D*4/tf/1e6:.0f} GB/s   LN bwd {tb*1e3:.1f} us  {M*D*8/tb/1e6:.0f} GB/s")
