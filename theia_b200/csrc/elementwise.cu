@@ -236,33 +236,59 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
 // LayerNorm over [C,H,W] per image (lconv heads), NHWC storage: n = H*W*C elements per image.
 // Statistics (sum, sumsq) come from the producing GEMM's epilogue.
 // ============================================================================================
+// One thread = 8 consecutive elements j of the [H,W,C] map, for LN3D_APPLY_G images: the fp32 affine (64 B per
+// thread) is fetched once and reused, so the L2 traffic of gamma/beta does not exceed the HBM traffic of x.
+constexpr int LN3D_APPLY_G = 8;
 __global__ void __launch_bounds__(256) ln3d_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         bf16* __restrict__ y, int n, long long total, float eps,
-                                                         int C, int Wp, int Wv) {
-  const long long i8 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
-  if (i8 >= total) return;
-  const int b = static_cast<int>(i8 / n);
-  const int j = static_cast<int>(i8 - static_cast<long long>(b) * n);
+                                                         bf16* __restrict__ y, int n, int B, float eps, int C, int Wp,
+                                                         int Wv) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (j >= n) return;
+  const int b0 = blockIdx.y * LN3D_APPLY_G;
   float ns = static_cast<float>(n);
+  bool pad = false;
   if (Wp > 0) {  // padded storage [Wp x Wp] of a [Wv x Wv] map: padding stays zero and is not counted
     const int pos = j / C, w = pos % Wp, h = pos / Wp;
     ns = static_cast<float>(Wv) * Wv * C;
-    if (w >= Wv || h >= Wv) {
-      *reinterpret_cast<uint4*>(y + i8) = make_uint4(0u, 0u, 0u, 0u);
-      return;
+    pad = (w >= Wv || h >= Wv);
+  }
+  float g[8], bb[8];
+  if (!pad) {
+    load8f(gamma + j, g);
+    load8f(beta + j, bb);
+  }
+#pragma unroll
+  for (int u0 = 0; u0 < LN3D_APPLY_G; u0 += 4) {
+    uint4 px[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = b0 + u0 + u;
+      px[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (!pad && b < B) px[u] = *reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * n + j);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int b = b0 + u0 + u;
+      if (b < B) {
+        uint4 outp = make_uint4(0u, 0u, 0u, 0u);
+        if (!pad) {
+          const float mean = stats[2 * b] / ns;
+          const float var = fmaxf(stats[2 * b + 1] / ns - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + eps);
+          const uint32_t* ux = reinterpret_cast<const uint32_t*>(&px[u]);
+          uint32_t* uo = reinterpret_cast<uint32_t*>(&outp);
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 v = unpack_bf16x2(ux[e2]);
+            uo[e2] = pack_bf16x2((v.x - mean) * rstd * g[2 * e2] + bb[2 * e2],
+                                 (v.y - mean) * rstd * g[2 * e2 + 1] + bb[2 * e2 + 1]);
+          }
+        }
+        *reinterpret_cast<uint4*>(y + static_cast<long long>(b) * n + j) = outp;
+      }
     }
   }
-  const float mean = stats[2 * b] / ns;
-  const float var = fmaxf(stats[2 * b + 1] / ns - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + eps);
-  float v[8], g[8], bb[8], o[8];
-  load8(x + i8, v);
-  load8f(gamma + j, g);
-  load8f(beta + j, bb);
-#pragma unroll
-  for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * g[e] + bb[e];
-  store8(y + i8, o);
 }
 
 // pass 1: per-image sums of g = dy*gamma and g*xhat (-> red[b][2]); dgamma/dbeta over the batch.
@@ -857,10 +883,9 @@ extern "C" int theia_layernorm_bwd(const void* dy, const void* x, const float* g
 extern "C" int theia_ln3d_apply(const void* x, const float* stats, const float* gamma_hwc, const float* beta_hwc,
                                 void* y, int B, int n, float eps, int C, int Wp, int Wv, void* stream) {
   if (n % 8 != 0 || C % 8 != 0) return set_error(THEIA_ERR_ARG, "ln3d: n, C %% 8 != 0");
-  const long long total = static_cast<long long>(B) * n;
-  const long long thr = total / 8;
-  ln3d_apply_kernel<<<static_cast<unsigned>((thr + 255) / 256), 256, 0, S(stream)>>>(
-      static_cast<const bf16*>(x), stats, gamma_hwc, beta_hwc, static_cast<bf16*>(y), n, total, eps, C, Wp, Wv);
+  dim3 ga((n / 8 + 255) / 256, (B + LN3D_APPLY_G - 1) / LN3D_APPLY_G);
+  ln3d_apply_kernel<<<ga, 256, 0, S(stream)>>>(static_cast<const bf16*>(x), stats, gamma_hwc, beta_hwc,
+                                               static_cast<bf16*>(y), n, B, eps, C, Wp, Wv);
   THEIA_CHECK_LAUNCH("ln3d_apply");
   return THEIA_OK;
 }

@@ -24,3 +24,16 @@ f = lambda: L.check(lib.theia_layernorm_fwd(x.data_ptr(), g.data_ptr(), b.data_p
 bw = lambda: L.check(lib.theia_layernorm_bwd(dy.data_ptr(), x.data_ptr(), g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dadd.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), dxs.data_ptr(), M, D, s))
 tf, tb = timeit(f), timeit(bw)
 print(f"LN fwd {tf*1e3:.1f} us  {M*D*4/tf/1e6:.0f} GB/s   LN bwd {tb*1e3:.1f} us  {M*D*8/tb/1e6:.0f} GB/s")
+
+# ---- LayerNorm[C,H,W] of the heads (stats from the conv epilogue): python tools/bench_ln.py M D ln3d
+if len(sys.argv) > 3 and sys.argv[3] == "ln3d":
+    B, C, HW = 256, 768, 256
+    n = HW * C
+    x3 = torch.randn(B, n, device=dev).to(torch.bfloat16); dy3 = torch.randn_like(x3); y3 = torch.empty_like(x3); dx3 = torch.empty_like(x3)
+    stats = torch.stack([x3.float().sum(1), (x3.float() ** 2).sum(1)], 1).contiguous()
+    g3 = torch.ones(n, device=dev); b3 = torch.zeros(n, device=dev); red = torch.zeros(B, 2, device=dev)
+    dg3 = torch.zeros(n, device=dev); db3 = torch.zeros(n, device=dev)
+    fa = lambda: L.check(lib.theia_ln3d_apply(x3.data_ptr(), stats.data_ptr(), g3.data_ptr(), b3.data_ptr(), y3.data_ptr(), B, n, 1e-5, C, 0, 0, s))
+    fb = lambda: L.check(lib.theia_ln3d_bwd(dy3.data_ptr(), x3.data_ptr(), stats.data_ptr(), g3.data_ptr(), red.data_ptr(), dx3.data_ptr(), dg3.data_ptr(), db3.data_ptr(), B, n, 1e-5, 1, C, 0, 0, s))
+    ta, tb3 = timeit(fa), timeit(fb)
+    print(f"ln3d apply {ta*1e3:.1f} us ({B*n*4/ta/1e6:.0f} GB/s)   ln3d bwd (reduce+apply) {tb3*1e3:.1f} us ({B*n*10/tb3/1e6:.0f} GB/s)")
