@@ -145,43 +145,51 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
       const int b = item / p.H, h = item - b * p.H;
       mbar_wait(&s_full[t], it & 1);
       tc_fence_after();
+      // Both passes stream the 13 sixteen-column chunks of the row with the TMEM load of chunk j+1 in flight while
+      // chunk j is processed (fully unrolled: the two register buffers alternate at compile time).
       // pass 1: row max over the valid keys
       float m = -INFINITY;
-#pragma unroll 1
-      for (int j = 0; j < AT_KSTEPS; ++j) {
-        uint32_t v[16];
-        tmem_ld16(trow + j * 16, v);
-        tmem_ld_wait();
+      {
+        uint32_t v[2][16];
+        tmem_ld16(trow, v[0]);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float s = __uint_as_float(v[e]);
-          if (j * 16 + e < p.N) m = fmaxf(m, s);
+        for (int j = 0; j < AT_KSTEPS; ++j) {
+          tmem_ld_wait();
+          if (j + 1 < AT_KSTEPS) tmem_ld16(trow + (j + 1) * 16, v[(j + 1) & 1]);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float s = __uint_as_float(v[j & 1][e]);
+            if (j * 16 + e < p.N) m = fmaxf(m, s);
+          }
         }
       }
       // pass 2: p = exp2((s - m) c2), row sum, bf16 P tile (K-major, 128-byte swizzle)
       float l = 0.f;
       const float mc = m * c2;
-#pragma unroll 1
-      for (int j = 0; j < AT_KSTEPS; ++j) {
-        uint32_t v[16];
-        tmem_ld16(trow + j * 16, v);
-        tmem_ld_wait();
-        float pv[16];
+      {
+        uint32_t v[2][16];
+        tmem_ld16(trow, v[0]);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float s = __uint_as_float(v[e]);
-          pv[e] = (j * 16 + e < p.N) ? ex2_approx_ftz(fmaf(s, c2, -mc)) : 0.f;
-          l += pv[e];
+        for (int j = 0; j < AT_KSTEPS; ++j) {
+          tmem_ld_wait();
+          if (j + 1 < AT_KSTEPS) tmem_ld16(trow + (j + 1) * 16, v[(j + 1) & 1]);
+          float pv[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float s = __uint_as_float(v[j & 1][e]);
+            pv[e] = (j * 16 + e < p.N) ? ex2_approx_ftz(fmaf(s, c2, -mc)) : 0.f;
+            l += pv[e];
+          }
+          uint4 lo, hi;
+          lo.x = pack_bf16x2(pv[0], pv[1]), lo.y = pack_bf16x2(pv[2], pv[3]);
+          lo.z = pack_bf16x2(pv[4], pv[5]), lo.w = pack_bf16x2(pv[6], pv[7]);
+          hi.x = pack_bf16x2(pv[8], pv[9]), hi.y = pack_bf16x2(pv[10], pv[11]);
+          hi.z = pack_bf16x2(pv[12], pv[13]), hi.w = pack_bf16x2(pv[14], pv[15]);
+          uint8_t* blk = prow + (j >> 2) * 16384;
+          const int ck = (j & 3) * 2;
+          *reinterpret_cast<uint4*>(blk + (((ck) ^ sw) << 4)) = lo;
+          *reinterpret_cast<uint4*>(blk + (((ck + 1) ^ sw) << 4)) = hi;
         }
-        uint4 lo, hi;
-        lo.x = pack_bf16x2(pv[0], pv[1]), lo.y = pack_bf16x2(pv[2], pv[3]);
-        lo.z = pack_bf16x2(pv[4], pv[5]), lo.w = pack_bf16x2(pv[6], pv[7]);
-        hi.x = pack_bf16x2(pv[8], pv[9]), hi.y = pack_bf16x2(pv[10], pv[11]);
-        hi.z = pack_bf16x2(pv[12], pv[13]), hi.w = pack_bf16x2(pv[14], pv[15]);
-        uint8_t* blk = prow + (j >> 2) * 16384;
-        const int ck = (j & 3) * 2;
-        *reinterpret_cast<uint4*>(blk + (((ck) ^ sw) << 4)) = lo;
-        *reinterpret_cast<uint4*>(blk + (((ck + 1) ^ sw) << 4)) = hi;
       }
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
       tc_fence_before();
@@ -233,11 +241,14 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
 // P and dS are elementwise given the saved row log-sum-exp and delta = rowsum(dO o O), so the 208 columns
 // of a row are split across 4 warps (16 compute warps); no atomics, S and dP are recomputed once (7 GEMM
 // units instead of 5) so that nothing but the 64-KB operand buffer leaves TMEM.
-// warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-19 compute.
+// warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 2-3 delta / lse of the NEXT item (two-deep smem ring,
+// so the global-load latency of that prologue is off the critical path: 0.486 -> 0.42 ms per layer), 4-19 compute.
+// (Issuing the next stage's score MMAs before the outputs of the previous one are drained -- outputs in separate
+// TMEM columns -- was measured SLOWER, 0.54 ms, and is not done.)
 // --------------------------------------------------------------------------------------------
 constexpr int ATB_THREADS = 640;
 constexpr int ATB_COMPUTE = 512;
-constexpr int ATB_SMEM = 4 * AT_TILE + AT_PBUF + 2 * AT_ROWS * 4 + 256 + 1024;
+constexpr int ATB_SMEM = 4 * AT_TILE + AT_PBUF + 4 * AT_ROWS * 4 + 256 + 1024;  // lse / delta double buffered
 
 struct AttnBwdParams {
   const bf16* out;
@@ -285,16 +296,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint8_t* sV = smem + 2 * AT_TILE;
   uint8_t* sdO = smem + 3 * AT_TILE;
   uint8_t* sPB = smem + 4 * AT_TILE;
-  float* sLse = reinterpret_cast<float*>(smem + 4 * AT_TILE + AT_PBUF);  // lse * log2(e); +inf beyond N
-  float* sDel = sLse + AT_ROWS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDel + AT_ROWS);
+  float* sLseAll = reinterpret_cast<float*>(smem + 4 * AT_TILE + AT_PBUF);  // [2][AT_ROWS] lse * log2(e); +inf beyond N
+  float* sDelAll = sLseAll + 2 * AT_ROWS;                                   // [2][AT_ROWS] rowsum(dO o O)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelAll + 2 * AT_ROWS);
   uint64_t* in_full = bars + 0;
   uint64_t* in_empty = bars + 1;
   uint64_t* sd_full = bars + 2;
   uint64_t* pb_full = bars + 3;
   uint64_t* acc_full = bars + 4;
   uint64_t* tm_free = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* del_full = bars + 6;   // [2]
+  uint64_t* del_empty = bars + 8;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -308,6 +321,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     mbar_init(pb_full, ATB_COMPUTE);
     mbar_init(acc_full, 1);
     mbar_init(tm_free, ATB_COMPUTE);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&del_full[i], 64);
+      mbar_init(&del_empty[i], ATB_COMPUTE);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -319,7 +336,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int D = p.D;
-  const uint32_t R0 = tmem_base, R1 = tmem_base + 256;
+  // TMEM columns: S 0-207 | dP 256-463; once a stage's S / dP have been consumed, dQ_t / dV_u reuse 0-63 (R2)
+  // and dK_u reuses 256-319 (RK)
+  const uint32_t R0 = tmem_base, R1 = tmem_base + 256, R2 = R0, RK = R1;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -371,62 +390,81 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           ph_tm ^= 1;
           tc_fence_after();
           mma_scores(aQ + t * 16384, aK, aO + t * 16384, aV);
-          mma_out(R0, aK);  // dQ_t = dS_t K
+          mma_out(R2, aK);  // dQ_t = dS_t K
         }
         for (int u = 0; u < 2; ++u) {  // stage B_u
           mbar_wait(tm_free, ph_tm ^ 1);
           ph_tm ^= 1;
           tc_fence_after();
           mma_scores(aK + u * 16384, aQ, aV + u * 16384, aO);
-          mma_out(R0, aO);  // dV_u = P^T_u dO
-          mma_out(R1, aQ);  // dK_u = dS^T_u Q
+          mma_out(R2, aO);  // dV_u = P^T_u dO
+          mma_out(RK, aQ);  // dK_u = dS^T_u Q
         }
         tc_commit(in_empty);
       }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ---- delta_i = sum_d dO[i,d] O[i,d] and lse_i of the NEXT item: two threads per row, straight from global ----
+    const int t = threadIdx.x - 64;  // 0..63
+    int buf = 0;
+    uint32_t ph = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int b = item / p.H, h = item - b * p.H;
+      mbar_wait(&del_empty[buf], ph ^ 1);
+      float* sLse = sLseAll + buf * AT_ROWS;
+      float* sDel = sDelAll + buf * AT_ROWS;
+#pragma unroll 1
+      for (int w0 = 0; w0 < 2 * AT_ROWS; w0 += 64) {
+        const int wi = w0 + t;
+        const int row = wi >> 1, half = wi & 1;
+        float acc = 0.f;
+        if (wi < 2 * AT_ROWS && row < p.N) {
+          const long long off = (static_cast<long long>(b) * p.N + row) * D + h * AT_HD + half * 32;
+          uint4 a[4], d[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            a[c] = *reinterpret_cast<const uint4*>(p.out + off + c * 8);
+            d[c] = *reinterpret_cast<const uint4*>(p.dout + off + c * 8);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a[c]);
+            const uint32_t* pd = reinterpret_cast<const uint32_t*>(&d[c]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = unpack_bf16x2(pa[e]), y = unpack_bf16x2(pd[e]);
+              acc += x.x * y.x + x.y * y.y;
+            }
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (wi < 2 * AT_ROWS && half == 0) {
+          sDel[row] = acc;
+          sLse[row] = row < p.N ? p.lse[(static_cast<long long>(b) * p.H + h) * p.N + row] * 1.4426950408889634f
+                                : INFINITY;
+        }
+      }
+      mbar_arrive(&del_full[buf]);
+      buf ^= 1;
+      if (buf == 0) ph ^= 1;
     }
   } else if (warp >= 4) {
     const int cw = warp - 4;
     const int wq = cw & 3;   // TMEM lane quarter (== warp % 4)
     const int cg = cw >> 2;  // column group: 16-column chunks j with (j & 3) == cg
     const int r = wq * 32 + lane;
-    const int ctid = threadIdx.x - 128;
     const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
     const float c2 = p.scale * 1.4426950408889634f;
     uint8_t* prow = sPB + r * 128;
     const int sw = r & 7;
-    uint32_t ph_sd = 0, ph_acc = 0;
+    uint32_t ph_sd = 0, ph_acc = 0, dph = 0;
+    int dbuf = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int b = item / p.H, h = item - b * p.H;
-      // ---- delta_i = sum_d dO[i,d] O[i,d], lse_i : two threads per row, straight from global ----
-      asm volatile("bar.sync 1, %0;" ::"n"(ATB_COMPUTE) : "memory");  // previous item's readers are done
-      {
-        const int row = ctid >> 1, half = ctid & 1;
-        if (row < AT_ROWS) {
-          float acc = 0.f;
-          if (row < p.N) {
-            const long long off = (static_cast<long long>(b) * p.N + row) * D + h * AT_HD + half * 32;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 a = *reinterpret_cast<const uint4*>(p.out + off + c * 8);
-              const uint4 d = *reinterpret_cast<const uint4*>(p.dout + off + c * 8);
-              const uint32_t* pa = reinterpret_cast<const uint32_t*>(&a);
-              const uint32_t* pd = reinterpret_cast<const uint32_t*>(&d);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 x = unpack_bf16x2(pa[e]), y = unpack_bf16x2(pd[e]);
-                acc += x.x * y.x + x.y * y.y;
-              }
-            }
-          }
-          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-          if (half == 0) {
-            sDel[row] = acc;
-            sLse[row] = row < p.N ? p.lse[(static_cast<long long>(b) * p.H + h) * p.N + row] * 1.4426950408889634f
-                                  : INFINITY;
-          }
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(ATB_COMPUTE) : "memory");
+      // lse / delta of this item were produced by warps 2-3 while the previous item ran
+      mbar_wait(&del_full[dbuf], dph);
+      const float* sLse = sLseAll + dbuf * AT_ROWS;
+      const float* sDel = sDelAll + dbuf * AT_ROWS;
 
       // ---------------- stage A_t : rows = queries, columns = keys ----------------
       for (int t = 0; t < 2; ++t) {
@@ -460,7 +498,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         ph_acc ^= 1;
         tc_fence_after();
         uint32_t o[16];
-        tmem_ld16(R0 + lane_sel + cg * 16, o);
+        tmem_ld16(R2 + lane_sel + cg * 16, o);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(tm_free);
@@ -524,8 +562,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         ph_acc ^= 1;
         tc_fence_after();
         uint32_t ov[16], ok_[16];
-        tmem_ld16(R0 + lane_sel + cg * 16, ov);
-        tmem_ld16(R1 + lane_sel + cg * 16, ok_);
+        tmem_ld16(R2 + lane_sel + cg * 16, ov);
+        tmem_ld16(RK + lane_sel + cg * 16, ok_);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(tm_free);
@@ -535,6 +573,9 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           store16_bf16(base + 2 * D, ov);
         }
       }
+      mbar_arrive(&del_empty[dbuf]);  // this thread no longer reads the item's lse / delta
+      dbuf ^= 1;
+      if (dbuf == 0) dph ^= 1;
     }
   }
   tc_fence_before();
