@@ -479,7 +479,7 @@ int pick_splits(int m_tiles, int nz_tiles, int bn, int num_kb) {
     const long long items = 1LL * tiles * s;
     const long long waves = (items + sms - 1) / sms;
     const double eff = static_cast<double>(items) / (waves * sms);
-    if (items < sms && s < maxs) continue;  // do not leave SMs idle when more splits are possible
+    if (items * 10 < sms * 9LL && s < maxs) continue;  // do not leave >10 % of the SMs idle when more splits are possible
     if (eff > best_eff + 0.02) best_eff = eff, best = s;
     if (items >= 4LL * sms && eff > 0.9) break;
   }
