@@ -6,6 +6,7 @@
 // Mirrors: src/theia/models/rvfm.py:115-136 (forward), hf:models/vit/modeling_vit.py:100-458
 // (ViTModel), src/theia/models/adapter_heads.py:279-359 (LightConvAdapterHead, 16x16 targets),
 // and their autograd graphs (train_rvfm.py:125).
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -473,6 +474,8 @@ int pick_splits(int m_tiles, int nz_tiles, int bn, int num_kb) {
   const int tiles = ((m_tiles + pair - 1) / pair) * nz_tiles;
   const int sms = num_sms() / pair;
   const int maxs = num_kb / 8 > 0 ? num_kb / 8 : 1;
+  // wave efficiency at which the search stops adding splits (THEIA_SPLITK_EFF overrides, for tuning runs)
+  static const double stop_eff = getenv("THEIA_SPLITK_EFF") ? atof(getenv("THEIA_SPLITK_EFF")) : 0.9;
   int best = 1;
   double best_eff = 0.0;
   for (int s = 1; s <= maxs && s <= 64; ++s) {
@@ -481,7 +484,7 @@ int pick_splits(int m_tiles, int nz_tiles, int bn, int num_kb) {
     const double eff = static_cast<double>(items) / (waves * sms);
     if (items * 10 < sms * 9LL && s < maxs) continue;  // do not leave >10 % of the SMs idle when more splits are possible
     if (eff > best_eff + 0.02) best_eff = eff, best = s;
-    if (items >= 4LL * sms && eff > 0.9) break;
+    if (items >= 4LL * sms && eff > stop_eff) break;
   }
   return best;
 }
