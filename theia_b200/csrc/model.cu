@@ -478,11 +478,12 @@ int pick_splits(int m_tiles, int nz_tiles, int bn, int num_kb) {
   static const double stop_eff = getenv("THEIA_SPLITK_EFF") ? atof(getenv("THEIA_SPLITK_EFF")) : 0.9;
   int best = 1;
   double best_eff = 0.0;
-  for (int s = 1; s <= maxs && s <= 64; ++s) {
+  const int smax = maxs < 256 ? maxs : 256;  // the last candidate is always eligible: tiny outputs (2 tiles) still split
+  for (int s = 1; s <= smax; ++s) {
     const long long items = 1LL * tiles * s;
     const long long waves = (items + sms - 1) / sms;
     const double eff = static_cast<double>(items) / (waves * sms);
-    if (items * 10 < sms * 9LL && s < maxs) continue;  // do not leave >10 % of the SMs idle when more splits are possible
+    if (items * 10 < sms * 9LL && s < smax) continue;  // do not leave >10 % of the SMs idle when more splits are possible
     if (eff > best_eff + 0.02) best_eff = eff, best = s;
     if (items >= 4LL * sms && eff > stop_eff) break;
   }
