@@ -212,7 +212,12 @@ int theia_prof_enable(int on);
 int theia_prof_collect(double* total_ms, double* total_flops, long long* launches);
 int theia_prof_record(int i, double* ms, int* meta8);
 
-/* debug knobs for bring-up (descriptor field overrides); key 0 clears all */
+/* Diagnostics of the GEMM kernel; key 0 clears all.
+ *   1-6: shared-memory descriptor field overrides (bring-up of new operand layouts)
+ *   7  : bit 0 = no operand loads after the first ring fill (MMA rate without operand traffic),
+ *        bit 1 = skip the epilogue (mainloop rate); results are garbage, timing only
+ *   8  : 1 = single-CTA kernels only (tcgen05 cta_group::1), 2 = CTA pairs wherever the tile allows, 0 = launcher's choice
+ * Environment: THEIA_GEMM_SINGLE_CTA (same as key 8 = 1), THEIA_SPLITK_EFF (wave efficiency at which split-K stops). */
 int theia_debug_set(int key, long long value);
 
 #ifdef __cplusplus
