@@ -238,7 +238,8 @@ def test_pad_conv_wgrad(lib, cta_mode):
 
 
 # ----------------------------------------------------------------------------- LayerNorm
-@pytest.mark.parametrize("M,D", [(591, 192), (300, 384), (394, 768)])
+@pytest.mark.parametrize("M,D", [(591, 192), (300, 384), (394, 768), (4133, 192), (4500, 768), (4099, 1024),
+                                 (30011, 192), (40000, 768)])  # >= 4096 rows: ring-staged forward; the last two wrap the rings
 def test_layernorm_fwd_bwd(lib, M, D):
     x, dy, dadd = rnd(M, D, seed=1, scale=2.0), rnd(M, D, seed=2), rnd(M, D, seed=3)
     gamma = 1 + 0.1 * rnd(D, seed=4, dtype=torch.float32)
