@@ -212,6 +212,10 @@ int theia_prof_enable(int on);
 int theia_prof_collect(double* total_ms, double* total_flops, long long* launches);
 int theia_prof_record(int i, double* ms, int* meta8);
 
+/* Host-side launch plan of a weight-gradient GEMM dW[Nout,Kin] += dY[Mtok,Nout]^T X[Mtok,Kin] (z = tap slices of a
+ * convolution wgrad, 1 for a Linear): N tile, CTAs per MMA (1 / 2) and split-K factor.  No GPU work. */
+int theia_plan_wgrad(int Nout, int Kin, int Mtok, int z, int* bn, int* ctas_per_mma, int* splits);
+
 /* Diagnostics of the GEMM kernel; key 0 clears all.
  *   1-6: shared-memory descriptor field overrides (bring-up of new operand layouts)
  *   7  : bit 0 = no operand loads after the first ring fill (MMA rate without operand traffic),

@@ -53,6 +53,7 @@ SYMBOLS = {
     "theia_launch_count": (_ll, []),
     "theia_gemm": (_i, [C.POINTER(GemmDesc), _vp]),
     "theia_debug_set": (_i, [_i, _ll]),
+    "theia_plan_wgrad": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "theia_prof_enable": (_i, [_i]),
     "theia_prof_record": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i)]),
     "theia_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),

@@ -490,15 +490,23 @@ int pick_splits(int m_tiles, int nz_tiles, int bn, int num_kb) {
   return best;
 }
 
+// launch plan of a wgrad GEMM (host logic only): N tile, CTAs per MMA, split-K factor; z = independent slices (taps)
+void plan_wgrad(int Nout, int Kin, int Mtok, int z, int* bn_out, int* pair_out, int* splits_out) {
+  const int bn = (Kin % 256 == 0) ? 256 : (Kin % 192 == 0 ? 192 : (Kin > 192 ? 256 : (Kin > 128 ? 192 : 128)));
+  const int m_tiles = (Nout + 127) / 128;
+  *bn_out = bn;
+  *pair_out = gemm_pair_mode(bn, m_tiles, THEIA_OP_MN2D);
+  *splits_out = pick_splits(m_tiles, z * ((Kin + bn - 1) / bn), bn, (Mtok + 63) / 64);
+}
+
 // dW[Nout,Kin] += dY[Mtok,Nout]^T * X[Mtok,Kin]   (fp32 atomics, split-K over tokens)
 int wgrad(const Ctx& c, const bf16* dy, const bf16* x, float* dw, int Mtok, int Nout, int Kin) {
   theia_gemm_desc d = gemm_base(Nout, Kin, Mtok);
   d.a_mode = THEIA_OP_MN2D, d.b_mode = THEIA_OP_MN2D;
   d.A = dy, d.lda = Nout, d.B = x, d.ldb = Kin;
   d.out = dw, d.ldo = Kin, d.epi = THEIA_EPI_ATOMIC;
-  const int bn = (Kin % 256 == 0) ? 256 : (Kin % 192 == 0 ? 192 : (Kin > 192 ? 256 : (Kin > 128 ? 192 : 128)));
-  d.bn = bn;
-  d.splits = pick_splits((Nout + 127) / 128, (Kin + bn - 1) / bn, bn, (Mtok + 63) / 64);
+  int pair = 1;
+  plan_wgrad(Nout, Kin, Mtok, 1, &d.bn, &pair, &d.splits);
   return theia_gemm(&d, c.s);
 }
 
@@ -913,5 +921,14 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
   THEIA_CHECK_LAUNCH("token_table_grad");
   TRY(wgrad(c, dx, c.AB(m->patches), c.G(m->pew), M, D, 768));
   TRY(theia_colsum_tokens(dx, c.G(m->peb), M, D, D, NT, m->p0, m->p0 + 196, c.s));
+  return THEIA_OK;
+}
+
+// Host-side launch plan of the wgrad GEMM dW[Nout,Kin] += dY[Mtok,Nout]^T X[Mtok,Kin] (z tap slices for a
+// convolution): no GPU work, lets the CPU tests check that no shape of the step leaves the grid underfilled.
+extern "C" int theia_plan_wgrad(int Nout, int Kin, int Mtok, int z, int* bn, int* ctas_per_mma, int* splits) {
+  if (!bn || !ctas_per_mma || !splits || Nout <= 0 || Kin <= 0 || Mtok <= 0 || z <= 0)
+    return set_error(THEIA_ERR_ARG, "theia_plan_wgrad: bad argument");
+  plan_wgrad(Nout, Kin, Mtok, z, bn, ctas_per_mma, splits);
   return THEIA_OK;
 }
