@@ -5,7 +5,8 @@
 // One persistent, warp-specialised kernel:
 //   warp 0   TMA producer   (cp.async.bulk.tensor 2-D / 4-D, 128-byte swizzle, OOB zero fill
 //                            = the convolution padding)
-//   warp 1   MMA issuer     (one thread, tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16)
+//   warp 1   MMA issuer     (one thread, tcgen05.mma.kind::f16: cta_group::1, 128 x BN x 16 per CTA -- or, PAIR = 2,
+//                            cta_group::2, 256 x BN x 16 per cluster of two CTAs, issued by the leader CTA only)
 //   warp 2   TMEM allocator
 //   warps 4-11 epilogue     (tcgen05.ld 32x32b: every thread owns one output row and 32 consecutive columns
 //                            of a chunk; the fused epilogue runs on that layout and stores with 256-bit
@@ -63,7 +64,7 @@ constexpr int BK = 64;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
-constexpr int STAGING_BYTES = EPI_WARPS * 4 * 32 * 4;  // per-warp bias slice of the current tile (<= 4 chunks x 32 floats)
+constexpr int BIAS_BYTES = EPI_WARPS * 4 * 32 * 4;  // per-warp bias slice of the current tile (<= 4 chunks x 32 floats)
 constexpr int SMEM_LIMIT = 232448;  // 227 KB
 
 constexpr int AUX_SLOTS = 3;                                  // per-warp ring depth (32x32 bf16 chunks)
@@ -78,7 +79,7 @@ struct Cfg {
   static constexpr int B_ROWS = BN / PAIR;  // B rows (K-major) / columns (MN-major) staged by one CTA
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EXTRA = STAGING_BYTES + (RING ? AUX_RING_BYTES : 0);
+  static constexpr int EXTRA = BIAS_BYTES + (RING ? AUX_RING_BYTES : 0);
   static constexpr int STAGES = (SMEM_LIMIT - EXTRA - 1024 - 256) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EXTRA + 256 + 1024;
@@ -149,7 +150,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* bias_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint8_t* aux_ring_all = smem + C::STAGES * C::STAGE_BYTES + STAGING_BYTES;
+  uint8_t* aux_ring_all = smem + C::STAGES * C::STAGE_BYTES + BIAS_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::EXTRA);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
