@@ -372,7 +372,7 @@ def test_preprocess_with_bicubic_resize(lib, chw):
 
 # ----------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
-@pytest.mark.parametrize("Bn,H", [(2, 3), (3, 12), (40, 6)])
+@pytest.mark.parametrize("Bn,H", [(2, 3), (3, 12), (40, 6), (100, 12)])  # the last: 8 (image, head) items per CTA, every ring wraps
 def test_attention_fwd_bwd(lib, Bn, H, impl):
     N, D = 197, H * 64
     qkv = rnd(Bn * N, 3 * D, seed=1, scale=1.5)
