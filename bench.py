@@ -100,21 +100,33 @@ def run_reference(args, cfgO, O):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B = args.cpu_batch
     P = O.init_params(cfgO, seed=0)
     params = {k: v.clone().requires_grad_(True) for k, v in P.items()}
     opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.01)
-    images, targets = O.synthetic_batch(cfgO, B, seed=0)
 
-    def step():
-        preds = O.forward(params, images, cfgO, do_resize=False)
-        losses = O.get_loss(preds, targets)
-        ml = O.main_loss(losses)
-        opt.zero_grad()
-        ml.backward()
-        opt.step()
-        return float(ml)
+    def make_step(B):
+        images, targets = O.synthetic_batch(cfgO, B, seed=0)
 
+        def step():
+            preds = O.forward(params, images, cfgO, do_resize=False)
+            losses = O.get_loss(preds, targets)
+            ml = O.main_loss(losses)
+            opt.zero_grad()
+            ml.backward()
+            opt.step()
+            return float(ml)
+        return step
+
+    # Bounded sample: the per-step batch is sized from a one-image probe step so that the whole
+    # --steps K --warmup W run stays within THEIA_REF_BUDGET_S seconds (default 240) on this host.
+    budget = float(os.environ.get("THEIA_REF_BUDGET_S", "240"))
+    probe = make_step(1)
+    probe()  # first call pays the allocator / thread-pool start-up
+    t0 = time.perf_counter()
+    probe()
+    t1 = time.perf_counter() - t0
+    B = max(1, min(args.cpu_batch, int(budget / (max(args.steps + args.warmup, 1) * t1))))
+    step = make_step(B)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -127,7 +139,8 @@ def run_reference(args, cfgO, O):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, B),
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"oracle port (torch fp32 CPU), batch {B} per step, {args.steps} steps"},
+                             "sample": f"oracle port (torch fp32 CPU), batch {B} per step (sized from a 1-image probe of {t1:.2f} s "
+                                       f"for a {budget:.0f} s budget), {args.steps} steps"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
