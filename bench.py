@@ -93,13 +93,48 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cpus():
+    """Logical CPUs this process may run on (affinity mask and cgroup quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(float(q[0]) / float(q[1]))))
+    except (OSError, ValueError, IndexError):
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
+def pick_cpu_threads(probe):
+    """The thread count the CPU arm runs with: the fastest of {all, 1/2, 1/4, 1/8 of the usable CPUs} on a
+    one-image probe step.  On a shared two-socket hyper-threaded host "all logical CPUs" can be an order of
+    magnitude slower than the physical cores of one socket; the reference gets the best of them.
+    Returns (threads, seconds of the best probe, {threads: seconds})."""
+    n = usable_cpus()
+    cand = sorted({max(1, n // d) for d in (1, 2, 4, 8)}, reverse=True)
+    timings = {}
+    for t in cand:
+        torch.set_num_threads(t)
+        probe()  # warm this thread count (pool start-up, first-touch)
+        t0 = time.perf_counter()
+        probe()
+        timings[t] = time.perf_counter() - t0
+    best = min(timings, key=timings.get)
+    torch.set_num_threads(best)
+    return best, timings[best], timings
+
+
 def run_reference(args, cfgO, O):
     """The reference's CPU implementation of the step (oracle port, torch fp32, all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     P = O.init_params(cfgO, seed=0)
     params = {k: v.clone().requires_grad_(True) for k, v in P.items()}
     opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.01)
@@ -121,10 +156,7 @@ def run_reference(args, cfgO, O):
     # --steps K --warmup W run stays within THEIA_REF_BUDGET_S seconds (default 240) on this host.
     budget = float(os.environ.get("THEIA_REF_BUDGET_S", "240"))
     probe = make_step(1)
-    probe()  # first call pays the allocator / thread-pool start-up
-    t0 = time.perf_counter()
-    probe()
-    t1 = time.perf_counter() - t0
+    cores, t1, thread_timings = pick_cpu_threads(probe)
     B = max(1, min(args.cpu_batch, int(budget / (max(args.steps + args.warmup, 1) * t1))))
     step = make_step(B)
     for _ in range(args.warmup):
@@ -140,9 +172,30 @@ def run_reference(args, cfgO, O):
             "config": workload_config(args, B),
             "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": f"oracle port (torch fp32 CPU), batch {B} per step (sized from a 1-image probe of {t1:.2f} s "
-                                       f"for a {budget:.0f} s budget), {args.steps} steps"},
+                                       f"for a {budget:.0f} s budget), {args.steps} steps; threads chosen from "
+                                       f"{ {k: round(v, 2) for k, v in thread_timings.items()} } s/probe"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(args, cfgO, O):
+    """`cpu_baseline` of the GPU arm: the oracle port timed on the host cores on a bounded sample (one step of
+    forward + loss + backward at --cpu-batch images)."""
+    Bc = args.cpu_batch
+    Pc = O.init_params(cfgO, seed=0)
+    i1, t1_ = O.synthetic_batch(cfgO, 1, seed=0)
+    cores, _, thread_timings = pick_cpu_threads(lambda: O.distill_step(Pc, i1, t1_, cfgO, do_resize=False))
+    ic, tc = O.synthetic_batch(cfgO, Bc, seed=0)
+    O.distill_step(Pc, ic, tc, cfgO, do_resize=False)  # warm-up
+    t0 = time.perf_counter()
+    nrep = 1
+    for _ in range(nrep):
+        O.distill_step(Pc, ic, tc, cfgO, do_resize=False)
+    dt = (time.perf_counter() - t0) / nrep
+    return {"value": Bc / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port (torch fp32 CPU) forward+loss+backward, batch {Bc}, {nrep} timed steps "
+                      f"(no optimizer step); threads chosen from "
+                      f"{ {k: round(v, 2) for k, v in thread_timings.items()} } s per 1-image probe"}
 
 
 def workload_config(args, B):
@@ -351,22 +404,7 @@ def main():
                 "step_tflops_all_kernels": 3.0 * fwd_g * B / 1e3 / (ms_step / 1e3),
                 "step_frac_of_peak": 3.0 * fwd_g * B / 1e3 / (ms_step / 1e3) / peak}
 
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        Bc = args.cpu_batch
-        Pc = O.init_params(cfgO, seed=0)
-        ic, tc = O.synthetic_batch(cfgO, Bc, seed=0)
-        O.distill_step(Pc, ic, tc, cfgO, do_resize=False)  # warm-up
-        t0 = time.perf_counter()
-        nrep = 1
-        for _ in range(nrep):
-            O.distill_step(Pc, ic, tc, cfgO, do_resize=False)
-        dt = (time.perf_counter() - t0) / nrep
-        cpu = {"value": Bc / dt, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": f"oracle port (torch fp32 CPU) forward+loss+backward, batch {Bc}, {nrep} timed steps "
-                         f"(no optimizer step)"}
+    cpu = cpu_baseline_leg(args, cfgO, O) if (world == 1 and not args.no_cpu_baseline) else None
 
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
