@@ -4,7 +4,8 @@
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+    python bench.py --impl reference ...      # the UNMODIFIED reference (baseline/_ref) on the host cores
+    python bench.py --impl eager ...          # the same reference modules through torch eager on one B200
 
 One step = train_rvfm.py:116-133 on one synthetic batch: forward (pre-process, DeiT student, lconv
 translator heads) -> get_loss -> main_loss = 0.9 cos + 0.1 smooth-l1 -> backward -> AdamW step,
@@ -130,27 +131,74 @@ def pick_cpu_threads(probe):
     return best, timings[best], timings
 
 
+def build_reference_module(cfgO, O, backbone, device):
+    """The UNMODIFIED reference `RobotVisionFM` (baseline/_ref, pip-installed copy of /root/reference) with the
+    oracle's deterministic weights, or None when that copy is absent."""
+    try:
+        from baseline import ref_shim
+        Ref = ref_shim.import_reference()
+    except Exception:
+        return None
+    ref = Ref(backbone=backbone, pretrained=False, translator="lconv", target_feature_sizes=dict(cfgO.teachers),
+              translator_kwargs={"hidden_size_factor": 1.0})
+    ref.load_state_dict(O.init_params(cfgO, seed=0))
+    return ref.to(device).train()
+
+
+def reference_step_fn(ref, cfgO, O, B, device, autocast=False, lr=1e-4):
+    """train_rvfm.py:101-133 on one synthetic batch with the reference's own module, loss and torch AdamW
+    (two weight-decay groups of optimizers/utils.py:8-35)."""
+    decay, no_decay = [], []
+    for n, p in ref.named_parameters():
+        (no_decay if (p.ndim <= 1 or n.endswith(".bias")) else decay).append(p)
+    opt = torch.optim.AdamW([{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": 0.01}],
+                            lr=lr, betas=(0.9, 0.999))
+    images, targets = O.synthetic_batch(cfgO, B, seed=0)
+    tb = {t: v.to(torch.bfloat16) for t, v in targets.items()}
+
+    def step():
+        im = images.to(device)                                    # train_rvfm.py:101
+        tg = {t: v.to(device).float() for t, v in tb.items()}    # :107-114
+        with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=autocast):
+            pred = ref(im, do_resize=False)                       # :116
+            losses = ref.get_loss(pred, tg)                       # :117
+            ml = 0.9 * losses["cos_loss"] + 0.1 * losses["l1_loss"]  # :119-122
+        opt.zero_grad()
+        ml.backward()
+        opt.step()
+        return float(ml.detach())
+    return step
+
+
 def run_reference(args, cfgO, O):
-    """The reference's CPU implementation of the step (oracle port, torch fp32, all host threads)."""
+    """The reference's own CPU implementation of the step on the host cores: the UNMODIFIED reference modules from
+    baseline/_ref (kind "reference"); the oracle port only when that copy is absent (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    P = O.init_params(cfgO, seed=0)
-    params = {k: v.clone().requires_grad_(True) for k, v in P.items()}
-    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.01)
+    backbone = BACKBONES[args.backbone]
+    ref = build_reference_module(cfgO, O, backbone, "cpu")
+    kind = "reference" if ref is not None else "port"
+    if ref is not None:
+        def make_step(B):
+            return reference_step_fn(ref, cfgO, O, B, "cpu")
+    else:
+        P = O.init_params(cfgO, seed=0)
+        params = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=0.01)
 
-    def make_step(B):
-        images, targets = O.synthetic_batch(cfgO, B, seed=0)
+        def make_step(B):
+            images, targets = O.synthetic_batch(cfgO, B, seed=0)
 
-        def step():
-            preds = O.forward(params, images, cfgO, do_resize=False)
-            losses = O.get_loss(preds, targets)
-            ml = O.main_loss(losses)
-            opt.zero_grad()
-            ml.backward()
-            opt.step()
-            return float(ml)
-        return step
+            def step():
+                preds = O.forward(params, images, cfgO, do_resize=False)
+                losses = O.get_loss(preds, targets)
+                ml = O.main_loss(losses)
+                opt.zero_grad()
+                ml.backward()
+                opt.step()
+                return float(ml.detach())
+            return step
 
     # Bounded sample: the per-step batch is sized from a one-image probe step so that the whole
     # --steps K --warmup W run stays within THEIA_REF_BUDGET_S seconds (default 240) on this host.
@@ -166,36 +214,109 @@ def run_reference(args, cfgO, O):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     val = B / dt
+    what = ("UNMODIFIED reference RobotVisionFM (baseline/_ref) + torch AdamW, fp32 CPU" if kind == "reference"
+            else "oracle port (torch fp32 CPU; baseline/_ref absent)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, B),
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": f"oracle port (torch fp32 CPU), batch {B} per step (sized from a 1-image probe of {t1:.2f} s "
-                                       f"for a {budget:.0f} s budget), {args.steps} steps; threads chosen from "
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind,
+                             "sample": f"{what}: fwd+loss+bwd+AdamW, batch {B} per step (sized from a 1-image probe of "
+                                       f"{t1:.2f} s for a {budget:.0f} s budget), {args.steps} timed steps; threads chosen from "
                                        f"{ {k: round(v, 2) for k, v in thread_timings.items()} } s/probe"},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def gpu_eager_leg(args, cfgO, O, dev, steps=3):
+    """The meaningful GPU comparator (SURVEY 8d / BASELINE.md section 3): the reference's own modules run by torch
+    eager (cuBLAS / cuDNN / ATen) on the SAME B200, same replayed step and batch, in fp32 (as the reference trains)
+    and under autocast(bfloat16).  Returns None when baseline/_ref is absent."""
+    out = {}
+    for mode in ("fp32", "autocast_bf16"):
+        ref = build_reference_module(cfgO, O, BACKBONES[args.backbone], dev)
+        if ref is None:
+            return None
+        B = args.batch
+        try:
+            step = reference_step_fn(ref, cfgO, O, B, dev, autocast=(mode == "autocast_bf16"))
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"value": B / (ms / 1e3), "unit": "images/s", "ms_per_step": ms, "batch": B, "steps": steps}
+        except torch.cuda.OutOfMemoryError:
+            out[mode] = {"value": None, "note": f"out of memory at batch {B}"}
+        del ref
+        torch.cuda.empty_cache()
+    out["what"] = ("UNMODIFIED reference RobotVisionFM (baseline/_ref) on this GPU through torch eager "
+                   "(cuBLAS/cuDNN/ATen), fwd+get_loss+bwd+torch AdamW; inputs copied from host each step as "
+                   "train_rvfm.py:101-114 does; matmul TF32 off (torch default), cuDNN conv TF32 on (torch default)")
+    return out
+
+
 def cpu_baseline_leg(args, cfgO, O):
-    """`cpu_baseline` of the GPU arm: the oracle port timed on the host cores on a bounded sample (one step of
-    forward + loss + backward at --cpu-batch images)."""
+    """`cpu_baseline` of the GPU arm: the reference's CPU path timed on the host cores on a bounded sample
+    (full steps -- forward, loss, backward, AdamW -- at --cpu-batch images)."""
     Bc = args.cpu_batch
-    Pc = O.init_params(cfgO, seed=0)
-    i1, t1_ = O.synthetic_batch(cfgO, 1, seed=0)
-    cores, _, thread_timings = pick_cpu_threads(lambda: O.distill_step(Pc, i1, t1_, cfgO, do_resize=False))
-    ic, tc = O.synthetic_batch(cfgO, Bc, seed=0)
-    O.distill_step(Pc, ic, tc, cfgO, do_resize=False)  # warm-up
+    ref = build_reference_module(cfgO, O, BACKBONES[args.backbone], "cpu")
+    kind = "reference" if ref is not None else "port"
+    if ref is not None:
+        probe = reference_step_fn(ref, cfgO, O, 1, "cpu")
+        step = reference_step_fn(ref, cfgO, O, Bc, "cpu")
+    else:
+        Pc = O.init_params(cfgO, seed=0)
+        i1, t1_ = O.synthetic_batch(cfgO, 1, seed=0)
+        ic, tc = O.synthetic_batch(cfgO, Bc, seed=0)
+        probe = lambda: O.distill_step(Pc, i1, t1_, cfgO, do_resize=False)  # noqa: E731
+        step = lambda: O.distill_step(Pc, ic, tc, cfgO, do_resize=False)  # noqa: E731
+    cores, _, thread_timings = pick_cpu_threads(probe)
+    step()  # warm-up
+    nrep = 3
     t0 = time.perf_counter()
-    nrep = 1
     for _ in range(nrep):
-        O.distill_step(Pc, ic, tc, cfgO, do_resize=False)
+        step()
     dt = (time.perf_counter() - t0) / nrep
-    return {"value": Bc / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"oracle port (torch fp32 CPU) forward+loss+backward, batch {Bc}, {nrep} timed steps "
-                      f"(no optimizer step); threads chosen from "
+    what = ("UNMODIFIED reference RobotVisionFM (baseline/_ref), fp32 CPU: fwd+loss+bwd+AdamW" if kind == "reference"
+            else "oracle port (torch fp32 CPU): fwd+loss+bwd")
+    return {"value": Bc / dt, "unit": "images/s", "cores": cores, "kind": kind,
+            "sample": f"{what}, batch {Bc}, {nrep} timed steps; threads chosen from "
                       f"{ {k: round(v, 2) for k, v in thread_timings.items()} } s per 1-image probe"}
+
+
+def parity_check(model, cfgO, O, d_images, d_targets, dev, n=4):
+    """Step-0 check of the benchmarked configuration against the fp32 oracle (same weights, first n images of the
+    batch, oracle run on this GPU in fp32): the three loss scalars and the predictions.  Raises on a miss."""
+    P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    im = d_images[:n]
+    tg = {t: v[:n].float() for t, v in d_targets.items()}
+    with torch.no_grad():
+        pred = model(im, do_resize=False)
+        losses = model.get_loss(pred, tg)
+        pred_o = O.forward(P, im, cfgO, do_resize=False)
+        losses_o = O.get_loss(pred_o, tg)
+    out = {"images": n, "against": "oracle (torch fp32 on this GPU, TF32 off), identical weights and inputs"}
+    worst = 0.0
+    for k in ("mse_loss", "cos_loss", "l1_loss"):
+        a, b = float(losses[k]), float(losses_o[k])
+        out[k] = {"ours": a, "oracle": b, "rel": abs(a - b) / abs(b)}
+        worst = max(worst, out[k]["rel"])
+    pr = 0.0
+    for t in pred:
+        pr = max(pr, ((pred[t].double() - pred_o[t].double()).norm() / pred_o[t].double().norm()).item())
+    out["pred_rel_l2_max"] = pr
+    out["loss_rel_max"] = worst
+    out["tolerance"] = {"loss_rel": 1e-3, "pred_rel_l2": 3e-2}
+    out["ok"] = bool(worst <= 1e-3 and pr <= 3e-2)
+    if not out["ok"]:
+        raise SystemExit("bench.py parity check FAILED: " + json.dumps(out))
+    return out
 
 
 def workload_config(args, B):
@@ -215,11 +336,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--backbone", default="base", choices=list(BACKBONES))
     ap.add_argument("--teachers", default="cdiv")
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager-on-this-GPU comparator leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the step-0 parity check against the oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dp-mode", default="flat", choices=["flat", "ddp"],
@@ -236,6 +359,13 @@ def main():
             args.steps = max(1, min(args.steps, 5))  # bounded sample: the whole run must end within minutes
         args.warmup = min(args.warmup, 1)
         run_reference(args, cfgO, O)
+        return
+    if args.impl == "eager":
+        if int(os.environ.get("RANK", "0")) == 0:
+            torch.cuda.set_device(0)
+            eg = gpu_eager_leg(args, cfgO, O, torch.device("cuda", 0), steps=max(1, min(args.steps, 5)))
+            print(json.dumps({"impl": "eager", "metric": METRIC, "unit": "images/s", "n_gpus": 1,
+                              "config": workload_config(args, args.batch), "gpu_eager_baseline": eg}), flush=True)
         return
 
     import torch.distributed as dist
@@ -315,6 +445,9 @@ def main():
             ms = float(t)
         return ms
 
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_check(model, cfgO, O, d_images, d_targets, dev)
     for _ in range(max(args.warmup, 3)):
         step(d_images, d_targets)
     # ---- device-resident timed region (value) with per-GEMM-launch events for the roofline ----
@@ -405,11 +538,17 @@ def main():
                 "step_frac_of_peak": 3.0 * fwd_g * B / 1e3 / (ms_step / 1e3) / peak}
 
     cpu = cpu_baseline_leg(args, cfgO, O) if (world == 1 and not args.no_cpu_baseline) else None
+    eager = None
+    if world == 1 and not args.no_eager:
+        del model, net, opt
+        torch.cuda.empty_cache()
+        eager = gpu_eager_leg(args, cfgO, O, dev)
 
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager, "parity_check": parity}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

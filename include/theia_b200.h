@@ -139,10 +139,7 @@ int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_f
 /* tokens / patch_off: rows per image of the patch matrix and the row of the first patch (197 / 1 for DeiT, 196 / 0
  * for DeiTNoCLS, 204 / 1 for DeiTReg); rows of non-patch tokens are zero */
 /* attention (hf:modeling_vit.py:171-196,232-246): qkv [B*N,3*H*64] bf16 -> out [B*N,H*64]; lse [B,H,N] */
-int theia_attention_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream);
-int theia_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N,
-                        int H, void* stream);
-/* tcgen05 version (S / dP accumulators in TMEM, TMA-fed, persistent): same contract */
+/* tcgen05 kernels: S / dP accumulators in TMEM, TMA-fed, persistent */
 int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream);
 int theia_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B,
                            int N, int H, void* stream);
@@ -150,11 +147,32 @@ int theia_attention_tc_bwd(const void* qkv, const void* out, const void* dout, c
 int theia_gather4(const void* in, void* out, int in_is_f32, int out_is_f32, int n0, int n1, int n2, int n3,
                   long long s0, long long s1, long long s2, long long s3, long long base, void* stream);
 /* Fused optimizer tail (train_rvfm.py:126-133; optimizers/utils.py:8-35): torch.optim.AdamW arithmetic over the
- * flat fp32 parameter / gradient / moment buffers in one pass.  decay_flag64[i] != 0 = elements [64 i, 64 i + 64)
- * belong to the weight-decay group; max_grad_norm > 0 applies clip_grad_norm_ first (scratch2: 2 floats). */
-int theia_adamw_flat(float* p, const float* g, float* m, float* v, const uint8_t* decay_flag64, long long n, float lr,
+ * flat fp32 parameter / gradient / moment buffers in one pass.  flag64[i] bit 0 = elements [64 i, 64 i + 64)
+ * belong to the weight-decay group, bit 1 = skip the block entirely (parameter without a gradient: torch leaves it
+ * untouched); max_grad_norm > 0 applies clip_grad_norm_ first (scratch2: 2 floats).  pack_table / packbf (optional,
+ * from theia_model_pack_table): the same pass refreshes the bf16 GEMM-operand copy of each updated weight block
+ * (pack_table[i] = destination 64-element block in packbf, or -1). */
+int theia_adamw_flat(float* p, const float* g, float* m, float* v, const uint8_t* flag64, long long n, float lr,
                      float beta1, float beta2, float eps, float weight_decay, int step, float max_grad_norm,
-                     float* scratch2, void* stream);
+                     float* scratch2, const int* pack_table, void* packbf, void* stream);
+/* bf16 copies of all blocks the pack table names (one launch; what theia_adamw_flat fuses) */
+int theia_pack_cast(const float* p, const int* pack_table, void* packbf, long long n, void* stream);
+/* One launch over a device table of strided layout conversions (conv-weight packs, LayerNorm[C,H,W] affine <-> NHWC,
+ * conv weight-gradient scratch -> reference layout); `in` is fp32, `out` bf16 or fp32 */
+typedef struct theia_perm_seg {
+  const void* in;
+  void* out;
+  int n0, n1, n2, n3;           /* output extents, row-major */
+  long long s0, s1, s2, s3;     /* input element strides */
+  long long base;               /* input element offset */
+  int lim1, lim2;               /* >0: output is zero where index1 >= lim1 or index2 >= lim2 (zero padding) */
+  int out_f32;
+  long long first_block;        /* prefix sum of ceil(n0*n1*n2*n3 / 256) over the preceding segments */
+} theia_perm_seg;
+/* out_rebase: byte address added to every segment's `out` (segments may store offsets relative to a buffer that is
+ * chosen at launch time, e.g. the current gradient buffer); NULL = `out` is absolute */
+int theia_perm_segments(const theia_perm_seg* segs_dev, int nseg, long long total_blocks, const void* out_rebase,
+                        void* stream);
 /* Target ingest (src/theia/dataset/data_utils.py:152-153,342-355): teacher embeddings [B,C,H*W] bf16 ->
  * [B,H*W,C] bf16, z-scored with per-channel bf16 mean/std (NULL = no normalisation); bit-exact with the
  * reference's bf16 `(x - mean) / std` */
@@ -201,7 +219,14 @@ int theia_model_param_info(const theia_model* m, int i, char* name, int name_cap
 /* test / bring-up accessor to a named internal activation of the last forward (see csrc/model.cu) */
 int theia_model_debug_ptr(theia_model* m, const char* name, int i, void** ptr, long long* elems, int* is_f32);
 int theia_model_bind(theia_model* m, float* master, float* grads, void* workspace);
-int theia_model_pack(theia_model* m, void* stream);
+/* switch the flat gradient buffer theia_model_backward writes (same layout; no device work, no synchronisation) */
+int theia_model_set_grads(theia_model* m, float* grads);
+/* fp32 master -> bf16 / permuted operand copies.  skip_linear_cast != 0: the Linear-weight casts were already done
+ * by theia_adamw_flat (pack table); only the token table and the permuted packs are refreshed. */
+int theia_model_pack(theia_model* m, int skip_linear_cast, void* stream);
+/* device pointers of the pack table (one int per 64 floats of the flat parameter buffer) and of the bf16 pack
+ * buffer, valid after theia_model_bind */
+int theia_model_pack_table(theia_model* m, const int** table, void** packbf);
 int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channels_first, int do_resize,
                         int do_rescale, int do_normalize, const float* mean3, const float* std3, int run_heads, float* const* preds,
                         void* tokens_bf16_out, void* stream);

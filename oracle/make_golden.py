@@ -7,13 +7,12 @@ each case the oracle's deterministic weights are loaded into the reference modul
 reference forward / get_loss / backward are run in fp32 on CPU, the oracle restatement is
 asserted equal, and a compact fixture (strided slices + norms + scalars) is saved.
 
-    python oracle/make_golden.py
+    python oracle/make_golden.py [case ...]      # no argument = every case
 """
 from __future__ import annotations
 
 import os
 import sys
-import types
 
 import torch
 
@@ -21,40 +20,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from oracle import theia_oracle as O  # noqa: E402
 
-REF_SRC = "/root/reference/src"
 
 
 def import_reference():
-    import transformers
-    from transformers import ViTConfig, ViTModel
-    from transformers.models.deit.image_processing_deit import DeiTImageProcessor
-
-    if "omegaconf" not in sys.modules:
-        m = types.ModuleType("omegaconf")
-
-        class OmegaConf:  # only use: rvfm.py:65
-            to_container = staticmethod(lambda x: dict(x))
-
-        m.OmegaConf = OmegaConf
-        sys.modules["omegaconf"] = m
-
-    def model_factory(name, *a, **k):
-        d, h = O.BACKBONES[name]
-        return ViTModel(ViTConfig(hidden_size=d, num_attention_heads=h, intermediate_size=4 * d))
-
-    def config_factory(name, *a, **k):
-        d, h = O.BACKBONES[name]
-        return ViTConfig(hidden_size=d, num_attention_heads=h, intermediate_size=4 * d)
-
-    def proc_factory(name, *a, **k):
-        return DeiTImageProcessor(image_mean=list(O.IMAGE_MEAN), image_std=list(O.IMAGE_STD))
-
-    transformers.AutoModel.from_pretrained = staticmethod(model_factory)
-    transformers.AutoProcessor.from_pretrained = staticmethod(proc_factory)
-    transformers.AutoConfig.from_pretrained = staticmethod(config_factory)
-    sys.path.insert(0, REF_SRC)
-    from theia.models.rvfm import RobotVisionFM
-    return RobotVisionFM
+    """the reference's RobotVisionFM straight from /root/reference/src (shims: baseline/ref_shim.py)"""
+    from baseline import ref_shim
+    return ref_shim.import_reference(prefer_installed=False)
 
 
 def sl(t: torch.Tensor) -> torch.Tensor:
@@ -77,6 +48,8 @@ CASES = [
     ("tiny_dinov2_cls_b3", "facebook/deit-tiny-patch16-224", "dinov2+cls", 3, False),  # distill_cls (train_rvfm.py:239-246)
     ("tiny_nocls_dinov2_b2", "nocls-facebook/deit-tiny-patch16-224", "dinov2", 2, False),  # DeiTNoCLS (backbones.py:344)
     ("tiny_reg_dinov2_b2", "reg-facebook/deit-tiny-patch16-224", "dinov2", 2, False),      # DeiTReg (backbones.py:424)
+    # the backbone / teacher set BASELINE.json's metric is quoted on (deit-base + cdiv)
+    ("base_cdiv_b2", "facebook/deit-base-patch16-224", "cdiv", 2, False),
 ]
 
 
@@ -84,7 +57,10 @@ def main():
     RobotVisionFM = import_reference()
     os.makedirs(os.path.join(os.path.dirname(HERE), "tests", "golden"), exist_ok=True)
     torch.manual_seed(0)
+    only = set(sys.argv[1:])
     for name, backbone, tset, B, do_resize in CASES:
+        if only and name not in only:
+            continue
         cfg = O.make_config(backbone, tset.replace("+cls", ""), distill_cls=tset.endswith("+cls"))
         P = O.init_params(cfg, seed=0)
         ref = RobotVisionFM(backbone=backbone, pretrained=False, translator="lconv",
@@ -113,15 +89,19 @@ def main():
             torch.testing.assert_close(pred_o[t], pred_ref[t], rtol=1e-4, atol=1e-4)
         for k in ("mse_loss", "cos_loss", "l1_loss"):
             torch.testing.assert_close(losses_o[k].detach(), losses_ref[k].detach(), rtol=1e-5, atol=1e-7)
-        worst = 0.0
+        worst, worst_k = 0.0, ""
         gmax = max(v.norm().item() for v in grads_ref.values())
         for k in grads_ref:
             num = (grads_o[k] - grads_ref[k]).norm().item()
             # key.bias has a mathematically-zero gradient (softmax shift invariance): floor the
             # denominator so fp noise there is not reported as a relative error
             den = grads_ref[k].norm().item() + 1e-6 * gmax
-            worst = max(worst, num / den)
-        assert worst < 5e-3, worst  # fp32 summation-order noise in the 3.1M-element LN of the 64x64 heads reaches ~1.6e-3
+            if num / den > worst:
+                worst, worst_k = num / den, k
+        # fp32 summation-order noise: ~1.6e-3 in the 3.1M-element LN of the 64x64 heads; deit-base (K = 3072 / 6912
+        # reductions, SDPA vs explicit softmax) reaches 5e-3 on its smallest-gradient tensor
+        assert worst < (1e-2 if "base" in backbone else 5e-3), (worst, worst_k)
+        print("   worst-agreeing gradient tensor:", worst_k, f"{worst:.2e}")
         fx = {
             "case": name, "backbone": backbone, "teachers": list(cfg.teachers), "B": B, "seed": 0,
             "kwargs": kw,
@@ -143,6 +123,8 @@ def main():
         print(f"{name}: oracle==reference (worst grad rel {worst:.2e}); main_loss {float(ml):.6f} -> {out} "
               f"({os.path.getsize(out) / 1024:.0f} KiB)")
 
+    if only and "readme_zeros" not in only:
+        return
     # README quick-start (BASELINE config #1): zeros image through deit-tiny forward_feature
     cfg = O.make_config("facebook/deit-tiny-patch16-224", "dinov2")
     P = O.init_params(cfg, seed=0)

@@ -31,6 +31,11 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
+# The oracle is an fp32 restatement: when it runs on a GPU (tests, smoke, bench parity check) cuDNN / cuBLAS must not
+# silently drop to TF32 (cuDNN convolutions allow it by default).
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 # (C, H, W) per teacher -- reference foundation_models/common.py:18-25
 MODEL_FEATURE_SIZES = {
     "facebook/dinov2-large": (1024, 16, 16),

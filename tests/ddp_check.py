@@ -66,9 +66,32 @@ def main():
     dist.all_gather(flats, m._flat)
     for r in range(1, world):
         assert torch.equal(flats[0], flats[r]), f"parameters diverged between rank 0 and {r}"
+    # the wrapper-free path: sync_gradients() (ONE all-reduce of the flat gradient buffer inside backward) stepped
+    # by the fused FlatAdamW -- parameters AND the bf16 operand copies must stay bit-identical across ranks
+    from theia_b200.optim import FlatAdamW
+    m3 = make()
+    m3.sync_gradients(True)
+    opt3 = FlatAdamW(m3, lr=1e-3, weight_decay=0.01)
+    for _ in range(3):
+        p3 = m3(images, do_resize=False)
+        l3 = m3.get_loss(p3, targets)
+        opt3.zero_grad(set_to_none=True)
+        (0.9 * l3["cos_loss"] + 0.1 * l3["l1_loss"]).backward()
+        opt3.step()
+    flats = [torch.empty_like(m3._flat) for _ in range(world)]
+    dist.all_gather(flats, m3._flat)
+    for r in range(1, world):
+        assert torch.equal(flats[0], flats[r]), f"FlatAdamW + sync_gradients: parameters diverged (rank 0 vs {r})"
+    with torch.no_grad():
+        feat = m3.forward_feature(shards[0][0], do_resize=False)  # same images on every rank
+    feats = [torch.empty_like(feat) for _ in range(world)]
+    dist.all_gather(feats, feat)
+    for r in range(1, world):
+        assert torch.equal(feats[0], feats[r]), f"forward differs between rank 0 and {r} after FlatAdamW steps"
     dist.barrier()
     if rank == 0:
-        print(f"DDP_CHECK_OK world={world} grad_rel={rel:.3e}")
+        print(f"DDP_CHECK_OK world={world} grad_rel={rel:.3e} flat_allreduce_rel={rel2:.3e} "
+              f"flat_adamw_sync_gradients=bit-identical-across-ranks")
     dist.destroy_process_group()
 
 

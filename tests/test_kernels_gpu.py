@@ -371,15 +371,14 @@ def test_preprocess_with_bicubic_resize(lib, chw):
 
 
 # ----------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("impl", ["mma_sync", "tcgen05"])
 @pytest.mark.parametrize("Bn,H", [(2, 3), (3, 12), (40, 6), (100, 12)])  # the last: 8 (image, head) items per CTA, every ring wraps
-def test_attention_fwd_bwd(lib, Bn, H, impl):
+def test_attention_fwd_bwd(lib, Bn, H):
     N, D = 197, H * 64
     qkv = rnd(Bn * N, 3 * D, seed=1, scale=1.5)
     do = rnd(Bn * N, D, seed=2)
     out = torch.full((Bn * N, D), float("nan"), dtype=torch.bfloat16, device=DEV)
     lse = torch.empty(Bn, H, N, device=DEV)
-    fwd = lib.theia_attention_fwd if impl == "mma_sync" else lib.theia_attention_tc_fwd
+    fwd = lib.theia_attention_tc_fwd
     L.check(fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), Bn, N, H, S()))
     x = qkv.float().view(Bn, N, 3, H, 64).requires_grad_(True)
     q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
@@ -389,7 +388,7 @@ def test_attention_fwd_bwd(lib, Bn, H, impl):
     torch.testing.assert_close(lse, torch.logsumexp(s, -1).detach(), rtol=1e-4, atol=1e-4)
     ref.backward(do.float())
     dqkv = torch.full_like(qkv, float("nan"))
-    bwd = lib.theia_attention_bwd if impl == "mma_sync" else lib.theia_attention_tc_bwd
+    bwd = lib.theia_attention_tc_bwd
     L.check(bwd(qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), Bn, N, H, S()))
     g = x.grad.view(Bn * N, 3, D)
     got = dqkv.float().view(Bn * N, 3, D)

@@ -74,7 +74,12 @@ def test_readme_quickstart_zeros():
                                              ("facebook/deit-tiny-patch16-224", "cddsv", 2),
                                              ("facebook/deit-tiny-patch16-224", "cdiv+cls", 3),
                                              ("nocls-facebook/deit-tiny-patch16-224", "dinov2", 2),
-                                             ("reg-facebook/deit-tiny-patch16-224", "cdiv", 2)])
+                                             ("reg-facebook/deit-tiny-patch16-224", "cdiv", 2),
+                                             # the configurations the headline numbers are quoted on (BASELINE.json
+                                             # metric = base+cdiv, config #4 = base+cddsv): BN=256 CTA-pair kernels,
+                                             # 12-head attention, D=768 LayerNorm paths
+                                             ("facebook/deit-base-patch16-224", "cdiv", 4),
+                                             ("facebook/deit-base-patch16-224", "cddsv", 2)])
 def test_distill_step_parity_vs_oracle(backbone, tset, B):
     cfg, P, m = build(backbone, tset)
     images, targets = O.synthetic_batch(cfg, B, seed=0, device=DEV)
@@ -220,14 +225,20 @@ def test_backbone_variants_against_reference_golden(fixture):
 
 
 def test_training_reduces_loss_and_repacks_weights():
-    """train_rvfm.py:116-133 replay with torch AdamW on the flat-view parameters: the loss must go down,
-    which also proves the bf16 operand copies are re-packed after optimizer.step()."""
+    """train_rvfm.py:116-133 replay with torch AdamW on the flat-view parameters: the loss goes down AND the bf16
+    operand copies follow the fp32 master (asserted directly on the packed weights -- biases and LayerNorm affines
+    are read from the master, so a falling loss alone would not prove re-packing)."""
+    from tests._gpu_util import fetch
     cfg, P, m = build("facebook/deit-tiny-patch16-224", "dinov2")
     images, targets = O.synthetic_batch(cfg, 8, seed=1, device=DEV)
     opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0.01)
     hist = []
-    for _ in range(6):
+    D = cfg.hidden
+    qw = dict(m.named_parameters())["backbone.model.encoder.layer.3.attention.attention.query.weight"]
+    for it in range(6):
         pred = m(images, do_resize=False)
+        packed = fetch(m, "wqkv", 3, (3 * D, D))[:D]  # the copy THIS forward used
+        assert torch.equal(packed, qw.detach().to(torch.bfloat16)), it
         losses = m.get_loss(pred, targets)
         main = 0.9 * losses["cos_loss"] + 0.1 * losses["l1_loss"]
         opt.zero_grad()
@@ -236,6 +247,79 @@ def test_training_reduces_loss_and_repacks_weights():
         hist.append(float(main))
     assert all(h == h for h in hist)
     assert hist[-1] < hist[0] - 1e-3, hist
+
+
+def test_inplace_weight_update_after_cuda_is_seen():
+    """after .cuda() every Parameter has its own version counter; an in-place update of a GEMM
+    weight through the Parameter (what any stock optimizer / load_state_dict does) must re-pack the bf16 copies."""
+    cfg, P, m = build("facebook/deit-tiny-patch16-224", "dinov2")
+    images, _ = O.synthetic_batch(cfg, 2, seed=0, device=DEV)
+    with torch.no_grad():
+        f0 = m.forward_feature(images, do_resize=False)
+        sd = dict(m.named_parameters())
+        for l in range(12):
+            sd[f"backbone.model.encoder.layer.{l}.intermediate.dense.weight"].mul_(0)  # MLP contributes bias only
+        f1 = m.forward_feature(images, do_resize=False)
+        assert relerr(f1, f0) > 1e-2
+        Pz = {k: v.clone() for k, v in P.items()}
+        for l in range(12):
+            Pz[f"backbone.model.encoder.layer.{l}.intermediate.dense.weight"].zero_()
+        assert relerr(f1, O.forward_feature(Pz, images, cfg, do_resize=False)) < 2e-2
+        # load_state_dict after a forward on the GPU goes through the same in-place path
+        m.load_state_dict({k: v.cpu() for k, v in P.items()})
+        f2 = m.forward_feature(images, do_resize=False)
+        assert relerr(f2, f0) < 1e-6
+
+
+def test_flat_adamw_frozen_translator_and_scheduler():
+    """freeze_translator() (train_rvfm.py:149-151): parameters without a gradient stay bit-identical under
+    FlatAdamW (torch.optim.AdamW skips `grad is None`); FlatAdamW is a torch Optimizer, so the reference's
+    LR scheduler (lr_schedulers.py:41-77 wraps torch.optim.lr_scheduler.*) drives it; its state round-trips."""
+    from tests._gpu_util import fetch
+    from theia_b200.optim import FlatAdamW
+    cfg, P, m = build("facebook/deit-tiny-patch16-224", "cdiv")
+    images, targets = O.synthetic_batch(cfg, 4, seed=5, device=DEV)
+    opt = FlatAdamW(m, lr=1e-3, weight_decay=0.05)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, start_factor=1e-2, total_iters=4)
+    assert isinstance(opt, torch.optim.Optimizer) and len(opt.param_groups) == 1
+
+    def one_step(names=None):
+        pred = m(images, target_model_names=names, do_resize=False)
+        losses = m.get_loss(pred, {t: targets[t] for t in pred})
+        opt.zero_grad(set_to_none=True)
+        (0.9 * losses["cos_loss"] + 0.1 * losses["l1_loss"]).backward()
+        opt.step()
+        sched.step()
+
+    one_step()
+    assert abs(opt.param_groups[0]["lr"] - 1e-3 * (1e-2 + 0.99 / 4)) < 1e-9
+    # fused bf16 refresh: the packed copy equals bf16(master) right after the step
+    D = cfg.hidden
+    w1 = dict(m.named_parameters())["backbone.model.encoder.layer.5.intermediate.dense.weight"]
+    assert torch.equal(fetch(m, "w1", 5, (4 * D, D)), w1.detach().to(torch.bfloat16))
+    # a head that is not selected gets no gradient: untouched (no decay, no moments)
+    tnames = list(cfg.teachers)
+    before = {k: v.detach().clone() for k, v in m.named_parameters()}
+    one_step(names=tnames[:1])
+    unused = O.head_key(tnames[2])
+    for k, v in m.named_parameters():
+        if unused in k:
+            assert torch.equal(v, before[k]), k
+    m.freeze_translator()
+    before = {k: v.detach().clone() for k, v in m.named_parameters()}
+    one_step()
+    changed = 0
+    for k, v in m.named_parameters():
+        if k.startswith("translator."):
+            assert torch.equal(v, before[k]), k
+        else:
+            changed += int(not torch.equal(v, before[k]))
+    assert changed > 100
+    sd = opt.state_dict()
+    opt2 = FlatAdamW(m, lr=5e-4)
+    opt2.load_state_dict(sd)
+    assert opt2.step_count == opt.step_count and torch.equal(opt2.m, opt.m)
+    assert opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"]
 
 
 def test_flat_adamw_matches_torch_adamw():
@@ -282,6 +366,46 @@ def test_full_batch_properties():
         assert relerr(big[t][:4], small[t]) < 2e-3, t  # fp32 atomics order the LN statistics differently
     losses = m.get_loss(big, targets)
     assert 0.5 < float(losses["cos_loss"]) < 1.5
+
+
+def test_headline_config_full_batch_vs_oracle():
+    """The configuration the metric is quoted on -- deit-base + cdiv at per-GPU batch 256 -- against the fp32 oracle
+    at the SAME batch (forward only, no_grad): the three loss scalars (<= 1e-3 rel, the north-star bar), the student
+    feature and predictions of the first 4 images, and the fixture the real reference produced for this backbone."""
+    B = 256
+    cfg, P, m = build("facebook/deit-base-patch16-224", "cdiv", max_batch=B)
+    images, targets = O.synthetic_batch(cfg, B, seed=7, device=DEV)
+    kw = {"do_resize": False}
+    with torch.no_grad():
+        pred = m(images, **kw)
+        losses = m.get_loss(pred, targets)
+        lo = {"mse_loss": 0.0, "cos_loss": 0.0, "l1_loss": 0.0}
+        chunk = 32  # oracle in 8 chunks: per-image cosine terms and element sums add up exactly like the full batch
+        first = None
+        for i in range(0, B, chunk):
+            pr = O.forward(P, images[i:i + chunk], cfg, **kw)
+            ls = O.get_loss(pr, {t: v[i:i + chunk] for t, v in targets.items()})
+            for k in lo:
+                lo[k] += float(ls[k]) * chunk / B
+            if first is None:
+                first = pr
+    for k in lo:
+        assert abs(float(losses[k]) - lo[k]) <= 1e-3 * abs(lo[k]), (k, float(losses[k]), lo[k])
+    for t in cfg.teachers:
+        assert relerr(pred[t][:4], first[t][:4]) < 3e-2, t
+    del pred, first
+    fx = torch.load(os.path.join(GOLDEN, "base_cdiv_b2.pt"), weights_only=False)
+    images2, targets2 = O.synthetic_batch(cfg, fx["B"], seed=fx["seed"], device=DEV)
+    pred2 = m(images2, **fx["kwargs"])
+    for t, gq in fx["pred"].items():
+        assert relerr(_sl(pred2[t]).cpu(), gq["sample"]) < 3e-2, t
+    losses2 = m.get_loss(pred2, targets2)
+    for k, v in fx["losses"].items():
+        assert abs(float(losses2[k]) - v) <= 1e-3 * abs(v), k
+    (0.9 * losses2["cos_loss"] + 0.1 * losses2["l1_loss"]).backward()
+    g = dict(m.named_parameters())
+    for k, s_ in fx["grad_sample"].items():
+        assert relerr(_sl(g[k].grad).cpu(), s_) < 0.3, k
 
 
 def test_subset_of_teachers_and_eval_cpu_images():

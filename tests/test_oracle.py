@@ -19,7 +19,7 @@ def _sl(t):
 
 
 def _cases():
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN, "tiny_*.pt")))
+    return sorted(glob.glob(os.path.join(GOLDEN, "tiny_*.pt")) + glob.glob(os.path.join(GOLDEN, "base_*.pt")))
 
 
 def test_golden_present():
@@ -47,7 +47,7 @@ def test_oracle_matches_reference_golden(path):
     gmax = max(fx["grad_l2"].values())
     for k, v in fx["grad_l2"].items():
         mine = grads[k].double().norm().item()
-        assert abs(mine - v) <= 5e-3 * v + 1e-6 * gmax, (k, mine, v)
+        assert abs(mine - v) <= (1e-2 if "base" in path else 5e-3) * v + 1e-6 * gmax, (k, mine, v)
 
 
 def test_readme_zeros_quickstart():

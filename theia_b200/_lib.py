@@ -61,17 +61,17 @@ SYMBOLS = {
     "theia_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "theia_ln3d_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _vp]),
     "theia_ln3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp]),
-    "theia_adamw_flat": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),
+    "theia_adamw_flat": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp, _vp, _vp, _vp]),
+    "theia_pack_cast": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "theia_perm_segments": (_i, [_vp, _i, _ll, _vp, _vp]),
     "theia_target_ingest": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_chw_to_hwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "theia_hwc_to_chw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "theia_loss_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "theia_loss_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _vp]),
-    "theia_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_attention_tc_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_attention_tc_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "theia_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_gather4": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _vp]),
     "theia_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "theia_transpose_cast_bf16": (_i, [_vp, _vp, _i, _i, _vp]),
@@ -86,7 +86,9 @@ SYMBOLS = {
     "theia_model_param_info": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_ll), C.POINTER(_i), C.POINTER(_ll)]),
     "theia_model_debug_ptr": (_i, [_vp, C.c_char_p, _i, C.POINTER(_vp), C.POINTER(_ll), C.POINTER(_i)]),
     "theia_model_bind": (_i, [_vp, _vp, _vp, _vp]),
-    "theia_model_pack": (_i, [_vp, _vp]),
+    "theia_model_pack": (_i, [_vp, _i, _vp]),
+    "theia_model_pack_table": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "theia_model_set_grads": (_i, [_vp, _vp]),
     "theia_model_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i,
                                  C.POINTER(_vp), _vp, _vp]),
     "theia_model_backward": (_i, [_vp, C.POINTER(_vp), _vp]),

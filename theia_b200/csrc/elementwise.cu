@@ -674,13 +674,16 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm
 }
 __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                          float* __restrict__ m, float* __restrict__ v,
-                                                         const uint8_t* __restrict__ decay_flag, long long n, float lr,
+                                                         const uint8_t* __restrict__ flag64, long long n, float lr,
                                                          float beta1, float beta2, float eps, float wd, float bc1,
-                                                         float sqrt_bc2, const float* __restrict__ gscale) {
+                                                         float sqrt_bc2, const float* __restrict__ gscale,
+                                                         const int* __restrict__ pack_table, bf16* __restrict__ packbf) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
+  const uint8_t fl = flag64[i >> 6];
+  if (fl & 2) return;  // parameter without a gradient (frozen / unused head): left bit-identical, like torch
   const float gs = gscale ? gscale[0] : 1.f;
-  const float decay = decay_flag[i >> 6] ? 1.f - lr * wd : 1.f;
+  const float decay = (fl & 1) ? 1.f - lr * wd : 1.f;
   const float step = lr / bc1;
   float4 P = *reinterpret_cast<float4*>(p + i), G = *reinterpret_cast<const float4*>(g + i);
   float4 M = *reinterpret_cast<float4*>(m + i), V = *reinterpret_cast<float4*>(v + i);
@@ -701,6 +704,61 @@ __global__ void __launch_bounds__(256) adamw_flat_kernel(float* __restrict__ p, 
   *reinterpret_cast<float4*>(p + i) = P;
   *reinterpret_cast<float4*>(m + i) = M;
   *reinterpret_cast<float4*>(v + i) = V;
+  if (pack_table != nullptr) {  // refresh the bf16 GEMM-operand copy of this weight in the same pass
+    const int dst = pack_table[i >> 6];
+    if (dst >= 0) {
+      uint2 u;
+      u.x = pack_bf16x2(P.x, P.y);
+      u.y = pack_bf16x2(P.z, P.w);
+      *reinterpret_cast<uint2*>(packbf + (static_cast<long long>(dst) << 6) + (i & 63)) = u;
+    }
+  }
+}
+
+// bf16 operand copies of every parameter block the pack table names (Linear / patch-embed weights: the copy is a
+// plain cast, 64-element blocks): ONE launch instead of a cast kernel per weight.
+__global__ void __launch_bounds__(256) pack_cast_kernel(const float* __restrict__ p, const int* __restrict__ pack_table,
+                                                        bf16* __restrict__ packbf, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  const int dst = pack_table[i >> 6];
+  if (dst < 0) return;
+  const float4 P = *reinterpret_cast<const float4*>(p + i);
+  uint2 u;
+  u.x = pack_bf16x2(P.x, P.y);
+  u.y = pack_bf16x2(P.z, P.w);
+  *reinterpret_cast<uint2*>(packbf + (static_cast<long long>(dst) << 6) + (i & 63)) = u;
+}
+
+// Segmented strided gather: ONE launch runs a table of layout conversions (conv-weight packs, LayerNorm[C,H,W]
+// affine <-> NHWC, conv weight-gradient scratch -> reference layout).  Segment s:
+//   out[((a*n1 + b)*n2 + c)*n3 + d] = (b < lim1 && c < lim2) ? in[base + a*s0 + b*s1 + c*s2 + d*s3] : 0
+__global__ void __launch_bounds__(256) perm_seg_kernel(const theia_perm_seg* __restrict__ segs, int nseg,
+                                                       uintptr_t out_rebase) {
+  int lo = 0, hi = nseg - 1;
+  const long long blk = blockIdx.x;
+  while (lo < hi) {  // last segment whose first_block <= blk
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].first_block <= blk) lo = mid;
+    else hi = mid - 1;
+  }
+  const theia_perm_seg sg = segs[lo];
+  const long long t = (blk - sg.first_block) * 256 + threadIdx.x;
+  const long long total = static_cast<long long>(sg.n0) * sg.n1 * sg.n2 * sg.n3;
+  if (t >= total) return;
+  long long r = t;
+  const int d = static_cast<int>(r % sg.n3);
+  r /= sg.n3;
+  const int c = static_cast<int>(r % sg.n2);
+  r /= sg.n2;
+  const int b = static_cast<int>(r % sg.n1);
+  const int a = static_cast<int>(r / sg.n1);
+  float v = 0.f;
+  if ((sg.lim1 <= 0 || b < sg.lim1) && (sg.lim2 <= 0 || c < sg.lim2))
+    v = static_cast<const float*>(sg.in)[sg.base + a * sg.s0 + b * sg.s1 + c * sg.s2 + d * sg.s3];
+  void* outp = reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(sg.out) + out_rebase);
+  if (sg.out_f32) static_cast<float*>(outp)[t] = v;
+  else static_cast<bf16*>(outp)[t] = __float2bfloat16_rn(v);
 }
 
 // Target ingest (src/theia/dataset/data_utils.py:152-153,342-355): teacher embedding stored
@@ -954,8 +1012,11 @@ static double bicubic_aa_filter(float xf) {
 }
 
 static int upload_resize_table() {
-  static bool done = false;
-  if (done) return 0;
+  static bool done[64] = {false};  // __constant__ memory is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (done[dev]) return 0;
   static ResizeTable rt;
   const float scale = 224.0f / 256.0f;
   const float support = 2.0f;  // interp_size 4 * 0.5 (scale < 1: no widening)
@@ -983,7 +1044,7 @@ static int upload_resize_table() {
   }
   cudaError_t e = cudaMemcpyToSymbol(c_rt, &rt, sizeof(rt));
   if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "resize table upload: %s", cudaGetErrorString(e));
-  done = true;
+  done[dev] = true;
   return 0;
 }
 
@@ -1038,9 +1099,9 @@ extern "C" int theia_gather4(const void* in, void* out, int in_is_f32, int out_i
   return THEIA_OK;
 }
 
-extern "C" int theia_adamw_flat(float* p, const float* g, float* m, float* v, const uint8_t* decay_flag64, long long n,
+extern "C" int theia_adamw_flat(float* p, const float* g, float* m, float* v, const uint8_t* flag64, long long n,
                                 float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                                float max_grad_norm, float* scratch2, void* stream) {
+                                float max_grad_norm, float* scratch2, const int* pack_table, void* packbf, void* stream) {
   if (n <= 0) return THEIA_OK;
   if (n % 4 != 0) return set_error(THEIA_ERR_ARG, "adamw: n %% 4 != 0");
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
@@ -1057,8 +1118,27 @@ extern "C" int theia_adamw_flat(float* p, const float* g, float* m, float* v, co
     gscale = scratch2 + 1;
   }
   adamw_flat_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, S(stream)>>>(
-      p, g, m, v, decay_flag64, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), gscale);
+      p, g, m, v, flag64, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), gscale,
+      packbf ? pack_table : nullptr, static_cast<bf16*>(packbf));
   THEIA_CHECK_LAUNCH("adamw_flat");
+  return THEIA_OK;
+}
+
+extern "C" int theia_pack_cast(const float* p, const int* pack_table, void* packbf, long long n, void* stream) {
+  if (n <= 0) return THEIA_OK;
+  if (n % 4 != 0) return set_error(THEIA_ERR_ARG, "pack_cast: n %% 4 != 0");
+  pack_cast_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, S(stream)>>>(p, pack_table,
+                                                                                     static_cast<bf16*>(packbf), n);
+  THEIA_CHECK_LAUNCH("pack_cast");
+  return THEIA_OK;
+}
+
+extern "C" int theia_perm_segments(const theia_perm_seg* segs_dev, int nseg, long long total_blocks,
+                                   const void* out_rebase, void* stream) {
+  if (nseg <= 0 || total_blocks <= 0) return THEIA_OK;
+  perm_seg_kernel<<<static_cast<unsigned>(total_blocks), 256, 0, S(stream)>>>(segs_dev, nseg,
+                                                                             reinterpret_cast<uintptr_t>(out_rebase));
+  THEIA_CHECK_LAUNCH("perm_segments");
   return THEIA_OK;
 }
 

@@ -36,11 +36,13 @@ struct HeadP {
 };
 
 // bf16 packed weights (offsets in elements of the bf16 pack buffer)
+// Linear weights keep ONE bf16 copy [out][in]: the forward reads it as a K-major B operand, the dgrad as an
+// MN-major one (no transposed copies).
 struct LayerW {
-  long long wqkv, wqkvT, wo, woT, w1, w1T, w2, w2T;
+  long long wqkv, wo, w1, w2;
 };
 struct HeadW {
-  long long padF, padD, c1F, c1D, c2F, c2D, l, lT;
+  long long padF, padD, c1F, c1D, c2F, c2D, l;
   long long gb[3][2];  // fp32 pack: gamma/beta HWC for the three LNs (offsets in floats)
 };
 
@@ -51,6 +53,19 @@ struct LayerA {
 struct HeadA {
   long long padout, ln0, c1, ln1, c2, ln2;  // bf16
   long long stats;                          // fp32 [3][B][2]
+  long long wsc[3];                         // fp32 backward scratch: conv weight gradients [tap][..][..] per conv
+  long long gbs[3];                         // fp32 backward scratch: LN dgamma | dbeta (HWC) per LayerNorm
+};
+
+// one strided layout conversion of the pack / unpack tables (pointers are resolved at bind time)
+enum { SEG_IN_MASTER = 0, SEG_IN_ACTF32 = 1 };
+enum { SEG_OUT_PACKBF = 0, SEG_OUT_PACKF32 = 1, SEG_OUT_GRADS = 2 };
+struct SegSpec {
+  int in_base, out_base;
+  long long in_off, out_off;
+  int n0, n1, n2, n3;
+  long long s0, s1, s2, s3, base;
+  int lim1, lim2;
 };
 
 }  // namespace theia
@@ -86,7 +101,14 @@ struct theia_model {
   std::vector<HeadA> ha;
   // backward scratch
   long long dtok, dx0, dx1, dln, dqkv, dh, dattn, dA0, dA1;  // bf16
-  long long red, wscratch, gbscratch;                         // fp32
+  long long red;                                              // fp32
+  long long bscr = 0, n_bscr = 0;                             // fp32 backward scratch (zeroed once per backward)
+  // pack table (one int per 64 floats of the flat buffer: destination 64-block in the bf16 pack, or -1) and the
+  // segment tables of the permuted packs / gradient unpacks; uploaded into the workspace by theia_model_bind
+  std::vector<int> h_table;
+  std::vector<SegSpec> pack_specs, unpack_specs;
+  long long o_table = 0, o_pack_segs = 0, o_unpack_segs = 0;  // byte offsets in the workspace
+  long long pack_blocks = 0, unpack_blocks = 0;
   int last_B = 0;
 };
 
@@ -231,41 +253,83 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   m->wpe = pb.take(static_cast<long long>(D) * 768, AL);
   m->tokt = pf.take(static_cast<long long>(m->N) * D, AL);
   m->tgrad = af.take(static_cast<long long>(m->N) * D, AL);
+  m->h_table.assign(static_cast<size_t>(m->n_params_total / 64), -1);
+  // pack-table entry: parameter pi (numel a multiple of 64) is cast into the bf16 pack at element offset dst
+  auto table_cast = [&](int pi, long long dst) {
+    const PInfo& q = m->params[pi];
+    for (long long j = 0; j < (q.numel + 63) / 64; ++j) m->h_table[q.off / 64 + j] = static_cast<int>(dst / 64 + j);
+  };
+  table_cast(m->pew, m->wpe);
   for (int l = 0; l < L; ++l) {
     LayerW w;
     const long long DD = static_cast<long long>(D) * D;
     w.wqkv = pb.take(3 * DD, AL);
-    w.wqkvT = pb.take(3 * DD, AL);
     w.wo = pb.take(DD, AL);
-    w.woT = pb.take(DD, AL);
     w.w1 = pb.take(4 * DD, AL);
-    w.w1T = pb.take(4 * DD, AL);
     w.w2 = pb.take(4 * DD, AL);
-    w.w2T = pb.take(4 * DD, AL);
     m->lw.push_back(w);
+    const LayerP& q = m->lp[l];
+    table_cast(q.qw, w.wqkv);  // q, k, v are adjacent in the flat buffer (D*D is a multiple of 64)
+    table_cast(q.kw, w.wqkv + DD);
+    table_cast(q.vw, w.wqkv + 2 * DD);
+    table_cast(q.ow, w.wo);
+    table_cast(q.f1w, w.w1);
+    table_cast(q.f2w, w.w2);
   }
+  auto seg = [&](std::vector<SegSpec>& v, int ib, long long ioff, int ob, long long ooff, int n0, int n1, int n2, int n3,
+                 long long s0, long long s1, long long s2, long long s3, long long base, int lim1 = 0, int lim2 = 0) {
+    SegSpec q{ib, ob, ioff, ooff, n0, n1, n2, n3, s0, s1, s2, s3, base, lim1, lim2};
+    v.push_back(q);
+  };
   for (int t = 0; t < T; ++t) {
     HeadW w;
     memset(&w, 0, sizeof(w));
-    if (m->hp[t].hw == 1) {
-      w.l = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
-      w.lT = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
+    const HeadP& hp = m->hp[t];
+    if (hp.hw == 1) {
+      w.l = pb.take(static_cast<long long>(hp.ct) * C, AL);
+      table_cast(hp.lw, w.l);
       m->hw.push_back(w);
       continue;
     }
-    const long long W9 = 9LL * C * C;
+    const long long W9 = 9LL * C * C, C9 = 9LL * C;
     w.padF = pb.take(W9, AL);
     w.padD = pb.take(W9, AL);
     w.c1F = pb.take(W9, AL);
     w.c1D = pb.take(W9, AL);
     w.c2F = pb.take(W9, AL);
     w.c2D = pb.take(W9, AL);
-    w.l = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
-    w.lT = pb.take(static_cast<long long>(m->hp[t].ct) * C, AL);
-    const long long npix[3] = {256, 1LL * m->hp[t].p1 * m->hp[t].p1, 1LL * m->hp[t].p2 * m->hp[t].p2};
+    w.l = pb.take(static_cast<long long>(hp.ct) * C, AL);
+    table_cast(hp.lw, w.l);
+    const long long npix[3] = {256, 1LL * hp.p1 * hp.p1, 1LL * hp.p2 * hp.p2};
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 2; ++j) w.gb[i][j] = pf.take(npix[i] * C, AL);
     m->hw.push_back(w);
+    auto& ps = m->pack_specs;
+    const auto off = [&](int pi) { return m->params[pi].off; };
+    // ConvTranspose2d weight [Cin][Cout][3][3]: fwd pack F[co][tap2][ci] = Wt[ci][co][8-tap2]
+    seg(ps, SEG_IN_MASTER, off(hp.padw), SEG_OUT_PACKBF, w.padF, C, 9, C, 1, 9, -1, C9, 0, 8);
+    // dgrad pack D[ci][tap][co] = Wt[ci][co][tap]
+    seg(ps, SEG_IN_MASTER, off(hp.padw), SEG_OUT_PACKBF, w.padD, C, 9, C, 1, C9, 1, 9, 0, 0);
+    const int cw[2] = {hp.c1w, hp.c2w};
+    const long long cF[2] = {w.c1F, w.c2F}, cD[2] = {w.c1D, w.c2D};
+    for (int i = 0; i < 2; ++i) {
+      if (hp.hw == 16) {
+        // Conv2d weight [Cout][Cin][3][3]: fwd F[co][tap][ci]; dgrad D[ci][tap2][co] = W[co][ci][8-tap2]
+        seg(ps, SEG_IN_MASTER, off(cw[i]), SEG_OUT_PACKBF, cF[i], C, 9, C, 1, C9, 1, 9, 0, 0);
+        seg(ps, SEG_IN_MASTER, off(cw[i]), SEG_OUT_PACKBF, cD[i], C, 9, C, 1, 9, -1, C9, 0, 8);
+      } else {
+        // ConvTranspose2d(s2) weight [Cin][Cout][3][3] -> tap-major F[tap][co][ci] and D[tap][ci][co]
+        seg(ps, SEG_IN_MASTER, off(cw[i]), SEG_OUT_PACKBF, cF[i], 9, C, C, 1, 1, 9, C9, 0, 0);
+        seg(ps, SEG_IN_MASTER, off(cw[i]), SEG_OUT_PACKBF, cD[i], 9, C, C, 1, 1, C9, 9, 0, 0);
+      }
+    }
+    // LN affine [C][Hv][Wv] -> NHWC [Hp][Wp][C] (zero padded for the 31x31 stage)
+    const int gbp[3][2] = {{hp.g0, hp.b0}, {hp.g1, hp.b1}, {hp.g2, hp.b2}};
+    const int vv[3] = {16, hp.v1, hp.v2}, pp[3] = {16, hp.p1, hp.p2};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 2; ++j)
+        seg(ps, SEG_IN_MASTER, off(gbp[i][j]), SEG_OUT_PACKF32, w.gb[i][j], 1, pp[i], pp[i], C, 0, vv[i], 1,
+            1LL * vv[i] * vv[i], 0, vv[i], vv[i]);
   }
   m->patches = ab.take(M * 768, AL);
   m->x.resize(L + 1);
@@ -309,6 +373,40 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
     a.stats = af.take(3LL * B * 2, AL);
     m->ha.push_back(a);
   }
+  {  // backward scratch of the heads (contiguous: one memset per backward) and the gradient unpack table
+    Carver sc;
+    for (int t = 0; t < T; ++t) {
+      const HeadP& hp = m->hp[t];
+      if (hp.hw == 1) continue;
+      HeadA& a = m->ha[t];
+      const long long npix[3] = {256, 1LL * hp.p1 * hp.p1, 1LL * hp.p2 * hp.p2};
+      for (int i = 0; i < 3; ++i) {
+        a.wsc[i] = sc.take(9LL * C * C, AL);
+        a.gbs[i] = sc.take(2 * npix[i] * C, AL);
+      }
+    }
+    m->n_bscr = align_up(sc.n, AL);
+    m->bscr = af.take(m->n_bscr, AL);
+    auto& us = m->unpack_specs;
+    const long long CC = 1LL * C * C;
+    for (int t = 0; t < T; ++t) {
+      const HeadP& hp = m->hp[t];
+      if (hp.hw == 1) continue;
+      const HeadA& a = m->ha[t];
+      const auto off = [&](int pi) { return m->params[pi].off; };
+      // pad (stride-1 ConvTranspose2d): grad Wt[ci][co][t] = ws[8-t][co][ci]
+      seg(us, SEG_IN_ACTF32, m->bscr + a.wsc[0], SEG_OUT_GRADS, off(hp.padw), C, C, 9, 1, 1, C, -CC, 0, 8 * CC);
+      // Conv2d: grad W[co][ci][tap] = ws[tap][co][ci];  ConvTranspose2d(s2): grad Wt[ci][co][tap] = ws[tap][ci][co]
+      seg(us, SEG_IN_ACTF32, m->bscr + a.wsc[1], SEG_OUT_GRADS, off(hp.c1w), C, C, 9, 1, C, 1, CC, 0, 0);
+      seg(us, SEG_IN_ACTF32, m->bscr + a.wsc[2], SEG_OUT_GRADS, off(hp.c2w), C, C, 9, 1, C, 1, CC, 0, 0);
+      const int gbp[3][2] = {{hp.g0, hp.b0}, {hp.g1, hp.b1}, {hp.g2, hp.b2}};
+      const int vv[3] = {16, hp.v1, hp.v2}, pp[3] = {16, hp.p1, hp.p2};
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 2; ++j)  // NHWC (pitch pp) -> [C][Hv][Wv]
+          seg(us, SEG_IN_ACTF32, m->bscr + a.gbs[i] + j * 1LL * pp[i] * pp[i] * C, SEG_OUT_GRADS, off(gbp[i][j]), 1, C,
+              vv[i], vv[i], 0, 1, 1LL * pp[i] * C, C, 0);
+    }
+  }
   m->dtok = ab.take(M * D, AL);
   m->dx0 = ab.take(M * D, AL);
   m->dx1 = ab.take(M * D, AL);
@@ -319,8 +417,6 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   m->dA0 = ab.take(Pmax * C, AL);
   m->dA1 = ab.take(Pmax * C, AL);
   m->red = af.take(2LL * B, AL);
-  m->wscratch = af.take(9LL * C * C, AL);
-  m->gbscratch = af.take(2LL * (Pmax / B) * C, AL);
   m->n_packbf = pb.n, m->n_packf32 = pf.n, m->n_actbf = ab.n, m->n_actf32 = af.n;
   long long o = 0;
   m->o_packbf = o;
@@ -331,6 +427,12 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   o = align_up(o + m->n_actbf * 2, 1024);
   m->o_actf32 = o;
   o = align_up(o + m->n_actf32 * 4, 1024);
+  m->o_table = o;
+  o = align_up(o + static_cast<long long>(m->h_table.size()) * 4, 1024);
+  m->o_pack_segs = o;
+  o = align_up(o + static_cast<long long>(m->pack_specs.size()) * sizeof(theia_perm_seg), 1024);
+  m->o_unpack_segs = o;
+  o = align_up(o + static_cast<long long>(m->unpack_specs.size()) * sizeof(theia_perm_seg), 1024);
   m->ws_bytes = o;
   *out = m;
   return THEIA_OK;
@@ -363,6 +465,20 @@ extern "C" int theia_model_debug_ptr(theia_model* m, const char* name, int i, vo
   if (n == "tokens") { *ptr = AB(m->tokens); *elems = M * D; return 0; }
   if (n == "dtok") { *ptr = AB(m->dtok); *elems = M * D; return 0; }
   if (n == "x") { if (i < 0 || i > m->L) return THEIA_ERR_ARG; *ptr = AB(m->x[i]); *elems = M * D; return 0; }
+  if (i >= 0 && i < m->L) {  // bf16 operand copies of the layer's Linear weights (refreshed by pack / adamw)
+    const LayerW& w = m->lw[i];
+    const long long DD = 1LL * D * D;
+    auto PBp = [&](long long off) { return static_cast<void*>(reinterpret_cast<bf16*>(m->ws + m->o_packbf) + off); };
+    if (n == "wqkv") { *ptr = PBp(w.wqkv); *elems = 3 * DD; return 0; }
+    if (n == "wo") { *ptr = PBp(w.wo); *elems = DD; return 0; }
+    if (n == "w1") { *ptr = PBp(w.w1); *elems = 4 * DD; return 0; }
+    if (n == "w2") { *ptr = PBp(w.w2); *elems = 4 * DD; return 0; }
+  }
+  if (i >= 0 && i < m->T && m->hp[i].hw != 1) {
+    auto PBp = [&](long long off) { return static_cast<void*>(reinterpret_cast<bf16*>(m->ws + m->o_packbf) + off); };
+    if (n == "c1F") { *ptr = PBp(m->hw[i].c1F); *elems = 9LL * D * D; return 0; }
+    if (n == "padD") { *ptr = PBp(m->hw[i].padD); *elems = 9LL * D * D; return 0; }
+  }
   if (i >= 0 && i < m->L) {
     const LayerA& a = m->la[i];
     if (n == "ln1") { *ptr = AB(a.ln1); *elems = M * D; return 0; }
@@ -386,11 +502,61 @@ extern "C" int theia_model_debug_ptr(theia_model* m, const char* name, int i, vo
   return set_error(THEIA_ERR_ARG, "unknown activation %s[%d]", name, i);
 }
 
+namespace {
+// resolve a segment table against the bound buffers and upload it (bind time only: synchronous copy)
+int upload_segs(theia_model* m, const std::vector<SegSpec>& specs, long long ws_off, long long* total_blocks) {
+  std::vector<theia_perm_seg> h(specs.size());
+  long long blocks = 0;
+  for (size_t i = 0; i < specs.size(); ++i) {
+    const SegSpec& q = specs[i];
+    theia_perm_seg& g = h[i];
+    memset(&g, 0, sizeof(g));
+    g.in = q.in_base == SEG_IN_MASTER ? static_cast<const void*>(m->master + q.in_off)
+                                      : static_cast<const void*>(reinterpret_cast<float*>(m->ws + m->o_actf32) + q.in_off);
+    if (q.out_base == SEG_OUT_PACKBF) g.out = reinterpret_cast<bf16*>(m->ws + m->o_packbf) + q.out_off;
+    else if (q.out_base == SEG_OUT_PACKF32) g.out = reinterpret_cast<float*>(m->ws + m->o_packf32) + q.out_off;
+    else g.out = reinterpret_cast<void*>(static_cast<uintptr_t>(q.out_off) * 4);  // relative to the gradient buffer
+    g.out_f32 = q.out_base != SEG_OUT_PACKBF;
+    g.n0 = q.n0, g.n1 = q.n1, g.n2 = q.n2, g.n3 = q.n3;
+    g.s0 = q.s0, g.s1 = q.s1, g.s2 = q.s2, g.s3 = q.s3, g.base = q.base;
+    g.lim1 = q.lim1, g.lim2 = q.lim2;
+    g.first_block = blocks;
+    blocks += (1LL * q.n0 * q.n1 * q.n2 * q.n3 + 255) / 256;
+  }
+  *total_blocks = blocks;
+  if (h.empty()) return THEIA_OK;
+  cudaError_t e = cudaMemcpy(m->ws + ws_off, h.data(), h.size() * sizeof(theia_perm_seg), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return theia::set_error(THEIA_ERR_CUDA, "segment table upload: %s", cudaGetErrorString(e));
+  return THEIA_OK;
+}
+}  // namespace
+
+// grads may be NULL (inference only) or re-bound before each backward (theia_model_set_grads)
 extern "C" int theia_model_bind(theia_model* m, float* master, float* grads, void* workspace) {
   if (!master || !workspace) return set_error(THEIA_ERR_ARG, "bind: null");
   m->master = master;
   m->grads = grads;
   m->ws = static_cast<uint8_t*>(workspace);
+  cudaError_t e = cudaMemcpy(m->ws + m->o_table, m->h_table.data(), m->h_table.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "pack table upload: %s", cudaGetErrorString(e));
+  int rc = upload_segs(m, m->pack_specs, m->o_pack_segs, &m->pack_blocks);
+  if (rc) return rc;
+  return upload_segs(m, m->unpack_specs, m->o_unpack_segs, &m->unpack_blocks);
+}
+
+// Switch the gradient buffer (same layout) without touching anything else: lets the caller hand out the buffer of
+// the previous backward (autograd keeps views of it as .grad) while the next backward writes another one.
+extern "C" int theia_model_set_grads(theia_model* m, float* grads) {
+  if (!m->master || !m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
+  if (!grads) return set_error(THEIA_ERR_ARG, "set_grads: null");
+  m->grads = grads;
+  return THEIA_OK;
+}
+
+extern "C" int theia_model_pack_table(theia_model* m, const int** table, void** packbf) {
+  if (!m->master || !m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
+  *table = reinterpret_cast<const int*>(m->ws + m->o_table);
+  *packbf = m->ws + m->o_packbf;
   return THEIA_OK;
 }
 
@@ -463,6 +629,15 @@ int linear(const Ctx& c, const bf16* x, const bf16* w, const float* bias, void* 
   theia_gemm_desc d = gemm_base(M, N, K);
   d.A = x, d.lda = K, d.B = w, d.ldb = K;
   d.out = out, d.ldo = N, d.bias = bias, d.epi = epi, d.aux = aux, d.out2 = out2, d.colsum = colsum;
+  return theia_gemm(&d, c.s);
+}
+
+// dx[M,N] = dy[M,K] * w[K,N]  with w = the forward weight [out = K][in = N] read in place as an MN-major B operand
+int linear_dgrad(const Ctx& c, const bf16* dy, const bf16* w, void* out, int M, int N, int K, int epi,
+                 const void* aux = nullptr, float* colsum = nullptr) {
+  theia_gemm_desc d = gemm_base(M, N, K);
+  d.A = dy, d.lda = K, d.B = w, d.ldb = N, d.b_mode = THEIA_OP_MN2D;
+  d.out = out, d.ldo = N, d.epi = epi, d.aux = aux, d.colsum = colsum;
   return theia_gemm(&d, c.s);
 }
 
@@ -644,63 +819,22 @@ int zero_f32(const Ctx& c, float* p, long long n) {
 
 }  // namespace
 
-// fp32 master -> bf16 / permuted operand copies.  Call after every optimizer step.
-extern "C" int theia_model_pack(theia_model* m, void* stream) {
+// fp32 master -> bf16 / permuted operand copies: 3 launches (Linear-weight casts through the pack table -- skipped
+// when theia_adamw_flat already refreshed them --, the token table, one segmented gather for the conv-weight packs
+// and the LayerNorm[C,H,W] affines).  Call after every optimizer step.
+extern "C" int theia_model_pack(theia_model* m, int skip_linear_cast, void* stream) {
   if (!m->master || !m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
   Ctx c{m, static_cast<cudaStream_t>(stream)};
-  const int D = m->D, C = m->D;
-  TRY(theia_cast_bf16(c.W(m->pew), c.PB(m->wpe), 768LL * D, c.s));
+  const int D = m->D;
+  if (!skip_linear_cast)
+    TRY(theia_pack_cast(m->master, reinterpret_cast<const int*>(m->ws + m->o_table), m->ws + m->o_packbf,
+                        m->n_params_total, c.s));
   token_table_kernel<<<(m->N * D + 255) / 256, 256, 0, c.s>>>(c.PF(m->tokt), c.W(m->pos), m->cls >= 0 ? c.W(m->cls) : nullptr,
                                                              m->regt >= 0 ? c.W(m->regt) : nullptr,
                                                              m->regp >= 0 ? c.W(m->regp) : nullptr, m->N, D, m->p0);
   THEIA_CHECK_LAUNCH("token_table");
-  for (int l = 0; l < m->L; ++l) {
-    const LayerP& p = m->lp[l];
-    const LayerW& w = m->lw[l];
-    TRY(theia_cast_bf16(c.W(p.qw), c.PB(w.wqkv), 3LL * D * D, c.s));  // q,k,v are adjacent in the flat buffer
-    TRY(theia_transpose_cast_bf16(c.W(p.qw), c.PB(w.wqkvT), 3 * D, D, c.s));
-    TRY(theia_cast_bf16(c.W(p.ow), c.PB(w.wo), 1LL * D * D, c.s));
-    TRY(theia_transpose_cast_bf16(c.W(p.ow), c.PB(w.woT), D, D, c.s));
-    TRY(theia_cast_bf16(c.W(p.f1w), c.PB(w.w1), 4LL * D * D, c.s));
-    TRY(theia_transpose_cast_bf16(c.W(p.f1w), c.PB(w.w1T), 4 * D, D, c.s));
-    TRY(theia_cast_bf16(c.W(p.f2w), c.PB(w.w2), 4LL * D * D, c.s));
-    TRY(theia_transpose_cast_bf16(c.W(p.f2w), c.PB(w.w2T), D, 4 * D, c.s));
-  }
-  for (int t = 0; t < m->T; ++t) {
-    const HeadP& p = m->hp[t];
-    const HeadW& w = m->hw[t];
-    if (p.hw == 1) {
-      TRY(theia_cast_bf16(c.W(p.lw), c.PB(w.l), 1LL * p.ct * C, c.s));
-      TRY(theia_transpose_cast_bf16(c.W(p.lw), c.PB(w.lT), p.ct, C, c.s));
-      continue;
-    }
-    const long long C9 = 9LL * C;
-    // ConvTranspose2d weight [Cin][Cout][3][3]: fwd pack F[co][tap2][ci] = Wt[ci][co][8-tap2]
-    TRY(theia_gather4(c.W(p.padw), c.PB(w.padF), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
-    // dgrad pack D[ci][tap][co] = Wt[ci][co][tap]
-    TRY(theia_gather4(c.W(p.padw), c.PB(w.padD), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
-    // Conv2d weight [Cout][Cin][3][3]: fwd F[co][tap][ci]; dgrad D[ci][tap2][co] = W[co][ci][8-tap2]
-    if (p.hw == 16) {
-      TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1F), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
-      TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1D), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
-      TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2F), 1, 0, C, 9, C, 1, C9, 1, 9, 0, 0, c.s));
-      TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2D), 1, 0, C, 9, C, 1, 9, -1, C9, 0, 8, c.s));
-    } else {
-      // ConvTranspose2d(s2) weight [Cin][Cout][3][3] -> tap-major F[tap][co][ci] and D[tap][ci][co]
-      TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1F), 1, 0, 9, C, C, 1, 1, 9, C9, 0, 0, c.s));
-      TRY(theia_gather4(c.W(p.c1w), c.PB(w.c1D), 1, 0, 9, C, C, 1, 1, C9, 9, 0, 0, c.s));
-      TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2F), 1, 0, 9, C, C, 1, 1, 9, C9, 0, 0, c.s));
-      TRY(theia_gather4(c.W(p.c2w), c.PB(w.c2D), 1, 0, 9, C, C, 1, 1, C9, 9, 0, 0, c.s));
-    }
-    TRY(theia_cast_bf16(c.W(p.lw), c.PB(w.l), 1LL * p.ct * C, c.s));
-    TRY(theia_transpose_cast_bf16(c.W(p.lw), c.PB(w.lT), p.ct, C, c.s));
-    // LN affine [C][Hv][Wv] -> NHWC [Hp][Wp][C] (zero padded for the 31x31 stage)
-    const int gbp[3][2] = {{p.g0, p.b0}, {p.g1, p.b1}, {p.g2, p.b2}};
-    const int vv[3] = {16, p.v1, p.v2}, pp[3] = {16, p.p1, p.p2};
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 2; ++j)
-        TRY(theia_chw_to_hwc(c.W(gbp[i][j]), c.PF(w.gb[i][j]), C, vv[i], vv[i], pp[i], pp[i], c.s));
-  }
+  TRY(theia_perm_segments(reinterpret_cast<const theia_perm_seg*>(m->ws + m->o_pack_segs),
+                          static_cast<int>(m->pack_specs.size()), m->pack_blocks, nullptr, c.s));
   return THEIA_OK;
 }
 
@@ -804,9 +938,8 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
   if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
   bf16* dA0 = c.AB(m->dA0);
   bf16* dA1 = c.AB(m->dA1);
-  float* wsc = c.AF(m->wscratch);
-  float* gbs = c.AF(m->gbscratch);
   float* red = c.AF(m->red);
+  bool any_head = false;
   for (int t = 0; t < m->T; ++t) {
     if (!dpreds || !dpreds[t]) continue;
     const HeadP& p = m->hp[t];
@@ -824,11 +957,15 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
       TRY(theia_colsum(dp, c.G(p.lb), B, p.ct, p.ct, 0, c.s));
       {  // d tokens[:, 0] += dp W
         theia_gemm_desc d = gemm_base(B, C, p.ct);
-        d.A = dp, d.lda = p.ct, d.B = c.PB(w.lT), d.ldb = p.ct;
+        d.A = dp, d.lda = p.ct, d.B = c.PB(w.l), d.ldb = C, d.b_mode = THEIA_OP_MN2D;
         d.out = c.AB(m->dtok), d.ldo = 1LL * NT * D, d.epi = THEIA_EPI_RESID, d.aux = c.AB(m->dtok);
         TRY(theia_gemm(&d, c.s));
       }
       continue;
+    }
+    if (!any_head) {  // conv weight-gradient / LN-affine-gradient scratch of ALL heads: one memset
+      TRY(zero_f32(c, c.AF(m->bscr), m->n_bscr));
+      any_head = true;
     }
     float* st0 = c.AF(a.stats);
     float* st1 = st0 + 2 * B;
@@ -837,13 +974,11 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     // Linear(C -> C_t)
     TRY(wgrad(c, dp, c.AB(a.ln2), c.G(p.lw), static_cast<int>(P2), p.ct, C));
     TRY(theia_colsum(dp, c.G(p.lb), static_cast<int>(P2), p.ct, p.ct, 0, c.s));
-    TRY(linear(c, dp, c.PB(w.lT), nullptr, dA0, static_cast<int>(P2), C, p.ct, 0));
+    TRY(linear_dgrad(c, dp, c.PB(w.l), dA0, static_cast<int>(P2), C, p.ct, 0));
     theia_conv_geom g;
-    const int gbp[3][2] = {{p.g0, p.b0}, {p.g1, p.b1}, {p.g2, p.b2}};
     const bf16* lnin[3] = {c.AB(a.padout), c.AB(a.c1), c.AB(a.c2)};
     float* sts[3] = {st0, st1, st2};
     const bf16* convin[3] = {nullptr, c.AB(a.ln0), c.AB(a.ln1)};
-    const int convw[3] = {p.padw, p.c1w, p.c2w};
     const int convb[3] = {p.padb, p.c1b, p.c2b};
     const long long convD[3] = {w.padD, w.c1D, w.c2D};
     const int vv[3] = {16, p.v1, p.v2}, pp[3] = {16, p.p1, p.p2};
@@ -851,32 +986,24 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
       // LayerNorm([C,H,W]) backward (+ ReLU mask of the conv that produced its input)
       const long long npix = 1LL * pp[i] * pp[i];
       const int rows = static_cast<int>(B * npix);
-      TRY(zero_f32(c, gbs, 2 * npix * C));
+      float* gbs = c.AF(m->bscr + a.gbs[i]);  // dgamma | dbeta in NHWC; unpacked to [C,H,W] at the end
+      float* wsc = c.AF(m->bscr + a.wsc[i]);  // conv weight gradient, tap-major; unpacked at the end
       TRY(theia_ln3d_bwd(dA0, lnin[i], sts[i], c.PF(w.gb[i][0]), red, dA1, gbs, gbs + npix * C, B,
                          static_cast<int>(npix * C), 1e-5f, i > 0 ? 1 : 0, C, pp[i] != vv[i] ? pp[i] : 0, vv[i], c.s));
-      TRY(theia_hwc_to_chw(gbs, c.G(gbp[i][0]), C, vv[i], vv[i], pp[i], pp[i], c.s));
-      TRY(theia_hwc_to_chw(gbs + npix * C, c.G(gbp[i][1]), C, vv[i], vv[i], pp[i], pp[i], c.s));
       // conv i backward: dA1 = gradient of its (pre-activation) output
       TRY(theia_colsum(dA1, c.G(convb[i]), rows, C, C, 0, c.s));
-      TRY(zero_f32(c, wsc, 9LL * C * C));
       if (i > 0 && p.hw == 16) {
         conv_geom_16(g, C, 16, B, C, 16LL * C, 256LL * C, -1);
         TRY(conv_wgrad(c, dA1, convin[i], g, wsc, C));
-        // grad W[co][ci][tap] = ws[tap][co][ci]
-        TRY(theia_gather4(wsc, c.G(convw[i]), 1, 1, C, C, 9, 1, C, 1, 1LL * C * C, 0, 0, c.s));
         TRY(conv3x3(c, dA1, g, c.PB(convD[i]), nullptr, dA0, C, C, 0, nullptr, nullptr));
       } else if (i > 0) {
         // stride-2 ConvTranspose2d: input map vv[i-1] (pitch pp[i-1]) -> output map vv[i] (pitch pp[i])
         const int pad = i == 1 ? 1 : 0;
         TRY(convT2x_wgrad(c, convin[i], dA1, wsc, C, B, vv[i - 1], pp[i - 1], vv[i], pp[i], pad));
-        // grad Wt[ci][co][tap] = ws[tap][ci][co]
-        TRY(theia_gather4(wsc, c.G(convw[i]), 1, 1, C, C, 9, 1, C, 1, 1LL * C * C, 0, 0, c.s));
         TRY(convT2x_dgrad(c, dA1, c.PB(convD[i]), dA0, C, B, vv[i - 1], pp[i - 1], vv[i], pp[i], pad));
       } else {
         conv_geom_16(g, C, 14, B, D, 14LL * D, 1LL * NT * D, -2);
         TRY(conv_wgrad(c, dA1, c.AB(m->tokens) + 1LL * m->p0 * D, g, wsc, C));
-        // grad Wt[ci][co][t] = ws[8-t][co][ci]
-        TRY(theia_gather4(wsc, c.G(convw[i]), 1, 1, C, C, 9, 1, 1, C, -1LL * C * C, 0, 8LL * C * C, c.s));
         // dgrad onto the 14x14 token grid, accumulated over heads
         conv_geom_16(g, C, 16, B, C, 16LL * C, 256LL * C, 0);
         g.out_h = 14, g.out_w = 14, g.out_img_rows = NT, g.out_row_off = m->p0, g.out_wpitch = 14;
@@ -884,6 +1011,10 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
       }
     }
   }
+  // tap-major conv weight gradients and NHWC LayerNorm-affine gradients of all heads -> reference layouts: one launch
+  if (any_head)
+    TRY(theia_perm_segments(reinterpret_cast<const theia_perm_seg*>(m->ws + m->o_unpack_segs),
+                            static_cast<int>(m->unpack_specs.size()), m->unpack_blocks, m->grads, c.s));
   // final LayerNorm
   bf16* dx = c.AB(m->dx0);
   bf16* dx2 = c.AB(m->dx1);
@@ -897,19 +1028,19 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     const LayerA& a = m->la[l];
     // MLP
     TRY(wgrad(c, dx, c.AB(a.a), c.G(p.f2w), M, D, 4 * D));
-    TRY(linear(c, dx, c.PB(w.w2T), nullptr, c.AB(m->dh), M, 4 * D, D, THEIA_EPI_MUL_AUX | THEIA_EPI_COLSUM,
-               c.AB(a.h), nullptr, c.G(p.f1b)));
+    TRY(linear_dgrad(c, dx, c.PB(w.w2), c.AB(m->dh), M, 4 * D, D, THEIA_EPI_MUL_AUX | THEIA_EPI_COLSUM, c.AB(a.h),
+                     c.G(p.f1b)));
     TRY(wgrad(c, c.AB(m->dh), c.AB(a.ln2), c.G(p.f1w), M, 4 * D, D));
-    TRY(linear(c, c.AB(m->dh), c.PB(w.w1T), nullptr, c.AB(m->dln), M, D, 4 * D, 0));
+    TRY(linear_dgrad(c, c.AB(m->dh), c.PB(w.w1), c.AB(m->dln), M, D, 4 * D, 0));
     TRY(theia_layernorm_bwd(c.AB(m->dln), c.AB(a.xmid), c.W(p.ln2w), c.AF(a.mean2), c.AF(a.rstd2), dx, dx2,
                             c.G(p.ln2w), c.G(p.ln2b), c.G(p.ob), M, D, c.s));
     // attention
     TRY(wgrad(c, dx2, c.AB(a.attn), c.G(p.ow), M, D, D));
-    TRY(linear(c, dx2, c.PB(w.woT), nullptr, c.AB(m->dattn), M, D, D, 0));
+    TRY(linear_dgrad(c, dx2, c.PB(w.wo), c.AB(m->dattn), M, D, D, 0));
     TRY(theia_attention_tc_bwd(c.AB(a.qkv), c.AB(a.attn), c.AB(m->dattn), c.AF(a.lse), c.AB(m->dqkv), B, NT, H, c.s));
     TRY(wgrad(c, c.AB(m->dqkv), c.AB(a.ln1), c.G(p.qw), M, 3 * D, D));
     TRY(theia_colsum(c.AB(m->dqkv), c.G(p.qb), M, 3 * D, 3 * D, 0, c.s));
-    TRY(linear(c, c.AB(m->dqkv), c.PB(w.wqkvT), nullptr, c.AB(m->dln), M, D, 3 * D, 0));
+    TRY(linear_dgrad(c, c.AB(m->dqkv), c.PB(w.wqkv), c.AB(m->dln), M, D, 3 * D, 0));
     TRY(theia_layernorm_bwd(c.AB(m->dln), c.AB(m->x[l]), c.W(p.ln1w), c.AF(a.mean1), c.AF(a.rstd1), dx2, dx,
                             c.G(p.ln1w), c.G(p.ln1b), l > 0 ? c.G(m->lp[l - 1].f2b) : nullptr, M, D, c.s));
   }

@@ -69,9 +69,12 @@ class _ForwardFn(torch.autograd.Function):
             raise L.TheiaError("backward() called for a stale forward: theia_b200 keeps the activations of the "
                                "most recent forward only")
         grads = m._run_backward(ctx.names, dpreds)
+        used = {m._teachers.index(t) for t in ctx.names}
         out = []
-        for i, p in enumerate(m._param_list):
-            out.append(grads[i] if ctx.needs_input_grad[4 + i] else None)
+        for i, h in enumerate(m._param_head):
+            # parameters of heads that were not run have no gradient at all (the reference's autograd never reaches
+            # them: grad stays None and torch.optim.AdamW skips them), not a zero gradient
+            out.append(grads[i] if (ctx.needs_input_grad[4 + i] and (h < 0 or h in used)) else None)
         return (None, None, None, None, *out)
 
 
@@ -95,8 +98,9 @@ class _LossFn(torch.autograd.Function):
             raise ValueError(f"target shape {tuple(target.shape)} does not match prediction {tuple(pred.shape)}")
         acc = torch.empty((B, 5), dtype=torch.float32, device=pred.device)
         out = torch.empty((3,), dtype=torch.float32, device=pred.device)
-        L.check(L.lib().theia_loss_fwd(pred.data_ptr(), target.data_ptr(), int(target.dtype == torch.bfloat16),
-                                       acc.data_ptr(), out.data_ptr(), B, n, L.stream_ptr()), "theia_loss_fwd")
+        with torch.cuda.device(pred.device):
+            L.check(L.lib().theia_loss_fwd(pred.data_ptr(), target.data_ptr(), int(target.dtype == torch.bfloat16),
+                                           acc.data_ptr(), out.data_ptr(), B, n, L.stream_ptr()), "theia_loss_fwd")
         ctx.save_for_backward(pred, target, acc)
         return out
 
@@ -107,9 +111,10 @@ class _LossFn(torch.autograd.Function):
         n = pred[0].numel()
         coef = g.contiguous().float()
         dpred = torch.empty_like(pred)
-        L.check(L.lib().theia_loss_bwd(pred.data_ptr(), target.data_ptr(), int(target.dtype == torch.bfloat16),
-                                       acc.data_ptr(), coef.data_ptr(), dpred.data_ptr(), 1, B, n, L.stream_ptr()),
-                "theia_loss_bwd")
+        with torch.cuda.device(pred.device):
+            L.check(L.lib().theia_loss_bwd(pred.data_ptr(), target.data_ptr(), int(target.dtype == torch.bfloat16),
+                                           acc.data_ptr(), coef.data_ptr(), dpred.data_ptr(), 1, B, n, L.stream_ptr()),
+                    "theia_loss_bwd")
         return dpred, None
 
 
@@ -168,7 +173,9 @@ class RobotVisionFM(nn.Module):
         self._handle = None
         self._handle_batch = 0
         self._workspace = None
-        self._grads = None
+        self._gbufs = [None, None]
+        self._gcur = 0
+        self._pack_table = (0, 0)
         self._packed_version = None
         self._fwd_id = 0
         self._dpred_bf16 = {}
@@ -197,6 +204,9 @@ class RobotVisionFM(nn.Module):
             p = nn.Parameter(self._flat[o:o + math.prod(shape)].view(shape))
             owner.register_parameter(parts[-1], p)
             self._param_list.append(p)
+        prefixes = ["translator.translator_heads." + t.replace(".", "_") + "." for t in self._teachers]
+        self._param_head = [next((i for i, pre in enumerate(prefixes) if name.startswith(pre)), -1)
+                            for name, _, _ in self._param_meta]
         self.reset_parameters()
         if checkpoint_path:
             self.load_pretrained_weights(checkpoint_path)
@@ -276,7 +286,8 @@ class RobotVisionFM(nn.Module):
             L.lib().theia_model_destroy(self._handle)
         self._handle = None
         self._workspace = None
-        self._grads = None
+        self._gbufs = [None, None]
+        self._pack_table = (0, 0)
         self._packed_version = None
 
     def __del__(self):
@@ -318,14 +329,52 @@ class RobotVisionFM(nn.Module):
             nbytes = lib.theia_model_workspace_bytes(self._handle)
             dev = self._flat.device
             self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            self._grads = torch.zeros_like(self._flat)
-            L.check(lib.theia_model_bind(self._handle, self._flat.data_ptr(), self._grads.data_ptr(),
-                                         self._workspace.data_ptr()), "theia_model_bind")
+            self._gbufs = [None, None]  # gradient buffers are allocated by the first backward (none for inference)
+            self._gcur = 0
+            L.check(lib.theia_model_bind(self._handle, self._flat.data_ptr(), 0, self._workspace.data_ptr()),
+                    "theia_model_bind")
+            tab, pk = C.c_void_p(), C.c_void_p()
+            L.check(lib.theia_model_pack_table(self._handle, C.byref(tab), C.byref(pk)), "theia_model_pack_table")
+            self._pack_table = (tab.value, pk.value)
             self._packed_version = None
-        v = self._flat._version
+        v = self._weights_version()
         if self._packed_version != v:
-            L.check(L.lib().theia_model_pack(self._handle, L.stream_ptr()), "theia_model_pack")
+            L.check(L.lib().theia_model_pack(self._handle, 0, L.stream_ptr()), "theia_model_pack")
             self._packed_version = v
+
+    def _adamw_pack_args(self):
+        """(pack table, bf16 pack buffer) device pointers for theia_adamw_flat, or (0, 0) before the first forward."""
+        return self._pack_table if self._handle is not None else (0, 0)
+
+    def _after_optimizer_step(self, fused_cast: bool) -> None:
+        """FlatAdamW updated the flat buffer through its raw pointer (no version counter moves): refresh the packs
+        that are not plain casts (token table, conv-weight gathers, LayerNorm[C,H,W] affines) right away."""
+        if self._handle is None:
+            return
+        L.check(L.lib().theia_model_pack(self._handle, int(fused_cast), L.stream_ptr()), "theia_model_pack")
+        self._packed_version = self._weights_version()
+
+    def _next_grad_buffer(self) -> torch.Tensor:
+        """Flat gradient buffer the next backward writes.  Two buffers alternate so that the views handed to autograd
+        by the previous backward (which it may keep as `.grad`) are never overwritten; if the candidate is STILL
+        referenced by some `.grad` (gradient accumulation over 3+ backwards), a fresh one replaces it."""
+        k = self._gcur ^ 1
+        buf = self._gbufs[k]
+        if buf is not None:
+            lo, hi = buf.data_ptr(), buf.data_ptr() + buf.numel() * 4
+            if any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self._param_list):
+                buf = None
+        if buf is None:
+            buf = torch.empty_like(self._flat)
+            self._gbufs[k] = buf
+        self._gcur = k
+        return buf
+
+    def _weights_version(self):
+        """Changes whenever any parameter is written in place.  After `.to()/.cuda()` every Parameter keeps its OWN
+        version counter (`p.data = view` does not share the new flat buffer's), so the key sums all of them: an
+        in-place update through any view (torch optimizers, `load_state_dict`, `p.mul_()`) is seen."""
+        return (self._flat._version, sum(p._version for p in self._param_list))
 
     def _prep_images(self, x, do_resize: bool) -> tuple[torch.Tensor, int]:
         """uint8 [B,224,224,3] or [B,3,224,224] on the model's device (backbones.py:337-339 accepts tensors,
@@ -373,9 +422,14 @@ class RobotVisionFM(nn.Module):
         return preds
 
     def _run_forward(self, images, names, kw):
-        return self._run_backbone(images, kw, True, names)
+        with torch.cuda.device(self._flat.device):  # kernels launch on the model's device whatever the current one is
+            return self._run_backbone(images, kw, True, names)
 
     def _run_backward(self, names, dpreds):
+        with torch.cuda.device(self._flat.device):
+            return self._run_backward_impl(names, dpreds)
+
+    def _run_backward_impl(self, names, dpreds):
         lib = L.lib()
         B = self._last_B
         ptrs = (C.c_void_p * L.MAX_TEACHERS)()
@@ -396,8 +450,9 @@ class RobotVisionFM(nn.Module):
                 self._dpred_bf16[t] = buf
             L.check(lib.theia_cast_bf16(g.data_ptr(), buf.data_ptr(), g.numel(), L.stream_ptr()), "theia_cast_bf16")
             ptrs[i] = buf.data_ptr()
+        flat_g = self._next_grad_buffer()  # autograd may keep what we return as .grad: buffers alternate, no copy
+        L.check(lib.theia_model_set_grads(self._handle, flat_g.data_ptr()), "theia_model_set_grads")
         L.check(lib.theia_model_backward(self._handle, ptrs, L.stream_ptr()), "theia_model_backward")
-        flat_g = self._grads.clone()  # autograd may keep what we return as .grad; the internal buffer is reused
         if self._grad_sync is not None:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(self._grad_sync[0]) > 1:
@@ -407,8 +462,12 @@ class RobotVisionFM(nn.Module):
     def forward_feature(self, x: torch.Tensor, **kwargs: Any) -> torch.Tensor:
         """rvfm.py:94-113.  Returns fp32 like the reference; not differentiable (inference API)."""
         B = len(x) if isinstance(x, (list, tuple)) else (1 if getattr(x, "ndim", 4) == 3 else x.shape[0])
-        tok = torch.empty((B, self._seq, self.hidden), dtype=torch.bfloat16, device=self._flat.device)
-        self._run_backbone(x, kwargs, False, (), tokens_out=tok)
+        if not self._flat.is_cuda:
+            raise L.TheiaError("theia_b200.RobotVisionFM runs on CUDA only: call .cuda()/.to(device) first "
+                               "(there is no CPU fallback)")
+        with torch.cuda.device(self._flat.device):
+            tok = torch.empty((B, self._seq, self.hidden), dtype=torch.bfloat16, device=self._flat.device)
+            self._run_backbone(x, kwargs, False, (), tokens_out=tok)
         return handle_feature_output(tok.float(), self.feature_reduce_method, self.num_reg_tokens)
 
     def forward(self, x: torch.Tensor, target_model_names: Optional[list[str]] = None,

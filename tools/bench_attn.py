@@ -21,10 +21,10 @@ def timeit(fn, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 fl = 4.0 * N * N * 64 * B * H
-for name in ("theia_attention_fwd", "theia_attention_tc_fwd"):
+for name in ("theia_attention_tc_fwd",):
     ms = timeit(lambda: L.check(getattr(lib, name)(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, s)))
     print(f"{name}: {ms:.4f} ms  {fl/ms/1e9:.1f} TFLOP/s (algorithmic)")
-for name in ("theia_attention_bwd", "theia_attention_tc_bwd"):
+for name in ("theia_attention_tc_bwd",):
     if not hasattr(lib, name): continue
     ms = timeit(lambda: L.check(getattr(lib, name)(qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, N, H, s)))
     print(f"{name}: {ms:.4f} ms  {2.5*fl/ms/1e9:.1f} TFLOP/s (algorithmic, 2.5x fwd)")
