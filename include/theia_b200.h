@@ -136,6 +136,9 @@ int theia_loss_bwd(const float* pred, const void* target, int target_is_bf16, co
  * bf16 patch rows [B*197, 768] (row b*197 is the zero CLS slot; column = c*256 + i*16 + j) */
 int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_resize, int do_rescale,
                      int do_normalize, const float* mean3, const float* std3, int tokens, int patch_off, void* stream);
+/* test hook for the byte stage: resized_u8_out != NULL -> following do_resize calls also write the resized +
+ * centre-cropped uint8 image [B,224,224,3] (what tvF.resize(..., antialias=True) + center_crop give the reference) */
+int theia_preprocess_debug_u8(void* resized_u8_out);
 /* tokens / patch_off: rows per image of the patch matrix and the row of the first patch (197 / 1 for DeiT, 196 / 0
  * for DeiTNoCLS, 204 / 1 for DeiTReg); rows of non-patch tokens are zero */
 /* attention (hf:modeling_vit.py:171-196,232-246): qkv [B*N,3*H*64] bf16 -> out [B*N,H*64]; lse [B,H,N] */

@@ -1,17 +1,14 @@
-// tcgen05 self-attention for the 197-token ViT sequence (head_dim 64), forward and backward.
+// tcgen05 self-attention for the ViT token sequence (<= 208 tokens, head_dim 64), forward and backward.
 // Replaces hf:models/vit/modeling_vit.py:171-196,232-246 (SDPA / eager attention) and its autograd.
 //
-// One persistent CTA per SM loops over (image, head) items.  Q/K/V (and dO) of an item are TMA-loaded
-// as 128-byte-swizzled [rows x 64] tiles straight from the fused qkv activation [B*N, 3*D]; the score
-// matrices live in TMEM; the probabilities go back to shared memory as the K-major A operand of the
-// second MMA; V (and K, Q, dO in backward) are read as MN-major B operands in place, so nothing is ever
-// transposed or copied.  Softmax is single pass (the whole 197-key row is in TMEM: no online rescaling).
-//
-//   forward, per item:    S_t = Q_t K^T  (2 query tiles of 128 rows, N = 208 keys)   -> TMEM
-//                         P_t = exp2((S_t - rowmax) * c)  (bf16, smem),  l = rowsum     (1 thread / row)
-//                         O_t = P_t V                                                   -> TMEM -> out, lse
-//   warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 softmax/epilogue of tile 0, 8-11 of tile 1.
+// One persistent CTA per SM loops over (image, head) items.  Q / K / V (and dO) of an item are TMA-loaded as
+// 128-byte-swizzled [rows x 64] tiles straight from the fused qkv activation [B*N, 3*D]; score matrices live in TMEM;
+// probabilities go back to shared memory as bf16 MMA operands; V (and K, Q, dO in the backward) are read as MN-major
+// B operands in place, so nothing is ever transposed or copied.  The whole key row of a query is on chip at once:
+// single-pass softmax, no online rescaling.  MMA-issuing warps run warp-uniform control flow with one elected lane
+// issuing (descriptors stay in uniform registers); all hand-offs are mbarriers.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -24,8 +21,16 @@ constexpr int AT_ROWS = 208;                  // rows per operand tile (197 padd
 constexpr int AT_TILE = AT_ROWS * 128;        // 26624 B, a multiple of the 1024-B swizzle atom
 constexpr int AT_PBUF = 128 * 128 * 4;        // P tile: 4 K-blocks of [128 rows x 64 keys] = 64 KB
 constexpr int AT_KSTEPS = AT_ROWS / 16;       // 13 MMA K-steps over the keys
-constexpr int ATF_THREADS = 384;
-constexpr int ATF_SMEM = 3 * AT_TILE + 2 * AT_PBUF + 256 + 1024;
+
+// Descriptor words for the MMA-issuing warps (128-byte swizzle, SBO = 1024, version 1): the high word is a constant,
+// the low word = address >> 4 | (LBO >> 4) << 16 advances by plain 32-bit adds (k-step of 32 bytes = +2, of 2048 = +128).
+// The whole issuing warp runs the (warp-uniform) control flow and one elected lane issues, which lets the compiler
+// keep all of this in uniform registers instead of wrapping every tcgen05.mma in a broadcast loop (gemm_tc.cu).
+constexpr uint32_t AT_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t at_desc_lo(uint32_t saddr, uint32_t lbo) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t at_desc(uint32_t lo) { return (static_cast<uint64_t>(AT_DESC_HI) << 32) | lo; }
 
 struct AttnFwdParams {
   bf16* out;
@@ -35,38 +40,135 @@ struct AttnFwdParams {
   float scale;
 };
 
-__global__ void __launch_bounds__(ATF_THREADS, 1)
-attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
+
+// --------------------------------------------------------------------------------------------
+// forward.  Per item two 128-query tiles u:  S_u = Q_u K^T (N = 208 keys) -> TMEM;  P_u = exp2((S_u - rowmax) c)
+// (bf16, shared memory), l = rowsum;  O_u = P_u V -> TMEM -> out, lse.
+//   * the 8 softmax warps work on ONE tile at a time, two warps per TMEM lane quarter, each thread holding its half
+//     of a score row (112 / 96 columns) in REGISTERS: the scores are read from TMEM once, the row maximum / sum of
+//     the two halves are exchanged through shared memory, and the TMEM score buffer is free for the next tile's
+//     MMAs as soon as it has been loaded;
+//   * two score buffers (columns 0-207 / 208-415) and a separate output accumulator (416-479): S_{u+1} = Q K^T and
+//     O_{u-1} = P V run on the tensor core WHILE the softmax of tile u runs on the SIMT pipes;
+//   * Q / K / V are double buffered across (image, head) items, so the loads of the next item are never exposed.
+// warps: 0 TMA, 1 MMA issue, 2 TMEM alloc, 4-11 softmax (quarter = warp % 4, column half = (warp - 4) / 4).
+// --------------------------------------------------------------------------------------------
+constexpr int AF_THREADS = 384;
+constexpr int AF_NSW = 8;
+constexpr int AF_OFF_Q = 0;
+constexpr int AF_OFF_K = 2 * AT_TILE;
+constexpr int AF_OFF_V = 4 * AT_TILE;
+constexpr int AF_OFF_P = 6 * AT_TILE;           // 4 blocks of [128 queries x 64 keys]
+constexpr int AF_OFF_X = AF_OFF_P + AT_PBUF;     // exchange: max[2][128] | sum[2][128] floats
+constexpr int AF_OFF_BAR = AF_OFF_X + 4 * 128 * 4;
+constexpr int AF_SMEM = AF_OFF_BAR + 256 + 1024;
+static_assert(AF_SMEM <= 232448, "attention forward: shared memory");
+
+
+// Softmax of one 128-query score tile for the column half HH of this thread's row: scores -> registers (the TMEM
+// buffer is released right after the load), row max / sum exchanged with the partner warp of the same lane quarter
+// through shared memory (named barrier 1 + quarter, 64 threads), P written as the K-major bf16 A operand of P V.
+// NFIX > 0: the sequence length is a compile-time constant, so only the chunk that holds padding keys is masked.
+template <int HH, int NFIX>
+__device__ __forceinline__ void softmax_tile(uint32_t tsb, int n_rt, float c2, uint64_t* s_free_bar, uint64_t* o_full_bar,
+                                             uint32_t o_wait, uint32_t o_parity, uint32_t xs, int wq, int r, int lane,
+                                             uint32_t prow_s, int sw, float& m_out, float& l_out) {
+  constexpr int CH0 = HH ? 7 : 0;
+  constexpr int NCH = HH ? AT_KSTEPS - 7 : 7;
+  const int N = NFIX > 0 ? NFIX : n_rt;
+  uint32_t v[NCH][16];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) tmem_ld16(tsb + (CH0 + k) * 16, v[k]);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(s_free_bar);
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int c0 = (CH0 + k) * 16;
+    if (NFIX > 0 ? (c0 + 16 > NFIX) : (c0 + 16 > N)) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (c0 + e >= N) v[k][e] = __float_as_uint(-INFINITY);
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) m = fmaxf(m, __uint_as_float(v[k][e]));
+  }
+  sts32(xs + (HH * 128 + r) * 4, __float_as_uint(m));
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
+  m = fmaxf(m, lds_f32(xs + ((HH ^ 1) * 128 + r) * 4));
+  const float mc = m * c2;
+  float l = 0.f;
+  uint32_t pk[NCH][8];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    float pv[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) pv[e] = ex2_approx_ftz(fmaf(__uint_as_float(v[k][e]), c2, -mc));
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};  // four partial sums: no 16-deep dependent FADD chain behind the MUFU results
+#pragma unroll
+    for (int e = 0; e < 16; ++e) l4[e & 3] += pv[e];
+    l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) pk[k][e] = pack_bf16x2(pv[2 * e], pv[2 * e + 1]);
+  }
+  sts32(xs + (256 + HH * 128 + r) * 4, __float_as_uint(l));
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
+  l += lds_f32(xs + (256 + (HH ^ 1) * 128 + r) * 4);
+  // P_{g-1} V has finished: its accumulator is complete and the P buffer may be overwritten
+  if (o_wait) {
+    mbar_wait(o_full_bar, o_parity);
+    tc_fence_after();
+  }
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    constexpr int dummy2 = 0;
+    (void)dummy2;
+    const int gch = CH0 + k;
+    const uint32_t blk = prow_s + (gch >> 2) * 16384;
+    const int ck = (gch & 3) * 2;
+    sts128(blk + ((ck ^ sw) << 4), pk[k][0], pk[k][1], pk[k][2], pk[k][3]);
+    sts128(blk + (((ck + 1) ^ sw) << 4), pk[k][4], pk[k][5], pk[k][6], pk[k][7]);
+  }
+  m_out = m, l_out = l;
+}
+
+template <int NFIX>
+__global__ void __launch_bounds__(AF_THREADS, 1)
+attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw_at[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_at) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + AT_TILE;
-  uint8_t* sV = smem + 2 * AT_TILE;
-  uint8_t* sP[2] = {smem + 3 * AT_TILE, smem + 3 * AT_TILE + AT_PBUF};
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * AT_TILE + 2 * AT_PBUF);
-  uint64_t* qk_full = bars + 0;
-  uint64_t* v_full = bars + 1;
-  uint64_t* qk_empty = bars + 2;
-  uint64_t* v_empty = bars + 3;
-  uint64_t* s_full = bars + 4;   // [2]
-  uint64_t* p_full = bars + 6;   // [2]
-  uint64_t* o_full = bars + 8;   // [2]
-  uint64_t* t_free = bars + 10;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* xmax = reinterpret_cast<float*>(smem + AF_OFF_X);  // [2 halves][128 rows]
+  float* xsum = xmax + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AF_OFF_BAR);
+  uint64_t* qk_full = bars + 0;   // [2]
+  uint64_t* qk_empty = bars + 2;  // [2]
+  uint64_t* v_full = bars + 4;    // [2]
+  uint64_t* v_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;    // [2] score buffers
+  uint64_t* s_free = bars + 10;   // [2]
+  uint64_t* p_full = bars + 12;
+  uint64_t* o_full = bars + 13;
+  uint64_t* o_free = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
   if (warp == 1 && lane == 0) {
-    mbar_init(qk_full, 1);
-    mbar_init(v_full, 1);
-    mbar_init(qk_empty, 1);
-    mbar_init(v_empty, 1);
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
-      mbar_init(&o_full[t], 1);
-      mbar_init(&t_free[t], 128);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qk_full[i], 1);
+      mbar_init(&qk_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], AF_NSW);
     }
+    mbar_init(p_full, AF_NSW);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, AF_NSW);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -78,6 +180,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int D = p.D;
+  const uint32_t T_O = tmem_base + 2 * AT_ROWS;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -85,129 +188,87 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const int b = item / p.H, h = item - b * p.H;
         const int row0 = b * p.N, col0 = h * AT_HD;
-        if (it > 0) mbar_wait(qk_empty, (it - 1) & 1);
-        mbar_expect_tx(qk_full, 2 * AT_TILE);
-        tma_load_2d(&tmQKV, sQ, qk_full, col0, row0);
-        tma_load_2d(&tmQKV, sK, qk_full, D + col0, row0);
-        if (it > 0) mbar_wait(v_empty, (it - 1) & 1);
-        mbar_expect_tx(v_full, AT_TILE);
-        tma_load_2d(&tmQKV, sV, v_full, 2 * D + col0, row0);
+        const int slot = it & 1;
+        if (it >= 2) mbar_wait(&qk_empty[slot], ((it >> 1) - 1) & 1);
+        mbar_expect_tx(&qk_full[slot], 2 * AT_TILE);
+        tma_load_2d(&tmQKV, smem + AF_OFF_Q + slot * AT_TILE, &qk_full[slot], col0, row0);
+        tma_load_2d(&tmQKV, smem + AF_OFF_K + slot * AT_TILE, &qk_full[slot], D + col0, row0);
+        if (it >= 2) mbar_wait(&v_empty[slot], ((it >> 1) - 1) & 1);
+        mbar_expect_tx(&v_full[slot], AT_TILE);
+        tma_load_2d(&tmQKV, smem + AF_OFF_V + slot * AT_TILE, &v_full[slot], 2 * D + col0, row0);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc_s = make_idesc_bf16(128, AT_ROWS, 0, 0);
       const uint32_t idesc_pv = make_idesc_bf16(128, AT_HD, 0, 1);
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
-      int it = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-        mbar_wait(qk_full, it & 1);
-        if (it > 0) {
-          mbar_wait(&t_free[0], (it - 1) & 1);
-          mbar_wait(&t_free[1], (it - 1) & 1);
-        }
+      const uint32_t p_lo = at_desc_lo(smem_u32(smem + AF_OFF_P), 16);
+      int n_items = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) ++n_items;
+      const int n_units = 2 * n_items;
+      auto issue_s = [&](int g) {  // S_g = Q_t K^T into score buffer g & 1
+        const int it = g >> 1, t = g & 1, slot = it & 1, sb = g & 1;
+        if (t == 0) mbar_wait(&qk_full[slot], (it >> 1) & 1);
+        if (g >= 2) mbar_wait(&s_free[sb], ((g >> 1) - 1) & 1);  // tile g-2 has been pulled into registers
         tc_fence_after();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
+        const uint32_t q_lo = at_desc_lo(smem_u32(smem + AF_OFF_Q + slot * AT_TILE) + t * 16384, 16);
+        const uint32_t k_lo = at_desc_lo(smem_u32(smem + AF_OFF_K + slot * AT_TILE), 16);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem_base + t * 256, make_smem_desc(aQ + t * 16384 + k * 32, 16, 1024),
-                        make_smem_desc(aK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-          tc_commit(&s_full[t]);
+            tc_mma_bf16(tmem_base + sb * AT_ROWS, at_desc(q_lo + 2 * k), at_desc(k_lo + 2 * k), idesc_s, k > 0 ? 1u : 0u);
+          tc_commit(&s_full[sb]);
+          if (t == 1) tc_commit(&qk_empty[slot]);
         }
-        tc_commit(qk_empty);
-        mbar_wait(v_full, it & 1);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], it & 1);
-          tc_fence_after();
-          const uint32_t aP = smem_u32(sP[t]);
+        __syncwarp();
+      };
+      issue_s(0);
+      for (int g = 0; g < n_units; ++g) {
+        if (g + 1 < n_units) issue_s(g + 1);
+        const int it = g >> 1, t = g & 1, slot = it & 1;
+        if (t == 0) mbar_wait(&v_full[slot], (it >> 1) & 1);
+        mbar_wait(p_full, g & 1);
+        if (g > 0) mbar_wait(o_free, (g - 1) & 1);  // O_{g-1} has been read out
+        tc_fence_after();
+        const uint32_t v_lo = at_desc_lo(smem_u32(smem + AF_OFF_V + slot * AT_TILE), 8192);
+        if (elect_one_sync()) {
 #pragma unroll
           for (int ks = 0; ks < AT_KSTEPS; ++ks)
-            tc_mma_bf16(tmem_base + t * 256, make_smem_desc(aP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                        make_smem_desc(aV + ks * 2048, 8192, 1024), idesc_pv, ks > 0 ? 1u : 0u);
-          tc_commit(&o_full[t]);
+            tc_mma_bf16(T_O, at_desc(p_lo + (ks >> 2) * 1024 + (ks & 3) * 2), at_desc(v_lo + ks * 128), idesc_pv,
+                        ks > 0 ? 1u : 0u);
+          tc_commit(o_full);
+          if (t == 1) tc_commit(&v_empty[slot]);
         }
-        tc_commit(v_empty);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
-    const int t = (warp - 4) >> 2;       // query tile
-    const int wq = warp & 3;             // TMEM lane quarter
-    const int r = wq * 32 + lane;        // row within the tile
-    const int q = t * 128 + r;           // query index
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + t * 256;
+    const int wq = warp & 3;          // TMEM lane quarter
+    const int hh = (warp - 4) >> 2;   // column half: 0 -> chunks 0..6, 1 -> chunks 7..12
+    const int r = wq * 32 + lane;     // row within the tile
+    const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
     const float c2 = p.scale * 1.4426950408889634f;
-    uint8_t* prow = sP[t] + r * 128;
+    const uint32_t prow_s = smem_u32(smem + AF_OFF_P + r * 128);
+    const uint32_t xs = smem_u32(xmax);
     const int sw = r & 7;
-    int it = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      const int b = item / p.H, h = item - b * p.H;
-      mbar_wait(&s_full[t], it & 1);
-      tc_fence_after();
-      // Both passes stream the 13 sixteen-column chunks of the row with the TMEM load of chunk j+1 in flight while
-      // chunk j is processed (fully unrolled: the two register buffers alternate at compile time).
-      // pass 1: row max over the valid keys
-      float m = -INFINITY;
-      {
-        uint32_t v[2][16];
-        tmem_ld16(trow, v[0]);
-#pragma unroll
-        for (int j = 0; j < AT_KSTEPS; ++j) {
-          tmem_ld_wait();
-          if (j + 1 < AT_KSTEPS) tmem_ld16(trow + (j + 1) * 16, v[(j + 1) & 1]);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float s = __uint_as_float(v[j & 1][e]);
-            if (j * 16 + e < p.N) m = fmaxf(m, s);
-          }
-        }
-      }
-      // pass 2: p = exp2((s - m) c2), row sum, bf16 P tile (K-major, 128-byte swizzle)
-      float l = 0.f;
-      const float mc = m * c2;
-      {
-        uint32_t v[2][16];
-        tmem_ld16(trow, v[0]);
-#pragma unroll
-        for (int j = 0; j < AT_KSTEPS; ++j) {
-          tmem_ld_wait();
-          if (j + 1 < AT_KSTEPS) tmem_ld16(trow + (j + 1) * 16, v[(j + 1) & 1]);
-          float pv[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float s = __uint_as_float(v[j & 1][e]);
-            pv[e] = (j * 16 + e < p.N) ? ex2_approx_ftz(fmaf(s, c2, -mc)) : 0.f;
-            l += pv[e];
-          }
-          uint4 lo, hi;
-          lo.x = pack_bf16x2(pv[0], pv[1]), lo.y = pack_bf16x2(pv[2], pv[3]);
-          lo.z = pack_bf16x2(pv[4], pv[5]), lo.w = pack_bf16x2(pv[6], pv[7]);
-          hi.x = pack_bf16x2(pv[8], pv[9]), hi.y = pack_bf16x2(pv[10], pv[11]);
-          hi.z = pack_bf16x2(pv[12], pv[13]), hi.w = pack_bf16x2(pv[14], pv[15]);
-          uint8_t* blk = prow + (j >> 2) * 16384;
-          const int ck = (j & 3) * 2;
-          *reinterpret_cast<uint4*>(blk + (((ck) ^ sw) << 4)) = lo;
-          *reinterpret_cast<uint4*>(blk + (((ck + 1) ^ sw) << 4)) = hi;
-        }
-      }
-      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async proxy
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
-      // O_t = P_t V (aliases the first 64 columns of S_t)
-      mbar_wait(&o_full[t], it & 1);
-      tc_fence_after();
-      uint32_t o[4][16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) tmem_ld16(trow + j * 16, o[j]);
+    // state of the previous tile (its output is read out one tile later, while its successor's MMAs run)
+    float m_prev = 0.f, l_prev = 1.f;
+    int item_prev = -1, t_prev = 0;
+    auto store_out = [&]() {  // O_{prev} columns hh*32 .. +31 of this lane's row
+      uint32_t o[2][16];
+      tmem_ld16(T_O + lane_sel + hh * 32, o[0]);
+      tmem_ld16(T_O + lane_sel + hh * 32 + 16, o[1]);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&t_free[t]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      const int q = t_prev * 128 + r;
       if (q < p.N) {
-        const float inv = 1.f / l;
-        bf16* dst = p.out + (static_cast<long long>(b) * p.N + q) * D + h * AT_HD;
+        const int b = item_prev / p.H, h = item_prev - b * p.H;
+        const float inv = 1.f / l_prev;
+        bf16* dst = p.out + (static_cast<long long>(b) * p.N + q) * D + h * AT_HD + hh * 32;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
           uint4 lo, hi;
           lo.x = pack_bf16x2(__uint_as_float(o[j][0]) * inv, __uint_as_float(o[j][1]) * inv);
           lo.y = pack_bf16x2(__uint_as_float(o[j][2]) * inv, __uint_as_float(o[j][3]) * inv);
@@ -220,8 +281,33 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
           *reinterpret_cast<uint4*>(dst + j * 16) = lo;
           *reinterpret_cast<uint4*>(dst + j * 16 + 8) = hi;
         }
-        if (p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.N + q] = m * p.scale + __logf(l);
+        if (hh == 0 && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.N + q] = m_prev * p.scale + __logf(l_prev);
       }
+    };
+    int g = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      for (int t = 0; t < 2; ++t, ++g) {
+        const int sb = g & 1;
+        mbar_wait(&s_full[sb], (g >> 1) & 1);
+        tc_fence_after();
+        float m, l;
+        const uint32_t tsb = tmem_base + lane_sel + sb * AT_ROWS;
+        const uint32_t o_wait = (g > 0) ? 1u : 0u;
+        if (hh == 0)
+          softmax_tile<0, NFIX>(tsb, p.N, c2, &s_free[sb], o_full, o_wait, (g - 1) & 1, xs, wq, r, lane, prow_s, sw, m, l);
+        else
+          softmax_tile<1, NFIX>(tsb, p.N, c2, &s_free[sb], o_full, o_wait, (g - 1) & 1, xs, wq, r, lane, prow_s, sw, m, l);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        if (g > 0) store_out();
+        m_prev = m, l_prev = l, item_prev = item, t_prev = t;
+      }
+    }
+    if (g > 0) {
+      mbar_wait(o_full, (g - 1) & 1);
+      tc_fence_after();
+      store_out();
     }
   }
   tc_fence_before();
@@ -233,23 +319,6 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
 }
 
 
-// --------------------------------------------------------------------------------------------
-// backward:  dV = P^T dO ; dP = dO V^T ; dS = P o (dP - delta) * scale ; dQ = dS K ; dK = dS^T Q
-//   stage A_t (query tile t): S_t = Q_t K^T, dP_t = dO_t V^T -> TMEM; dS_t (bf16, smem) ; dQ_t = dS_t K
-//   stage B_u (key tile u):   S^T_u = K_u Q^T, dP^T_u = V_u dO^T -> TMEM; P^T_u (smem) -> dV_u = P^T_u dO;
-//                             dS^T_u (kept packed in registers, then smem) -> dK_u = dS^T_u Q
-// P and dS are elementwise given the saved row log-sum-exp and delta = rowsum(dO o O), so the 208 columns
-// of a row are split across 4 warps (16 compute warps); no atomics, S and dP are recomputed once (7 GEMM
-// units instead of 5) so that nothing but the 64-KB operand buffer leaves TMEM.
-// warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 2-3 delta / lse of the NEXT item (two-deep smem ring,
-// so the global-load latency of that prologue is off the critical path: 0.486 -> 0.42 ms per layer), 4-19 compute.
-// (Issuing the next stage's score MMAs before the outputs of the previous one are drained -- outputs in separate
-// TMEM columns -- was measured SLOWER, 0.54 ms, and is not done.)
-// --------------------------------------------------------------------------------------------
-constexpr int ATB_THREADS = 640;
-constexpr int ATB_COMPUTE = 512;
-constexpr int ATB_SMEM = 4 * AT_TILE + AT_PBUF + 4 * AT_ROWS * 4 + 256 + 1024;  // lse / delta double buffered
-
 struct AttnBwdParams {
   const bf16* out;
   const bf16* dout;
@@ -259,18 +328,6 @@ struct AttnBwdParams {
   int items;
   float scale;
 };
-
-__device__ __forceinline__ void pack16_store(uint8_t* prow, int j, int sw, const float (&v)[16]) {
-  uint4 lo, hi;
-  lo.x = pack_bf16x2(v[0], v[1]), lo.y = pack_bf16x2(v[2], v[3]);
-  lo.z = pack_bf16x2(v[4], v[5]), lo.w = pack_bf16x2(v[6], v[7]);
-  hi.x = pack_bf16x2(v[8], v[9]), hi.y = pack_bf16x2(v[10], v[11]);
-  hi.z = pack_bf16x2(v[12], v[13]), hi.w = pack_bf16x2(v[14], v[15]);
-  uint8_t* blk = prow + (j >> 2) * 16384;
-  const int ck = (j & 3) * 2;
-  *reinterpret_cast<uint4*>(blk + ((ck ^ sw) << 4)) = lo;
-  *reinterpret_cast<uint4*>(blk + (((ck + 1) ^ sw) << 4)) = hi;
-}
 
 __device__ __forceinline__ void store16_bf16(bf16* dst, const uint32_t (&o)[16]) {
   uint4 lo, hi;
@@ -286,45 +343,95 @@ __device__ __forceinline__ void store16_bf16(bf16* dst, const uint32_t (&o)[16])
   *reinterpret_cast<uint4*>(dst + 8) = hi;
 }
 
-__global__ void __launch_bounds__(ATB_THREADS, 1)
-attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const AttnBwdParams p) {
+
+// --------------------------------------------------------------------------------------------
+// backward:  dV = P^T dO ; dP = dO V^T ; dS = P o (dP - delta) * scale ; dQ = dS K ; dK = dS^T Q, with no
+// recomputation: every score element is computed, exponentiated and read from TMEM exactly once.
+//
+// Rows = KEYS.  For key tile u (128 rows) and query block j (64 queries; the last block has 16) -- one "sub-unit":
+//     S^T = K_u Q_j^T ,  dP^T = V_u dO_j^T                      -> TMEM [128 x 64] each (two score sets, alternating)
+//     P^T = exp2(S^T c - lse_q) ,  dS^T = P^T (dP^T scale - delta_q scale)   (registers -> bf16 smem blocks)
+//     dV_u += P^T  dO_j          dK_u += dS^T Q_j               (A = the smem block, K-major; K = queries of j)
+//     dQ[queries of blocks j-1, j] += (dS^T blocks j-1, j)^T K_u    after every second block: the two blocks are
+//                                                 read IN PLACE as an MN-major A operand (M = queries, K = keys)
+// The compute warps hold their 16-column chunk of S^T / dP^T in registers, so a score set is free for new MMAs as soon
+// as it has been loaded; the MMA warp runs an event loop (non-blocking barrier tests): output MMAs of the oldest
+// published sub-unit and score MMAs of the next one are issued as soon as their barriers allow.  The read-outs of
+// dV_u / dK_u (per key tile) and dQ (per item) happen one sub-unit later, after that sub-unit's scores are in registers.
+//   TMEM (512 columns): score set b: S^T 128 b, dP^T 128 b + 64 | dV_u 256-319 | dK_u 320-383 | dQ 384-511
+//   smem: Q, dO double buffered across items (prefetch), K / V single (tile 0 and tile 1 halves refilled as soon
+//   as their tile is done), P^T 2 blocks, dS^T 2 blocks, lse / delta double buffered.
+// warps: 0 TMA, 1 MMA issue, 2 TMEM alloc, 2-3 delta / lse of the NEXT item, 4-19 compute (quarter = warp % 4, 16-column
+// chunk = (warp - 4) / 4).
+// --------------------------------------------------------------------------------------------
+constexpr int AB_THREADS = 640;
+constexpr int AB_NCW = 16;
+constexpr int AB_KB = 16384;  // one operand block [128 rows x 64 bf16], 128-byte swizzle
+constexpr int AB_OFF_Q = 0;
+constexpr int AB_OFF_DO = 2 * AT_TILE;
+constexpr int AB_OFF_K = 4 * AT_TILE;
+constexpr int AB_OFF_V = 5 * AT_TILE;
+constexpr int AB_OFF_P = 6 * AT_TILE;
+constexpr int AB_OFF_DS = AB_OFF_P + 2 * AB_KB;
+constexpr int AB_OFF_VEC = AB_OFF_DS + 2 * AB_KB;
+constexpr int AB_OFF_BAR = AB_OFF_VEC + 4 * AT_ROWS * 4;
+constexpr int AB_SMEM = AB_OFF_BAR + 256 + 1024;
+static_assert(AB_SMEM <= 232448, "attention backward: shared memory");
+static_assert((6 * AT_TILE) % 1024 == 0, "operand blocks must stay 1024-byte aligned");
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
+                    const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmDO,
+                    const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw_at[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_at) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + AT_TILE;
-  uint8_t* sV = smem + 2 * AT_TILE;
-  uint8_t* sdO = smem + 3 * AT_TILE;
-  uint8_t* sPB = smem + 4 * AT_TILE;
-  float* sLseAll = reinterpret_cast<float*>(smem + 4 * AT_TILE + AT_PBUF);  // [2][AT_ROWS] lse * log2(e); +inf beyond N
-  float* sDelAll = sLseAll + 2 * AT_ROWS;                                   // [2][AT_ROWS] rowsum(dO o O)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelAll + 2 * AT_ROWS);
-  uint64_t* in_full = bars + 0;
-  uint64_t* in_empty = bars + 1;
-  uint64_t* sd_full = bars + 2;
-  uint64_t* pb_full = bars + 3;
-  uint64_t* acc_full = bars + 4;
-  uint64_t* tm_free = bars + 5;
-  uint64_t* del_full = bars + 6;   // [2]
-  uint64_t* del_empty = bars + 8;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* sLseAll = reinterpret_cast<float*>(smem + AB_OFF_VEC);  // [2][AT_ROWS] lse * log2(e); +inf beyond N
+  float* sDelAll = sLseAll + 2 * AT_ROWS;                        // [2][AT_ROWS] rowsum(dO o O)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_OFF_BAR);
+  uint64_t* qdo_full = bars + 0;    // [2]
+  uint64_t* qdo_empty = bars + 2;   // [2]
+  uint64_t* kv_full = bars + 4;     // [2] key tile 0 / 1
+  uint64_t* kv_empty = bars + 6;    // [2]
+  uint64_t* sd_full = bars + 8;     // [2] score sets
+  uint64_t* sd_free = bars + 10;    // [2]
+  // [2], by sub-unit parity: the scores run two sub-units ahead, so a fast warp can publish sub-unit s+1 before a
+  // slow one has published s -- with one barrier its arrival would complete the wrong phase
+  uint64_t* pb_full = bars + 12;
+  uint64_t* dsq_done = bars + 14;
+  uint64_t* acc_full = bars + 15;
+  uint64_t* acc_free = bars + 16;
+  uint64_t* dq_full = bars + 17;
+  uint64_t* dq_free = bars + 18;
+  uint64_t* del_full = bars + 19;   // [2]
+  uint64_t* del_empty = bars + 21;  // [2]
+  uint64_t* slot_free = bars + 23;  // [2] the output MMAs of sub-unit n (readers of the P^T / dS^T blocks n & 1) are done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK0);
+    tma_prefetch_desc(&tmK1);
     tma_prefetch_desc(&tmDO);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(in_full, 1);
-    mbar_init(in_empty, 1);
-    mbar_init(sd_full, 1);
-    mbar_init(pb_full, ATB_COMPUTE);
-    mbar_init(acc_full, 1);
-    mbar_init(tm_free, ATB_COMPUTE);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&sd_full[i], 1);
+      mbar_init(&sd_free[i], AB_NCW);
+      mbar_init(&pb_full[i], AB_NCW);
+      mbar_init(&slot_free[i], 1);
       mbar_init(&del_full[i], 64);
-      mbar_init(&del_empty[i], ATB_COMPUTE);
+      mbar_init(&del_empty[i], AB_NCW);
     }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, AB_NCW);
+    mbar_init(dsq_done, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, AB_NCW);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -336,71 +443,135 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int D = p.D;
-  // TMEM columns: S 0-207 | dP 256-463; once a stage's S / dP have been consumed, dQ_t / dV_u reuse 0-63 (R2)
-  // and dK_u reuses 256-319 (RK)
-  const uint32_t R0 = tmem_base, R1 = tmem_base + 256, R2 = R0, RK = R1;
+  // score set b: S^T at 128 b, dP^T at 128 b + 64 | dV_u 256-319 | dK_u 320-383 | dQ 384-511
+  const uint32_t T_SET = tmem_base, T_DV = tmem_base + 256, T_DK = tmem_base + 320, T_DQ = tmem_base + 384;
 
   if (warp == 0) {
+    // ============================== TMA producer ==============================
     if (lane == 0) {
-      uint32_t ph = 0;
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const int b = item / p.H, h = item - b * p.H;
         const int row0 = b * p.N, col0 = h * AT_HD;
-        mbar_wait(in_empty, ph ^ 1);
-        ph ^= 1;
-        mbar_expect_tx(in_full, 4 * AT_TILE);
-        tma_load_2d(&tmQKV, sQ, in_full, col0, row0);
-        tma_load_2d(&tmQKV, sK, in_full, D + col0, row0);
-        tma_load_2d(&tmQKV, sV, in_full, 2 * D + col0, row0);
-        tma_load_2d(&tmDO, sdO, in_full, col0, row0);
+        const int slot = it & 1;
+        if (it >= 2) mbar_wait(&qdo_empty[slot], ((it >> 1) - 1) & 1);
+        mbar_expect_tx(&qdo_full[slot], 2 * AT_TILE);
+        tma_load_2d(&tmQ, smem + AB_OFF_Q + slot * AT_TILE, &qdo_full[slot], col0, row0);
+        tma_load_2d(&tmDO, smem + AB_OFF_DO + slot * AT_TILE, &qdo_full[slot], col0, row0);
+        if (it >= 1) mbar_wait(&kv_empty[0], (it - 1) & 1);
+        mbar_expect_tx(&kv_full[0], 2 * AB_KB);
+        tma_load_2d(&tmK0, smem + AB_OFF_K, &kv_full[0], D + col0, row0);
+        tma_load_2d(&tmK0, smem + AB_OFF_V, &kv_full[0], 2 * D + col0, row0);
+        if (it >= 1) mbar_wait(&kv_empty[1], (it - 1) & 1);
+        mbar_expect_tx(&kv_full[1], 2 * (AT_TILE - AB_KB));
+        tma_load_2d(&tmK1, smem + AB_OFF_K + AB_KB, &kv_full[1], D + col0, row0 + 128);
+        tma_load_2d(&tmK1, smem + AB_OFF_V + AB_KB, &kv_full[1], 2 * D + col0, row0 + 128);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, AT_ROWS, 0, 0);   // [128 x 208] = A(K-major) B(K-major)^T
-      const uint32_t idesc_o = make_idesc_bf16(128, AT_HD, 0, 1);     // [128 x 64]  = A(K-major) B(MN-major)
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aO = smem_u32(sdO), aP = smem_u32(sPB);
-      uint32_t ph_in = 0, ph_tm = 0, ph_pb = 0;
-      auto mma_scores = [&](uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(R0, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024), idesc_s,
-                      k > 0 ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(R1, make_smem_desc(a1 + k * 32, 16, 1024), make_smem_desc(b1 + k * 32, 16, 1024), idesc_s,
-                      k > 0 ? 1u : 0u);
-        tc_commit(sd_full);
+    // ============================== MMA issuer ==============================
+    {
+      const uint32_t idesc_s64 = make_idesc_bf16(128, 64, 0, 0);   // scores: A (keys) K-major, B (queries) K-major
+      const uint32_t idesc_s16 = make_idesc_bf16(128, 16, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, AT_HD, 0, 1);   // dV / dK: A K-major (queries), B MN-major
+      const uint32_t idesc_q = make_idesc_bf16(128, AT_HD, 1, 1);   // dQ: A MN-major (dS^T blocks), B MN-major (K_u)
+      const uint32_t aK = smem_u32(smem + AB_OFF_K), aV = smem_u32(smem + AB_OFF_V);
+      const uint32_t aP = smem_u32(smem + AB_OFF_P), aDS = smem_u32(smem + AB_OFF_DS);
+      const uint32_t ds_mn_lo = at_desc_lo(aDS, AB_KB);  // both dS^T blocks as one MN-major A operand (atoms AB_KB apart)
+      int n_items = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) ++n_items;
+      const int total = 8 * n_items;  // sub-unit n: item n >> 3, key tile (n >> 2) & 1, query block n & 3
+      int n_sub = 0;                  // sub-units whose scores have been issued (into score set n_sub & 1)
+      int n_out = 0;                  // sub-units whose output MMAs have been issued
+      // non-blocking barrier test by lane 0, broadcast: the control flow stays warp-uniform
+      auto ready = [&](uint64_t* bar, uint32_t parity) -> bool {
+        uint32_t ok = 0;
+        if (lane == 0) ok = mbar_try_wait(bar, parity) ? 1u : 0u;
+        return __shfl_sync(0xffffffffu, ok, 0) != 0;
       };
-      auto mma_out = [&](uint32_t dst, uint32_t bmn) {  // dst[128 x 64] = PB[128 x 208] * B[208 x 64]
-        mbar_wait(pb_full, ph_pb);
-        ph_pb ^= 1;
+      auto issue_scores = [&](int n) {
+        const int it = n >> 3, u = (n >> 2) & 1, j = n & 3, slot = it & 1, set = n & 1;
         tc_fence_after();
+        const uint32_t idesc = j < 3 ? idesc_s64 : idesc_s16;
+        const uint32_t k_lo = at_desc_lo(aK + u * AB_KB, 16), v_lo = at_desc_lo(aV + u * AB_KB, 16);
+        const uint32_t q_lo = at_desc_lo(smem_u32(smem + AB_OFF_Q + slot * AT_TILE) + j * 8192, 16);
+        const uint32_t o_lo = at_desc_lo(smem_u32(smem + AB_OFF_DO + slot * AT_TILE) + j * 8192, 16);
+        const uint32_t ts = T_SET + set * 128;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int ks = 0; ks < AT_KSTEPS; ++ks)
-          tc_mma_bf16(dst, make_smem_desc(aP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                      make_smem_desc(bmn + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
-        tc_commit(acc_full);
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(ts, at_desc(k_lo + 2 * k), at_desc(q_lo + 2 * k), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(ts + 64, at_desc(v_lo + 2 * k), at_desc(o_lo + 2 * k), idesc, k > 0 ? 1u : 0u);
+          tc_commit(&sd_full[set]);
+        }
+        __syncwarp();
       };
-      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-        mbar_wait(in_full, ph_in);
-        ph_in ^= 1;
-        for (int t = 0; t < 2; ++t) {  // stage A_t
-          mbar_wait(tm_free, ph_tm ^ 1);
-          ph_tm ^= 1;
-          tc_fence_after();
-          mma_scores(aQ + t * 16384, aK, aO + t * 16384, aV);
-          mma_out(R2, aK);  // dQ_t = dS_t K
+      auto issue_out = [&](int n) {
+        const int it = n >> 3, u = (n >> 2) & 1, j = n & 3, slot = it & 1;
+        tc_fence_after();
+        const uint32_t kmn_lo = at_desc_lo(aK + u * AB_KB, 8192);
+        const uint32_t omn_lo = at_desc_lo(smem_u32(smem + AB_OFF_DO + slot * AT_TILE) + j * 8192, 8192);
+        const uint32_t qmn_lo = at_desc_lo(smem_u32(smem + AB_OFF_Q + slot * AT_TILE) + j * 8192, 8192);
+        const uint32_t pb_lo = at_desc_lo(aP + (n & 1) * AB_KB, 16);
+        const uint32_t db_lo = at_desc_lo(aDS + (n & 1) * AB_KB, 16);
+        if (elect_one_sync()) {
+          if (j & 1) {  // dQ[tile m] (+)= (dS^T blocks j-1, j)^T K_u : M = 128 queries, K = 128 keys
+            const uint32_t dq = T_DQ + (j >> 1) * 64;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              tc_mma_bf16(dq, at_desc(ds_mn_lo + kk * 128), at_desc(kmn_lo + kk * 128), idesc_q, (u > 0 || kk > 0) ? 1u : 0u);
+            tc_commit(dsq_done);
+          }
+          if (j < 3) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma_bf16(T_DV, at_desc(pb_lo + 2 * kk), at_desc(omn_lo + kk * 128), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              tc_mma_bf16(T_DK, at_desc(db_lo + 2 * kk), at_desc(qmn_lo + kk * 128), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          } else {  // the last query block holds 16 queries: one k-step
+            tc_mma_bf16(T_DV, at_desc(pb_lo), at_desc(omn_lo), idesc_o, 1u);
+            tc_mma_bf16(T_DK, at_desc(db_lo), at_desc(qmn_lo), idesc_o, 1u);
+            tc_commit(acc_full);
+            tc_commit(&kv_empty[u]);
+            if (u == 1) {
+              tc_commit(dq_full);
+              tc_commit(&qdo_empty[slot]);
+            }
+          }
+          tc_commit(&slot_free[n & 1]);
         }
-        for (int u = 0; u < 2; ++u) {  // stage B_u
-          mbar_wait(tm_free, ph_tm ^ 1);
-          ph_tm ^= 1;
-          tc_fence_after();
-          mma_scores(aK + u * 16384, aQ, aV + u * 16384, aO);
-          mma_out(R2, aO);  // dV_u = P^T_u dO
-          mma_out(RK, aQ);  // dK_u = dS^T_u Q
+        __syncwarp();
+      };
+      // Event loop: whichever is possible next -- the output MMAs of the oldest published sub-unit (they unblock the
+      // compute warps' next block writes and the dQ chain) or the scores of the next sub-unit (at most two score
+      // sets in flight) -- is issued as soon as its barriers allow; nothing is waited for in a fixed order.
+      while (n_out < total) {
+        bool progressed = false;
+        if (n_out < n_sub) {
+          const int n = n_out, it = n >> 3, u = (n >> 2) & 1, j = n & 3;
+          bool ok = ready(&pb_full[n & 1], (n >> 1) & 1);
+          if (ok && u == 0 && j == 1 && it > 0) ok = ready(dq_free, (it - 1) & 1);  // previous item's dQ read out
+          if (ok && j == 0 && n >= 4) ok = ready(acc_free, ((n >> 2) - 1) & 1);      // previous key tile read out
+          if (ok) {
+            issue_out(n);
+            ++n_out;
+            progressed = true;
+          }
         }
-        tc_commit(in_empty);
+        if (n_sub < total) {  // bounded by the two score sets: sub-unit n_sub - 2 must be in registers
+          const int n = n_sub, it = n >> 3, u = (n >> 2) & 1, j = n & 3;
+          bool ok = true;
+          if (j == 0 && u == 0) ok = ready(&qdo_full[it & 1], (it >> 1) & 1);
+          if (ok && j == 0) ok = ready(&kv_full[u], it & 1);
+          if (ok && n >= 2) ok = ready(&sd_free[n & 1], ((n >> 1) - 1) & 1);  // sub-unit n-2 is in registers
+          if (ok) {
+            issue_scores(n);
+            ++n_sub;
+            progressed = true;
+          }
+        }
+        (void)progressed;
       }
     }
   } else if (warp == 2 || warp == 3) {
@@ -439,7 +610,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         if (wi < 2 * AT_ROWS && half == 0) {
-          sDel[row] = acc;
+          sDel[row] = acc * p.scale;  // pre-scaled: dS = p (dp scale - delta scale)
           sLse[row] = row < p.N ? p.lse[(static_cast<long long>(b) * p.H + h) * p.N + row] * 1.4426950408889634f
                                 : INFINITY;
         }
@@ -448,134 +619,148 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       buf ^= 1;
       if (buf == 0) ph ^= 1;
     }
-  } else if (warp >= 4) {
+  } else {
+    // ============================== compute warps ==============================
     const int cw = warp - 4;
-    const int wq = cw & 3;   // TMEM lane quarter (== warp % 4)
-    const int cg = cw >> 2;  // column group: 16-column chunks j with (j & 3) == cg
+    const int wq = cw & 3;  // TMEM lane quarter (== warp % 4)
+    const int cg = cw >> 2; // 16-column chunk of the 64-column block
     const int r = wq * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(wq * 32) << 16;
     const float c2 = p.scale * 1.4426950408889634f;
-    uint8_t* prow = sPB + r * 128;
+    uint8_t* prow_p = smem + AB_OFF_P + r * 128;
+    uint8_t* prow_d = smem + AB_OFF_DS + r * 128;
     const int sw = r & 7;
-    uint32_t ph_sd = 0, ph_acc = 0, dph = 0;
+    uint32_t dph = 0;
     int dbuf = 0;
-    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
-      const int b = item / p.H, h = item - b * p.H;
-      // lse / delta of this item were produced by warps 2-3 while the previous item ran
-      mbar_wait(&del_full[dbuf], dph);
-      const float* sLse = sLseAll + dbuf * AT_ROWS;
-      const float* sDel = sDelAll + dbuf * AT_ROWS;
-
-      // ---------------- stage A_t : rows = queries, columns = keys ----------------
-      for (int t = 0; t < 2; ++t) {
-        const int q = t * 128 + r;
-        const bool qok = q < p.N;
-        const float lse_r = qok ? sLse[q] : INFINITY;
-        const float del_r = qok ? sDel[q] : 0.f;
-        mbar_wait(sd_full, ph_sd);
-        ph_sd ^= 1;
-        tc_fence_after();
-#pragma unroll 1
-        for (int j = cg; j < AT_KSTEPS; j += 4) {
-          uint32_t s[16], dp[16];
-          tmem_ld16(R0 + lane_sel + j * 16, s);
-          tmem_ld16(R1 + lane_sel + j * 16, dp);
-          tmem_ld_wait();
-          float ds[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float pe = ex2_approx_ftz(fmaf(__uint_as_float(s[e]), c2, -lse_r));
-            const float v = pe * (__uint_as_float(dp[e]) - del_r) * p.scale;
-            ds[e] = (qok && (j * 16 + e < p.N)) ? v : 0.f;
-          }
-          pack16_store(prow, j, sw, ds);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(pb_full);
-        // dQ_t
-        mbar_wait(acc_full, ph_acc);
-        ph_acc ^= 1;
-        tc_fence_after();
-        uint32_t o[16];
-        tmem_ld16(R2 + lane_sel + cg * 16, o);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(tm_free);
-        if (qok) store16_bf16(p.dqkv + (static_cast<long long>(b) * p.N + q) * 3 * D + h * AT_HD + cg * 16, o);
+    int n_sub = 0;
+    // read-outs: dV_u / dK_u of a finished key tile, dQ of a finished item
+    auto drain_acc = [&](int u, int ditem, uint32_t parity) {
+      mbar_wait(acc_full, parity);
+      tc_fence_after();
+      uint32_t ov[16], ok_[16];
+      tmem_ld16(T_DV + lane_sel + cg * 16, ov);
+      tmem_ld16(T_DK + lane_sel + cg * 16, ok_);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
+      const int b = ditem / p.H, h = ditem - b * p.H;
+      const int key = u * 128 + r;
+      if (key < p.N) {
+        bf16* base = p.dqkv + (static_cast<long long>(b) * p.N + key) * 3 * D + h * AT_HD + cg * 16;
+        store16_bf16(base + D, ok_);
+        store16_bf16(base + 2 * D, ov);
       }
-      // ---------------- stage B_u : rows = keys, columns = queries ----------------
+    };
+    auto drain_dq = [&](int ditem, uint32_t parity) {
+      mbar_wait(dq_full, parity);
+      tc_fence_after();
+      uint32_t o0[16], o1[16];
+      tmem_ld16(T_DQ + lane_sel + cg * 16, o0);
+      tmem_ld16(T_DQ + 64 + lane_sel + cg * 16, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
+      const int b = ditem / p.H, h = ditem - b * p.H;
+      bf16* base = p.dqkv + static_cast<long long>(b) * p.N * 3 * D + h * AT_HD + cg * 16;
+      if (r < p.N) store16_bf16(base + static_cast<long long>(r) * 3 * D, o0);
+      if (128 + r < p.N) store16_bf16(base + static_cast<long long>(128 + r) * 3 * D, o1);
+    };
+    const float sc = p.scale;
+    int it = 0, prev_item = -1;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      mbar_wait(&del_full[dbuf], dph);
+      const uint32_t sLse = smem_u32(sLseAll + dbuf * AT_ROWS);
+      const uint32_t sDel = smem_u32(sDelAll + dbuf * AT_ROWS);
       for (int u = 0; u < 2; ++u) {
-        const int key = u * 128 + r;
-        mbar_wait(sd_full, ph_sd);
-        ph_sd ^= 1;
-        tc_fence_after();
-        uint32_t dsp[4][8];  // dS^T of this thread's chunks, packed bf16
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = cg + 4 * jj;
-          if (j < AT_KSTEPS) {
-            uint32_t s[16], dp[16];
-            tmem_ld16(R0 + lane_sel + j * 16, s);
-            tmem_ld16(R1 + lane_sel + j * 16, dp);
+        const bool kvalid = (u * 128 + r) < p.N;
+        const bool rows_ok = __all_sync(0xffffffffu, kvalid);
+        for (int j = 0; j < 4; ++j, ++n_sub) {
+          const int set = n_sub & 1;
+          mbar_wait(&sd_full[set], (n_sub >> 1) & 1);
+          tc_fence_after();
+          const bool active = (j < 3) || (cg == 0);
+          uint32_t s[16], dp[16];
+          if (active) {
+            const uint32_t ts = T_SET + set * 128 + lane_sel + cg * 16;
+            tmem_ld16(ts, s);
+            tmem_ld16(ts + 64, dp);
             tmem_ld_wait();
-            float pt[16];
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sd_free[set]);
+          // the outputs of the key tile (item) that finished one sub-unit ago: their last MMAs were issued when that
+          // sub-unit's operands were published, they are complete (or nearly) by now, and the score registers of
+          // this sub-unit are already loaded -- the read-out costs no waiting
+          if (j == 0) {
+            if (u == 1) {
+              drain_acc(0, item, 0u);  // key tile 2 it: even
+            } else if (it > 0) {
+              drain_acc(1, prev_item, 1u);
+              drain_dq(prev_item, (it - 1) & 1);
+            }
+          }
+          uint32_t pkp[8], pkd[8];  // P^T / dS^T of this thread's 16 columns, packed bf16
+          const int q0 = j * 64 + cg * 16;
+          if (active) {
+            const bool mask = !rows_ok || j == 3;  // padding keys (rows) / padding queries (columns): exact zeros
+            // p = exp2(s c - lse), dS = p (dp scale - delta scale): 4 instructions per element (+ bf16 packing)
 #pragma unroll
             for (int e4 = 0; e4 < 4; ++e4) {
-              const float4 l4 = *reinterpret_cast<const float4*>(sLse + j * 16 + e4 * 4);
-              const float4 d4 = *reinterpret_cast<const float4*>(sDel + j * 16 + e4 * 4);
-              const float ls[4] = {l4.x, l4.y, l4.z, l4.w};
-              const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-              float dsv[4];
+              const int qq = q0 + e4 * 4;
+              const uint4 l4 = lds128(sLse + qq * 4);
+              const uint4 d4 = lds128(sDel + qq * 4);
+              const float ls[4] = {__uint_as_float(l4.x), __uint_as_float(l4.y), __uint_as_float(l4.z), __uint_as_float(l4.w)};
+              const float dl[4] = {__uint_as_float(d4.x), __uint_as_float(d4.y), __uint_as_float(d4.z), __uint_as_float(d4.w)};
+              float pe[4], de[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int col = e4 * 4 + e;
-                const bool cok = (j * 16 + col) < p.N;
-                const float pe = cok ? ex2_approx_ftz(fmaf(__uint_as_float(s[col]), c2, -ls[e])) : 0.f;
-                pt[col] = pe;
-                dsv[e] = cok ? pe * (__uint_as_float(dp[col]) - dl[e]) * p.scale : 0.f;
+                pe[e] = ex2_approx_ftz(fmaf(__uint_as_float(s[col]), c2, -ls[e]));  // lse = +inf beyond N: 0
+                de[e] = pe[e] * fmaf(__uint_as_float(dp[col]), sc, -dl[e]);
               }
-              dsp[jj][e4 * 2] = pack_bf16x2(dsv[0], dsv[1]);
-              dsp[jj][e4 * 2 + 1] = pack_bf16x2(dsv[2], dsv[3]);
-            }
-            pack16_store(prow, j, sw, pt);
-          }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(pb_full);  // P^T_u ready -> dV_u
-        mbar_wait(acc_full, ph_acc);
-        ph_acc ^= 1;  // dV_u done: the operand buffer may be overwritten
+              if (mask) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = cg + 4 * jj;
-          if (j < AT_KSTEPS) {
-            uint8_t* blk = prow + (j >> 2) * 16384;
-            const int ck = (j & 3) * 2;
-            *reinterpret_cast<uint4*>(blk + ((ck ^ sw) << 4)) = make_uint4(dsp[jj][0], dsp[jj][1], dsp[jj][2], dsp[jj][3]);
-            *reinterpret_cast<uint4*>(blk + (((ck + 1) ^ sw) << 4)) = make_uint4(dsp[jj][4], dsp[jj][5], dsp[jj][6], dsp[jj][7]);
+                for (int e = 0; e < 4; ++e) {
+                  const bool ok = kvalid && (qq + e) < p.N;
+                  pe[e] = ok ? pe[e] : 0.f;
+                  de[e] = ok ? de[e] : 0.f;
+                }
+              }
+              pkp[2 * e4] = pack_bf16x2(pe[0], pe[1]), pkp[2 * e4 + 1] = pack_bf16x2(pe[2], pe[3]);
+              pkd[2 * e4] = pack_bf16x2(de[0], de[1]), pkd[2 * e4 + 1] = pack_bf16x2(de[2], de[3]);
+            }
           }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(pb_full);  // dS^T_u ready -> dK_u
-        mbar_wait(acc_full, ph_acc);
-        ph_acc ^= 1;
-        tc_fence_after();
-        uint32_t ov[16], ok_[16];
-        tmem_ld16(R2 + lane_sel + cg * 16, ov);
-        tmem_ld16(RK + lane_sel + cg * 16, ok_);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(tm_free);
-        if (key < p.N) {
-          bf16* base = p.dqkv + (static_cast<long long>(b) * p.N + key) * 3 * D + h * AT_HD + cg * 16;
-          store16_bf16(base + D, ok_);
-          store16_bf16(base + 2 * D, ov);
+          // dS^T blocks are also the A operand of the dQ MMAs issued after every odd block: the block written at
+          // an even j was last read by the group issued after j-1, which is NOT ordered before this block's score
+          // MMAs -> wait for it explicitly, after the math (odd j: ordered by the score commit)
+          if ((j & 1) == 0 && n_sub >= 2) mbar_wait(dsq_done, ((n_sub >> 1) - 1) & 1);  // group of sub-unit n_sub - 1
+          // the blocks of this parity were last read by the output MMAs of sub-unit n_sub - 2
+          if (n_sub >= 2) mbar_wait(&slot_free[set], ((n_sub >> 1) - 1) & 1);
+          if (active) {
+            const uint32_t bp = smem_u32(prow_p) + set * AB_KB, bd = smem_u32(prow_d) + set * AB_KB;
+            const int ck = cg * 2;
+            sts128(bp + ((ck ^ sw) << 4), pkp[0], pkp[1], pkp[2], pkp[3]);
+            sts128(bp + (((ck + 1) ^ sw) << 4), pkp[4], pkp[5], pkp[6], pkp[7]);
+            sts128(bd + ((ck ^ sw) << 4), pkd[0], pkd[1], pkd[2], pkd[3]);
+            sts128(bd + (((ck + 1) ^ sw) << 4), pkd[4], pkd[5], pkd[6], pkd[7]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pb_full[set]);
         }
       }
-      mbar_arrive(&del_empty[dbuf]);  // this thread no longer reads the item's lse / delta
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&del_empty[dbuf]);
       dbuf ^= 1;
       if (dbuf == 0) dph ^= 1;
+      prev_item = item;
+    }
+    if (prev_item >= 0) {
+      drain_acc(1, prev_item, 1u);
+      drain_dq(prev_item, (it - 1) & 1);
     }
   }
   tc_fence_before();
@@ -590,10 +775,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
 using namespace theia;
 
-static int encode_qkv_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols) {
+static int encode_qkv_map(CUtensorMap* tm, const void* ptr, long long rows, long long cols, int box_rows = AT_ROWS) {
   uint64_t dims[2] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows)};
   uint64_t strides[1] = {static_cast<uint64_t>(cols) * 2};
-  uint32_t box[2] = {64, AT_ROWS};
+  uint32_t box[2] = {64, static_cast<uint32_t>(box_rows)};
   return encode_tensor_map(tm, ptr, 2, dims, strides, box);
 }
 
@@ -603,12 +788,6 @@ extern "C" int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, in
   CUtensorMap tm;
   int rc = encode_qkv_map(&tm, qkv, static_cast<long long>(B) * N, 3LL * D);
   if (rc) return rc;
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATF_SMEM);
-    if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc fwd attr: %s", cudaGetErrorString(e));
-    done = true;
-  }
   AttnFwdParams p;
   p.out = static_cast<bf16*>(out);
   p.lse = lse;
@@ -616,9 +795,20 @@ extern "C" int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, in
   p.items = B * H;
   p.scale = 0.125f;
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  attn_tc_fwd_kernel<<<grid, ATF_THREADS, ATF_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
-  THEIA_CHECK_LAUNCH("attention_tc_fwd");
-  return THEIA_OK;
+  {
+    static bool done2 = false;
+    if (!done2) {
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd2_kernel<197>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM);
+      if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc fwd2 attr: %s", cudaGetErrorString(e));
+      done2 = true;
+    }
+    // 197 tokens (DeiT: CLS + 196 patches) gets the compile-time sequence length; DeiTNoCLS / DeiTReg run the generic one
+    if (N == 197) attn_tc_fwd2_kernel<197><<<grid, AF_THREADS, AF_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
+    else attn_tc_fwd2_kernel<0><<<grid, AF_THREADS, AF_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
+    THEIA_CHECK_LAUNCH("attention_tc_fwd2");
+    return THEIA_OK;
+  }
 }
 
 extern "C" int theia_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
@@ -630,12 +820,6 @@ extern "C" int theia_attention_tc_bwd(const void* qkv, const void* out, const vo
   if (rc) return rc;
   rc = encode_qkv_map(&tmd, dout, static_cast<long long>(B) * N, D);
   if (rc) return rc;
-  static bool done = false;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATB_SMEM);
-    if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc bwd attr: %s", cudaGetErrorString(e));
-    done = true;
-  }
   AttnBwdParams p;
   p.out = static_cast<const bf16*>(out);
   p.dout = static_cast<const bf16*>(dout);
@@ -645,7 +829,20 @@ extern "C" int theia_attention_tc_bwd(const void* qkv, const void* out, const vo
   p.items = B * H;
   p.scale = 0.125f;
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  attn_tc_bwd_kernel<<<grid, ATB_THREADS, ATB_SMEM, static_cast<cudaStream_t>(stream)>>>(tmq, tmd, p);
-  THEIA_CHECK_LAUNCH("attention_tc_bwd");
-  return THEIA_OK;
+  {
+    CUtensorMap tmk0, tmk1;
+    rc = encode_qkv_map(&tmk0, qkv, static_cast<long long>(B) * N, 3LL * D, 128);
+    if (rc) return rc;
+    rc = encode_qkv_map(&tmk1, qkv, static_cast<long long>(B) * N, 3LL * D, AT_ROWS - 128);
+    if (rc) return rc;
+    static bool done2 = false;
+    if (!done2) {
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+      if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc bwd2 attr: %s", cudaGetErrorString(e));
+      done2 = true;
+    }
+    attn_tc_bwd2_kernel<<<grid, AB_THREADS, AB_SMEM, static_cast<cudaStream_t>(stream)>>>(tmq, tmk0, tmk1, tmd, p);
+    THEIA_CHECK_LAUNCH("attention_tc_bwd2");
+    return THEIA_OK;
+  }
 }

@@ -578,7 +578,7 @@ __constant__ ResizeTable c_rt;
 
 __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int NT, int P0,
                                                                 int B, int chw, float s0, float s1, float s2, float o0,
-                                                                float o1, float o2) {
+                                                                float o1, float o2, uint8_t* __restrict__ dbg_u8) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * NT * 96;
   if (t >= total) return;
@@ -616,6 +616,9 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* _
       }
       acc = rintf(fminf(fmaxf(acc, 0.f), 255.f));
       o[e] = (acc - of) * sc;
+      // test hook: the resized + centre-cropped uint8 image [B,224,224,3] the reference's processor produces
+      if (dbg_u8 != nullptr)
+        dbg_u8[((static_cast<long long>(b) * 224 + (py * 16 + i)) * 224 + (px * 16 + j + e)) * 3 + c] = static_cast<uint8_t>(acc);
     }
   }
   store8(out + row * 768 + k8 * 8, o);
@@ -1048,6 +1051,14 @@ static int upload_resize_table() {
   return 0;
 }
 
+static uint8_t* g_resize_dbg_u8 = nullptr;
+// Test hook: when set, the next theia_preprocess(do_resize=1) calls also write the resized + centre-cropped uint8
+// image [B,224,224,3] (the byte stage of the reference's processor) to this device buffer.  NULL switches it off.
+extern "C" int theia_preprocess_debug_u8(void* resized_u8_out) {
+  g_resize_dbg_u8 = static_cast<uint8_t*>(resized_u8_out);
+  return THEIA_OK;
+}
+
 extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_resize,
                                 int do_rescale, int do_normalize, const float* mean3, const float* std3, int tokens,
                                 int patch_off, void* stream) {
@@ -1072,7 +1083,7 @@ extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int
     if (rc) return rc;
     preprocess_resize_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), tokens, patch_off, B,
                                                           channels_first,
-                                                          sc[0], sc[1], sc[2], of[0], of[1], of[2]);
+                                                          sc[0], sc[1], sc[2], of[0], of[1], of[2], g_resize_dbg_u8);
   } else {
     preprocess_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), tokens, patch_off, B,
                                                    channels_first, sc[0],

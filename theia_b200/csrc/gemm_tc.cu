@@ -193,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    {  // whole warp, elected lane issues (uniform operands stay in uniform registers; see the MMA issuer)
       int stage = 0;
       uint32_t phase = 0;
       int filled = 0;
@@ -204,11 +204,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           if ((p.dbg & 1) && filled >= C::STAGES) {  // diagnostic: MMA rate without operand traffic
-            if (cta_rank == 0) mbar_arrive(&full[stage]);
+            if (cta_rank == 0 && lane == 0) mbar_arrive(&full[stage]);
+            __syncwarp();
             if (++stage == C::STAGES) stage = 0, phase ^= 1;
             continue;
           }
           ++filled;
+          if (elect_one_sync()) {
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           // both CTAs of a pair complete their bytes on the LEADER's barrier, which expects the sum
@@ -243,6 +245,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d_g<PAIR>(&tmB, sb + i * 8192, fb, n0 + 64 * i, p.dw[it.z],
                                   p.es * hb * p.rows_per_kb + p.dh[it.z], b);
           }
+          }  // elected lane
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -252,11 +256,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0 && cta_rank == 0) {
+    // The WHOLE warp runs this loop (warp-uniform control flow, every value below is uniform), one elected lane
+    // issues: the compiler then keeps the descriptors in uniform registers.  With `if (lane == 0)` around the loop
+    // it could not prove uniformity and wrapped every tcgen05.mma in an ELECT / R2UR broadcast loop plus the full
+    // 64-bit descriptor arithmetic -- ~35 SASS instructions per MMA on ONE thread, as long as the 64-cycle
+    // execution of a 128 x 256 x 16 MMA (r2 ncu source view).  The descriptor's high word is constant and the low
+    // word (address >> 4 | LBO << 16) only advances by constants: two 32-bit adds per MMA.
+    if (cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t smem0 = smem_u32(smem);
+      const uint32_t a_hi = ((p.a_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t b_hi = ((p.b_sbo >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = ((smem0 >> 4) & 0x3FFFu) | (((p.a_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t b_lo0 = (((smem0 + A_BYTES) >> 4) & 0x3FFFu) | (((p.b_lbo >> 4) & 0x3FFFu) << 16);
+      const uint32_t a_step = p.a_kstep >> 4, b_step = p.b_kstep >> 4;
+      constexpr uint32_t STAGE16 = C::STAGE_BYTES >> 4;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
       for (int item = unit0; item < p.total_items; item += nunits) {
         const Item it = decode_item(p, item);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -265,21 +283,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * p.a_kstep, p.a_lbo, p.a_sbo);
-            const uint64_t db = make_smem_desc(b_addr + k * p.b_kstep, p.b_lbo, p.b_sbo);
-            tc_mma_bf16_g<PAIR>(d_tmem, da, db, p.idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * a_step);
+              const uint64_t db = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * b_step);
+              tc_mma_bf16_g<PAIR>(d_tmem, da, db, p.idesc, (kb > it.kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_g<PAIR>(&empty[stage]);  // smem slot (of both CTAs) reusable once these MMAs have read it
           }
-          tc_commit_g<PAIR>(&empty[stage]);  // smem slot (of both CTAs) reusable once these MMAs have read it
+          __syncwarp();
+          a_lo += STAGE16, b_lo += STAGE16;
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
+            a_lo = a_lo0, b_lo = b_lo0;
           }
         }
-        tc_commit_g<PAIR>(&tfull[acc]);  // accumulator complete (each CTA drains its own 128 TMEM lanes)
+        if (elect_one_sync()) tc_commit_g<PAIR>(&tfull[acc]);  // accumulator complete (each CTA drains its own 128 TMEM lanes)
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -700,7 +722,8 @@ int theia::gemm_pair_mode(int bn, int m_tiles, int a_mode) {
   // measured (r01, B200): the pair wins 2-14 % on every 2-D operand shape of the step, but loses ~8 % on the
   // implicit-GEMM convolutions whose A operand is the 4-D TMA gather -- the two gathers of a pair have to
   // finish in lockstep -- so those keep the single-CTA kernel
-  if (a_mode == THEIA_OP_CONV_K && g_dbg[8] != 2) return 1;
+  static const bool env_pair_conv = getenv("THEIA_GEMM_PAIR_CONV") != nullptr;  // A/B switch for tuning runs
+  if (a_mode == THEIA_OP_CONV_K && g_dbg[8] != 2 && !env_pair_conv) return 1;
   return (bn == 256 && m_tiles >= 2 && g_dbg[8] != 1 && !env_single) ? 2 : 1;
 }
 

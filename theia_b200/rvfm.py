@@ -153,8 +153,8 @@ class RobotVisionFM(nn.Module):
             hsf = float(dict(translator_kwargs).get("hidden_size_factor", 1.0))
         if hsf != 1.0:
             raise NotImplementedError("only hidden_size_factor 1.0 (configs/model/translator/lconv.yaml:3)")
-        if image_size != 224:
-            raise NotImplementedError("only 224x224 inputs (interpolate_pos_encoding is not built)")
+        # `image_size` is stored, not used to build the model: the reference's DeiT wrapper does the same
+        # (backbones.py:267-285 always instantiates the 224-pixel hub config)
         self.target_feature_sizes = target_feature_sizes
         self.preprocessor = None
         self.pretrained = pretrained
@@ -397,8 +397,9 @@ class RobotVisionFM(nn.Module):
 
     def _run_backbone(self, x, kw, run_heads: bool, names, tokens_out=None):
         do_resize = kw.get("do_resize", True)
-        if kw.get("interpolate_pos_encoding"):
-            raise NotImplementedError("interpolate_pos_encoding is not built yet")
+        # interpolate_pos_encoding=True is the identity for 224x224 inputs (hf:modeling_vit.py:74-76 returns the
+        # stored table when the patch grid matches); other input sizes are rejected in _prep_images like the
+        # reference rejects them without the flag (hf:modeling_vit.py:160-165)
         images, chw = self._prep_images(x, do_resize)
         B = images.shape[0]
         self._ensure(B)
