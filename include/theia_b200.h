@@ -128,9 +128,11 @@ int theia_ln3d_bwd(const void* dy, const void* x, const float* stats, const floa
 /* Loss terms of one teacher (src/theia/models/rvfm.py:153-176): acc scratch [B][5]; out3 = {mse, cos, l1} */
 int theia_loss_fwd(const float* pred, const void* target, int target_is_bf16, float* acc, float* out3, int B, int n,
                    void* stream);
-/* dpred (bf16 or fp32) = coef3[0]*d(mse)/dp + coef3[1]*d(cos)/dp + coef3[2]*d(l1)/dp ; coef3 lives on the device */
+/* dpred (bf16 or fp32) = coef3[0]*d(mse)/dp + coef3[1]*d(cos)/dp + coef3[2]*d(l1)/dp ; coef3 lives on the device.
+ * dpred_bf16_copy (optional, with an fp32 dpred): a bf16 copy written in the same pass (the operand of the head-Linear
+ * backward GEMMs; saves a separate cast over the largest tensor of the loss path) */
 int theia_loss_bwd(const float* pred, const void* target, int target_is_bf16, const float* acc, const float* coef3,
-                   void* dpred, int dpred_is_f32, int B, int n, void* stream);
+                   void* dpred, int dpred_is_f32, void* dpred_bf16_copy, int B, int n, void* stream);
 /* DeiT image processor (backbones.py:337-339; hf:image_processing_backends.py:361-414): uint8 HWC/CHW
  * 224x224 -> [bicubic-antialias resize to 256 + centre crop 224 when do_resize] -> rescale/normalise ->
  * bf16 patch rows [B*197, 768] (row b*197 is the zero CLS slot; column = c*256 + i*16 + j) */
@@ -160,6 +162,19 @@ int theia_adamw_flat(float* p, const float* g, float* m, float* v, const uint8_t
                      float* scratch2, const int* pack_table, void* packbf, void* stream);
 /* bf16 copies of all blocks the pack table names (one launch; what theia_adamw_flat fuses) */
 int theia_pack_cast(const float* p, const int* pack_table, void* packbf, long long n, void* stream);
+/* Conv-weight layout conversions through shared-memory tiles (coalesced on both sides), one launch for all conv
+ * weights.  Reference layout W[a][b][9] (Conv2d: a = Cout, b = Cin; ConvTranspose2d: a = Cin, b = Cout) <-> GEMM
+ * packs P[X][T][Y] (or tap-major P[T][X][Y]) with (X, Y) = (a, b) / (b, a) and T = t / 8 - t. */
+enum { THEIA_CP_SWAP = 1, THEIA_CP_FLIP = 2, THEIA_CP_TAPMAJOR = 4 };
+typedef struct theia_conv_perm {
+  const void* ref;   /* pack: fp32 master weight.  unpack: byte OFFSET of the weight in the gradient buffer */
+  void* pack0;       /* pack: bf16 pack (or NULL).    unpack: fp32 tap-major scratch ws[T][X][Y]             */
+  void* pack1;       /* pack: second bf16 pack (or NULL) */
+  int flags0, flags1;
+  int C;
+} theia_conv_perm;
+int theia_conv_pack(const theia_conv_perm* segs_dev, int nconv, int C, void* stream);
+int theia_conv_unpack(const theia_conv_perm* segs_dev, int nconv, int C, const void* out_rebase, void* stream);
 /* One launch over a device table of strided layout conversions (conv-weight packs, LayerNorm[C,H,W] affine <-> NHWC,
  * conv weight-gradient scratch -> reference layout); `in` is fp32, `out` bf16 or fp32 */
 typedef struct theia_perm_seg {

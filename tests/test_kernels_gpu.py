@@ -313,12 +313,14 @@ def test_loss_fwd_bwd(lib, tgt_dtype):
     coef = torch.tensor([0.3, 0.9, 0.1], device=DEV)
     (0.3 * ref["mse_loss"] + 0.9 * ref["cos_loss"] + 0.1 * ref["l1_loss"]).backward()
     d32 = torch.empty_like(pred)
+    dcp = torch.empty(pred.shape, dtype=torch.bfloat16, device=DEV)  # bf16 copy written in the same pass
     L.check(lib.theia_loss_bwd(pred.data_ptr(), tgt.data_ptr(), int(tgt_dtype == torch.bfloat16), acc.data_ptr(),
-                               coef.data_ptr(), d32.data_ptr(), 1, Bn, n, S()))
+                               coef.data_ptr(), d32.data_ptr(), 1, dcp.data_ptr(), Bn, n, S()))
     assert relerr(d32, pr.grad) < 1e-4
+    assert torch.equal(dcp, d32.to(torch.bfloat16))
     d16 = torch.empty(pred.shape, dtype=torch.bfloat16, device=DEV)
     L.check(lib.theia_loss_bwd(pred.data_ptr(), tgt.data_ptr(), int(tgt_dtype == torch.bfloat16), acc.data_ptr(),
-                               coef.data_ptr(), d16.data_ptr(), 0, Bn, n, S()))
+                               coef.data_ptr(), d16.data_ptr(), 0, 0, Bn, n, S()))
     assert relerr(d16.float(), pr.grad) < 5e-3
 
 

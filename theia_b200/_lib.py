@@ -63,12 +63,14 @@ SYMBOLS = {
     "theia_ln3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp]),
     "theia_adamw_flat": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp, _vp, _vp, _vp]),
     "theia_pack_cast": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "theia_conv_pack": (_i, [_vp, _i, _i, _vp]),
+    "theia_conv_unpack": (_i, [_vp, _i, _i, _vp, _vp]),
     "theia_perm_segments": (_i, [_vp, _i, _ll, _vp, _vp]),
     "theia_target_ingest": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_chw_to_hwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "theia_hwc_to_chw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "theia_loss_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _vp]),
-    "theia_loss_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "theia_loss_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "theia_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _vp]),
     "theia_preprocess_debug_u8": (_i, [_vp]),
     "theia_attention_tc_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -490,7 +490,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ acc, float* __res
 template <typename TT, typename TO>
 __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict__ pred, const TT* __restrict__ tgt,
                                                         const float* __restrict__ acc, const float* __restrict__ coef,
-                                                        TO* __restrict__ dpred, int n, int B) {
+                                                        TO* __restrict__ dpred, int n, int B, bf16* __restrict__ dpred_bf16) {
   const int b = blockIdx.y;
   const long long base = static_cast<long long>(b) * n;
   const float* a = acc + b * 5;
@@ -511,6 +511,12 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(const float* __restrict_
   for (int e = 0; e < 4; ++e) {
     const float d = p[e] - t[e];
     o[e] = km * d + kl * fminf(fmaxf(d, -1.f), 1.f) + ct * t[e] + cp * p[e];
+  }
+  if (dpred_bf16 != nullptr) {  // bf16 copy for the head-Linear backward GEMMs, written in the same pass
+    uint2 u;
+    u.x = pack_bf16x2(o[0], o[1]);
+    u.y = pack_bf16x2(o[2], o[3]);
+    *reinterpret_cast<uint2*>(dpred_bf16 + base + j) = u;
   }
   if constexpr (sizeof(TO) == 4) {
     *reinterpret_cast<float4*>(dpred + base + j) = make_float4(o[0], o[1], o[2], o[3]);
@@ -894,6 +900,70 @@ __global__ void __launch_bounds__(256) batchsum_kernel(const bf16* __restrict__ 
   for (int e = 0; e < 8; ++e) out[j + e] = a[e];
 }
 
+// --------------------------------------------------------------------------------------------
+// Conv-weight layout conversions through shared-memory tiles (coalesced on both sides).
+//   reference layout  W[a][b][9]  (a, b < C; Conv2d: a = Cout, b = Cin; ConvTranspose2d: a = Cin, b = Cout)
+//   GEMM pack         P[X][T][Y] ("tap in the middle") or P[T][X][Y] (tap-major), (X, Y) = (a, b) or (b, a),
+//                     T = t or 8 - t (flipped kernel)
+// pack:   W (fp32 master) -> up to two bf16 packs per weight (forward and dgrad operand)
+// unpack: tap-major fp32 weight-gradient scratch ws[T][X][Y] -> reference layout (fp32 gradient buffer)
+// One launch per direction for ALL conv weights of the model (segment table in device memory).
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long conv_perm_index(int a, int b, int t, int C, int flags) {
+  const int X = (flags & THEIA_CP_SWAP) ? b : a, Y = (flags & THEIA_CP_SWAP) ? a : b;
+  const int T = (flags & THEIA_CP_FLIP) ? 8 - t : t;
+  return (flags & THEIA_CP_TAPMAJOR) ? (static_cast<long long>(T) * C + X) * C + Y
+                                     : (static_cast<long long>(X) * 9 + T) * C + Y;
+}
+
+__global__ void __launch_bounds__(256) conv_pack_kernel(const theia_conv_perm* __restrict__ segs, int tiles_per_conv,
+                                                        int tiles_b) {
+  __shared__ float tile[32][32 * 9 + 1];
+  const theia_conv_perm sg = segs[blockIdx.x / tiles_per_conv];
+  const int tix = blockIdx.x % tiles_per_conv;
+  const int a0 = (tix / tiles_b) * 32, b0 = (tix % tiles_b) * 32;
+  const int C = sg.C;
+  const float* in = static_cast<const float*>(sg.ref);
+  for (int i = threadIdx.x; i < 32 * 288; i += 256) {  // row a0 + i / 288: 288 contiguous floats (32 b x 9 taps)
+    const int ar = i / 288, k = i - ar * 288;
+    tile[ar][k] = in[(static_cast<long long>(a0 + ar) * C + b0) * 9 + k];
+  }
+  __syncthreads();
+  for (int which = 0; which < 2; ++which) {
+    bf16* out = static_cast<bf16*>(which ? sg.pack1 : sg.pack0);
+    const int flags = which ? sg.flags1 : sg.flags0;
+    if (out == nullptr) continue;
+    // 32 consecutive Y per (X, T): Y = b without SWAP, a with SWAP
+    for (int i = threadIdx.x; i < 32 * 9 * 32; i += 256) {
+      const int y = i & 31, xt = i >> 5, t = xt % 9, x = xt / 9;
+      const int a = (flags & THEIA_CP_SWAP) ? y : x, b = (flags & THEIA_CP_SWAP) ? x : y;
+      out[conv_perm_index(a0 + a, b0 + b, t, C, flags)] = __float2bfloat16_rn(tile[a][b * 9 + t]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) conv_unpack_kernel(const theia_conv_perm* __restrict__ segs, int tiles_per_conv,
+                                                          int tiles_b, uintptr_t out_rebase) {
+  __shared__ float tile[32][32 * 9 + 1];
+  const theia_conv_perm sg = segs[blockIdx.x / tiles_per_conv];
+  const int tix = blockIdx.x % tiles_per_conv;
+  const int a0 = (tix / tiles_b) * 32, b0 = (tix % tiles_b) * 32;
+  const int C = sg.C;
+  const float* ws = static_cast<const float*>(sg.pack0);
+  const int flags = sg.flags0 | THEIA_CP_TAPMAJOR;
+  for (int i = threadIdx.x; i < 32 * 9 * 32; i += 256) {
+    const int y = i & 31, xt = i >> 5, t = xt % 9, x = xt / 9;
+    const int a = (flags & THEIA_CP_SWAP) ? y : x, b = (flags & THEIA_CP_SWAP) ? x : y;
+    tile[a][b * 9 + t] = ws[conv_perm_index(a0 + a, b0 + b, t, C, flags)];
+  }
+  __syncthreads();
+  float* out = reinterpret_cast<float*>(reinterpret_cast<uintptr_t>(sg.ref) + out_rebase);
+  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+    const int ar = i / 288, k = i - ar * 288;
+    out[(static_cast<long long>(a0 + ar) * C + b0) * 9 + k] = tile[ar][k];
+  }
+}
+
 }  // namespace theia
 
 using namespace theia;
@@ -987,19 +1057,21 @@ extern "C" int theia_loss_fwd(const float* pred, const void* target, int target_
 }
 
 extern "C" int theia_loss_bwd(const float* pred, const void* target, int target_is_bf16, const float* acc,
-                              const float* coef3, void* dpred, int dpred_is_f32, int B, int n, void* stream) {
+                              const float* coef3, void* dpred, int dpred_is_f32, void* dpred_bf16_copy, int B, int n,
+                              void* stream) {
   if (n % 4 != 0) return set_error(THEIA_ERR_ARG, "loss: n %% 4 != 0");
   dim3 g((n / 4 + 255) / 256, B);
   const bf16* tb = static_cast<const bf16*>(target);
   const float* tf = static_cast<const float*>(target);
+  bf16* cp = dpred_is_f32 ? static_cast<bf16*>(dpred_bf16_copy) : nullptr;
   if (target_is_bf16 && dpred_is_f32)
-    loss_grad_kernel<bf16, float><<<g, 256, 0, S(stream)>>>(pred, tb, acc, coef3, static_cast<float*>(dpred), n, B);
+    loss_grad_kernel<bf16, float><<<g, 256, 0, S(stream)>>>(pred, tb, acc, coef3, static_cast<float*>(dpred), n, B, cp);
   else if (target_is_bf16)
-    loss_grad_kernel<bf16, bf16><<<g, 256, 0, S(stream)>>>(pred, tb, acc, coef3, static_cast<bf16*>(dpred), n, B);
+    loss_grad_kernel<bf16, bf16><<<g, 256, 0, S(stream)>>>(pred, tb, acc, coef3, static_cast<bf16*>(dpred), n, B, cp);
   else if (dpred_is_f32)
-    loss_grad_kernel<float, float><<<g, 256, 0, S(stream)>>>(pred, tf, acc, coef3, static_cast<float*>(dpred), n, B);
+    loss_grad_kernel<float, float><<<g, 256, 0, S(stream)>>>(pred, tf, acc, coef3, static_cast<float*>(dpred), n, B, cp);
   else
-    loss_grad_kernel<float, bf16><<<g, 256, 0, S(stream)>>>(pred, tf, acc, coef3, static_cast<bf16*>(dpred), n, B);
+    loss_grad_kernel<float, bf16><<<g, 256, 0, S(stream)>>>(pred, tf, acc, coef3, static_cast<bf16*>(dpred), n, B, cp);
   THEIA_CHECK_LAUNCH("loss_grad");
   return THEIA_OK;
 }
@@ -1132,6 +1204,24 @@ extern "C" int theia_adamw_flat(float* p, const float* g, float* m, float* v, co
       p, g, m, v, flag64, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), gscale,
       packbf ? pack_table : nullptr, static_cast<bf16*>(packbf));
   THEIA_CHECK_LAUNCH("adamw_flat");
+  return THEIA_OK;
+}
+
+extern "C" int theia_conv_pack(const theia_conv_perm* segs_dev, int nconv, int C, void* stream) {
+  if (nconv <= 0) return THEIA_OK;
+  if (C % 32 != 0) return set_error(THEIA_ERR_ARG, "conv_pack: C %% 32 != 0");
+  const int tb = C / 32;
+  conv_pack_kernel<<<nconv * tb * tb, 256, 0, S(stream)>>>(segs_dev, tb * tb, tb);
+  THEIA_CHECK_LAUNCH("conv_pack");
+  return THEIA_OK;
+}
+
+extern "C" int theia_conv_unpack(const theia_conv_perm* segs_dev, int nconv, int C, const void* out_rebase, void* stream) {
+  if (nconv <= 0) return THEIA_OK;
+  if (C % 32 != 0) return set_error(THEIA_ERR_ARG, "conv_unpack: C %% 32 != 0");
+  const int tb = C / 32;
+  conv_unpack_kernel<<<nconv * tb * tb, 256, 0, S(stream)>>>(segs_dev, tb * tb, tb, reinterpret_cast<uintptr_t>(out_rebase));
+  THEIA_CHECK_LAUNCH("conv_unpack");
   return THEIA_OK;
 }
 

@@ -60,6 +60,12 @@ struct HeadA {
 // one strided layout conversion of the pack / unpack tables (pointers are resolved at bind time)
 enum { SEG_IN_MASTER = 0, SEG_IN_ACTF32 = 1 };
 enum { SEG_OUT_PACKBF = 0, SEG_OUT_PACKF32 = 1, SEG_OUT_GRADS = 2 };
+// one conv weight of the tiled pack / unpack tables (theia_conv_pack / theia_conv_unpack)
+struct ConvSpec {
+  long long w_off;                 // parameter offset (floats) in the flat master / gradient buffers
+  long long pack0, pack1;          // pack: bf16 pack offsets; unpack: pack0 = fp32 scratch offset (act f32 region)
+  int flags0, flags1;
+};
 struct SegSpec {
   int in_base, out_base;
   long long in_off, out_off;
@@ -107,7 +113,9 @@ struct theia_model {
   // segment tables of the permuted packs / gradient unpacks; uploaded into the workspace by theia_model_bind
   std::vector<int> h_table;
   std::vector<SegSpec> pack_specs, unpack_specs;
+  std::vector<ConvSpec> conv_pack, conv_unpack;
   long long o_table = 0, o_pack_segs = 0, o_unpack_segs = 0;  // byte offsets in the workspace
+  long long o_conv_pack = 0, o_conv_unpack = 0;
   long long pack_blocks = 0, unpack_blocks = 0;
   int last_B = 0;
 };
@@ -306,22 +314,16 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
     m->hw.push_back(w);
     auto& ps = m->pack_specs;
     const auto off = [&](int pi) { return m->params[pi].off; };
-    // ConvTranspose2d weight [Cin][Cout][3][3]: fwd pack F[co][tap2][ci] = Wt[ci][co][8-tap2]
-    seg(ps, SEG_IN_MASTER, off(hp.padw), SEG_OUT_PACKBF, w.padF, C, 9, C, 1, 9, -1, C9, 0, 8);
+    // ConvTranspose2d weight Wt[ci][co][3][3] (a = ci, b = co): fwd pack F[co][tap2][ci] = Wt[ci][co][8-tap2],
     // dgrad pack D[ci][tap][co] = Wt[ci][co][tap]
-    seg(ps, SEG_IN_MASTER, off(hp.padw), SEG_OUT_PACKBF, w.padD, C, 9, C, 1, C9, 1, 9, 0, 0);
+    m->conv_pack.push_back(ConvSpec{off(hp.padw), w.padF, w.padD, THEIA_CP_SWAP | THEIA_CP_FLIP, 0});
     const int cw[2] = {hp.c1w, hp.c2w};
     const long long cF[2] = {w.c1F, w.c2F}, cD[2] = {w.c1D, w.c2D};
     for (int i = 0; i < 2; ++i) {
-      if (hp.hw == 16) {
-        // Conv2d weight [Cout][Cin][3][3]: fwd F[co][tap][ci]; dgrad D[ci][tap2][co] = W[co][ci][8-tap2]
-        seg(ps, SEG_IN_MASTER, off(cw[i]), SEG_OUT_PACKBF, cF[i], C, 9, C, 1, C9, 1, 9, 0, 0);
-        seg(ps, SEG_IN_MASTER, off(cw[i]), SEG_OUT_PACKBF, cD[i], C, 9, C, 1, 9, -1, C9, 0, 8);
-      } else {
-        // ConvTranspose2d(s2) weight [Cin][Cout][3][3] -> tap-major F[tap][co][ci] and D[tap][ci][co]
-        seg(ps, SEG_IN_MASTER, off(cw[i]), SEG_OUT_PACKBF, cF[i], 9, C, C, 1, 1, 9, C9, 0, 0);
-        seg(ps, SEG_IN_MASTER, off(cw[i]), SEG_OUT_PACKBF, cD[i], 9, C, C, 1, 1, C9, 9, 0, 0);
-      }
+      if (hp.hw == 16)  // Conv2d W[co][ci][3][3]: fwd F[co][tap][ci]; dgrad D[ci][tap2][co] = W[co][ci][8-tap2]
+        m->conv_pack.push_back(ConvSpec{off(cw[i]), cF[i], cD[i], 0, THEIA_CP_SWAP | THEIA_CP_FLIP});
+      else  // ConvTranspose2d(s2) Wt[ci][co][3][3] -> tap-major F[tap][co][ci] and D[tap][ci][co]
+        m->conv_pack.push_back(ConvSpec{off(cw[i]), cF[i], cD[i], THEIA_CP_TAPMAJOR | THEIA_CP_SWAP, THEIA_CP_TAPMAJOR});
     }
     // LN affine [C][Hv][Wv] -> NHWC [Hp][Wp][C] (zero padded for the 31x31 stage)
     const int gbp[3][2] = {{hp.g0, hp.b0}, {hp.g1, hp.b1}, {hp.g2, hp.b2}};
@@ -388,17 +390,16 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
     m->n_bscr = align_up(sc.n, AL);
     m->bscr = af.take(m->n_bscr, AL);
     auto& us = m->unpack_specs;
-    const long long CC = 1LL * C * C;
     for (int t = 0; t < T; ++t) {
       const HeadP& hp = m->hp[t];
       if (hp.hw == 1) continue;
       const HeadA& a = m->ha[t];
       const auto off = [&](int pi) { return m->params[pi].off; };
-      // pad (stride-1 ConvTranspose2d): grad Wt[ci][co][t] = ws[8-t][co][ci]
-      seg(us, SEG_IN_ACTF32, m->bscr + a.wsc[0], SEG_OUT_GRADS, off(hp.padw), C, C, 9, 1, 1, C, -CC, 0, 8 * CC);
-      // Conv2d: grad W[co][ci][tap] = ws[tap][co][ci];  ConvTranspose2d(s2): grad Wt[ci][co][tap] = ws[tap][ci][co]
-      seg(us, SEG_IN_ACTF32, m->bscr + a.wsc[1], SEG_OUT_GRADS, off(hp.c1w), C, C, 9, 1, C, 1, CC, 0, 0);
-      seg(us, SEG_IN_ACTF32, m->bscr + a.wsc[2], SEG_OUT_GRADS, off(hp.c2w), C, C, 9, 1, C, 1, CC, 0, 0);
+      // pad (stride-1 ConvTranspose2d): grad Wt[ci][co][t] = ws[8-t][co][ci];  Conv2d: grad W[co][ci][tap] =
+      // ws[tap][co][ci];  ConvTranspose2d(s2): grad Wt[ci][co][tap] = ws[tap][ci][co]
+      m->conv_unpack.push_back(ConvSpec{off(hp.padw), m->bscr + a.wsc[0], 0, THEIA_CP_SWAP | THEIA_CP_FLIP, 0});
+      m->conv_unpack.push_back(ConvSpec{off(hp.c1w), m->bscr + a.wsc[1], 0, 0, 0});
+      m->conv_unpack.push_back(ConvSpec{off(hp.c2w), m->bscr + a.wsc[2], 0, 0, 0});
       const int gbp[3][2] = {{hp.g0, hp.b0}, {hp.g1, hp.b1}, {hp.g2, hp.b2}};
       const int vv[3] = {16, hp.v1, hp.v2}, pp[3] = {16, hp.p1, hp.p2};
       for (int i = 0; i < 3; ++i)
@@ -433,6 +434,10 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
   o = align_up(o + static_cast<long long>(m->pack_specs.size()) * sizeof(theia_perm_seg), 1024);
   m->o_unpack_segs = o;
   o = align_up(o + static_cast<long long>(m->unpack_specs.size()) * sizeof(theia_perm_seg), 1024);
+  m->o_conv_pack = o;
+  o = align_up(o + static_cast<long long>(m->conv_pack.size()) * sizeof(theia_conv_perm), 1024);
+  m->o_conv_unpack = o;
+  o = align_up(o + static_cast<long long>(m->conv_unpack.size()) * sizeof(theia_conv_perm), 1024);
   m->ws_bytes = o;
   *out = m;
   return THEIA_OK;
@@ -541,7 +546,28 @@ extern "C" int theia_model_bind(theia_model* m, float* master, float* grads, voi
   if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "pack table upload: %s", cudaGetErrorString(e));
   int rc = upload_segs(m, m->pack_specs, m->o_pack_segs, &m->pack_blocks);
   if (rc) return rc;
-  return upload_segs(m, m->unpack_specs, m->o_unpack_segs, &m->unpack_blocks);
+  rc = upload_segs(m, m->unpack_specs, m->o_unpack_segs, &m->unpack_blocks);
+  if (rc) return rc;
+  // conv-weight tables: pack (master -> two bf16 packs), unpack (tap-major fp32 scratch -> gradient buffer offset)
+  std::vector<theia_conv_perm> hp(m->conv_pack.size()), hu(m->conv_unpack.size());
+  bf16* pbf = reinterpret_cast<bf16*>(m->ws + m->o_packbf);
+  float* af32 = reinterpret_cast<float*>(m->ws + m->o_actf32);
+  for (size_t i = 0; i < hp.size(); ++i) {
+    const ConvSpec& q = m->conv_pack[i];
+    hp[i] = theia_conv_perm{m->master + q.w_off, pbf + q.pack0, pbf + q.pack1, q.flags0, q.flags1, m->D};
+  }
+  for (size_t i = 0; i < hu.size(); ++i) {
+    const ConvSpec& q = m->conv_unpack[i];
+    hu[i] = theia_conv_perm{reinterpret_cast<const void*>(static_cast<uintptr_t>(q.w_off) * 4), af32 + q.pack0, nullptr,
+                            q.flags0, 0, m->D};
+  }
+  if (!hp.empty()) {
+    e = cudaMemcpy(m->ws + m->o_conv_pack, hp.data(), hp.size() * sizeof(theia_conv_perm), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+      e = cudaMemcpy(m->ws + m->o_conv_unpack, hu.data(), hu.size() * sizeof(theia_conv_perm), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "conv table upload: %s", cudaGetErrorString(e));
+  }
+  return THEIA_OK;
 }
 
 // Switch the gradient buffer (same layout) without touching anything else: lets the caller hand out the buffer of
@@ -833,6 +859,8 @@ extern "C" int theia_model_pack(theia_model* m, int skip_linear_cast, void* stre
                                                              m->regt >= 0 ? c.W(m->regt) : nullptr,
                                                              m->regp >= 0 ? c.W(m->regp) : nullptr, m->N, D, m->p0);
   THEIA_CHECK_LAUNCH("token_table");
+  TRY(theia_conv_pack(reinterpret_cast<const theia_conv_perm*>(m->ws + m->o_conv_pack),
+                      static_cast<int>(m->conv_pack.size()), D, c.s));
   TRY(theia_perm_segments(reinterpret_cast<const theia_perm_seg*>(m->ws + m->o_pack_segs),
                           static_cast<int>(m->pack_specs.size()), m->pack_blocks, nullptr, c.s));
   return THEIA_OK;
@@ -1012,9 +1040,12 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     }
   }
   // tap-major conv weight gradients and NHWC LayerNorm-affine gradients of all heads -> reference layouts: one launch
-  if (any_head)
+  if (any_head) {
+    TRY(theia_conv_unpack(reinterpret_cast<const theia_conv_perm*>(m->ws + m->o_conv_unpack),
+                          static_cast<int>(m->conv_unpack.size()), C, m->grads, c.s));
     TRY(theia_perm_segments(reinterpret_cast<const theia_perm_seg*>(m->ws + m->o_unpack_segs),
                             static_cast<int>(m->unpack_specs.size()), m->unpack_blocks, m->grads, c.s));
+  }
   // final LayerNorm
   bf16* dx = c.AB(m->dx0);
   bf16* dx2 = c.AB(m->dx1);

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from typing import Any, Optional
 
 import torch
@@ -78,6 +79,25 @@ class _ForwardFn(torch.autograd.Function):
         return (None, None, None, None, *out)
 
 
+# id(fp32 loss gradient tensor, as autograd carries it) -> (weakref to it, the bf16 copy the loss kernel wrote in the
+# same pass, its version).  Keyed by id with an identity check (tensors cannot be dict keys: == is elementwise).
+_DPRED_BF16 = {}
+
+
+def _stash_dpred(dpred, dbf):
+    if len(_DPRED_BF16) > 64:  # entries whose gradient tensor died without reaching _run_backward
+        for k in [k for k, v in _DPRED_BF16.items() if v[0]() is None]:
+            del _DPRED_BF16[k]
+    _DPRED_BF16[id(dpred)] = (weakref.ref(dpred), dbf, dpred._version)
+
+
+def _take_dpred(g):
+    ent = _DPRED_BF16.pop(id(g), None)
+    if ent is not None and ent[0]() is g and ent[2] == g._version and ent[1].shape == g.shape:
+        return ent[1]
+    return None
+
+
 class _LossFn(torch.autograd.Function):
     """(pred, target) -> tensor [3] = (mse, cos, l1) as nn.MSELoss / CosineEmbeddingLoss /
     SmoothL1Loss return them (rvfm.py:153-168)."""
@@ -111,10 +131,15 @@ class _LossFn(torch.autograd.Function):
         n = pred[0].numel()
         coef = g.contiguous().float()
         dpred = torch.empty_like(pred)
+        # autograd needs the fp32 gradient (dtype of `pred`); the head-Linear backward GEMMs need bf16: the same pass
+        # writes both, and the copy is handed to RobotVisionFM._run_backward through a weak table keyed by the
+        # gradient tensor itself (used only if that very tensor, unmodified, arrives there)
+        dbf = torch.empty(pred.shape, dtype=torch.bfloat16, device=pred.device)
         with torch.cuda.device(pred.device):
             L.check(L.lib().theia_loss_bwd(pred.data_ptr(), target.data_ptr(), int(target.dtype == torch.bfloat16),
-                                           acc.data_ptr(), coef.data_ptr(), dpred.data_ptr(), 1, B, n, L.stream_ptr()),
-                    "theia_loss_bwd")
+                                           acc.data_ptr(), coef.data_ptr(), dpred.data_ptr(), 1, dbf.data_ptr(), B, n,
+                                           L.stream_ptr()), "theia_loss_bwd")
+        _stash_dpred(dpred, dbf)
         return dpred, None
 
 
@@ -435,12 +460,18 @@ class RobotVisionFM(nn.Module):
         B = self._last_B
         ptrs = (C.c_void_p * L.MAX_TEACHERS)()
         k = 0
+        keep = []  # bf16 gradients stay alive until the backward kernels have been enqueued
         for i, t in enumerate(self._teachers):
             if t not in names:
                 continue
             g = dpreds[k]
             k += 1
             if g is None:
+                continue
+            hit = _take_dpred(g)
+            if hit is not None:
+                ptrs[i] = hit.data_ptr()  # produced by theia_loss_bwd together with g: no cast
+                keep.append(hit)
                 continue
             g = g.contiguous()
             if g.dtype != torch.float32:
