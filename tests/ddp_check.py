@@ -83,7 +83,7 @@ def main():
     for r in range(1, world):
         assert torch.equal(flats[0], flats[r]), f"FlatAdamW + sync_gradients: parameters diverged (rank 0 vs {r})"
     with torch.no_grad():
-        feat = m3.forward_feature(shards[0][0], do_resize=False)  # same images on every rank
+        feat = m3.forward_feature(shards[0][0], do_resize=False).contiguous()  # same images on every rank
     feats = [torch.empty_like(feat) for _ in range(world)]
     dist.all_gather(feats, feat)
     for r in range(1, world):
