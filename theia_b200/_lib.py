@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtheia_b200.so")
+# THEIA_B200_LIB: A/B experiments against an alternative in-tree build (tools only; the product path is the default)
+LIB_PATH = os.environ.get("THEIA_B200_LIB") or os.path.join(_PKG, "libtheia_b200.so")
 
 OP_K2D, OP_MN2D, OP_CONV_K, OP_CONV_MN = 0, 1, 2, 3
 EPI_GELU, EPI_RELU, EPI_RESID, EPI_OUT_F32, EPI_ATOMIC = 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5
