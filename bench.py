@@ -525,7 +525,9 @@ def main():
     achieved = gemm_alg_tflop / (gemm_ms_step / 1e3) if gemm_ms_step > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.backbone == "base":
         traffic = json.load(open(tpath)).get("traffic_bytes_per_launch_mean")  # ncu --set full capture, see profiles/
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv, all instances)",

@@ -486,7 +486,7 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // non-blocking barrier test by lane 0, broadcast: the control flow stays warp-uniform
       auto ready = [&](uint64_t* bar, uint32_t parity) -> bool {
         uint32_t ok = 0;
-        if (lane == 0) ok = mbar_try_wait(bar, parity) ? 1u : 0u;
+        if (lane == 0) ok = mbar_test_wait(bar, parity) ? 1u : 0u;
         return __shfl_sync(0xffffffffu, ok, 0) != 0;
       };
       auto issue_scores = [&](int n) {
@@ -547,7 +547,6 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // compute warps' next block writes and the dQ chain) or the scores of the next sub-unit (at most two score
       // sets in flight) -- is issued as soon as its barriers allow; nothing is waited for in a fixed order.
       while (n_out < total) {
-        bool progressed = false;
         if (n_out < n_sub) {
           const int n = n_out, it = n >> 3, u = (n >> 2) & 1, j = n & 3;
           bool ok = ready(&pb_full[n & 1], (n >> 1) & 1);
@@ -556,7 +555,6 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (ok) {
             issue_out(n);
             ++n_out;
-            progressed = true;
           }
         }
         if (n_sub < total) {  // bounded by the two score sets: sub-unit n_sub - 2 must be in registers
@@ -568,10 +566,8 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (ok) {
             issue_scores(n);
             ++n_sub;
-            progressed = true;
           }
         }
-        (void)progressed;
       }
     }
   } else if (warp == 2 || warp == 3) {
