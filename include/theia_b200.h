@@ -134,7 +134,9 @@ int theia_loss_fwd(const float* pred, const void* target, int target_is_bf16, fl
 int theia_loss_bwd(const float* pred, const void* target, int target_is_bf16, const float* acc, const float* coef3,
                    void* dpred, int dpred_is_f32, void* dpred_bf16_copy, int B, int n, void* stream);
 /* DeiT image processor (backbones.py:337-339; hf:image_processing_backends.py:361-414): uint8 HWC/CHW
- * 224x224 -> [bicubic-antialias resize to 256 + centre crop 224 when do_resize] -> rescale/normalise ->
+ * 224x224 -> [bicubic-antialias resize to 256 + centre crop 224 when do_resize: 1 = float arithmetic + round, what
+ * torchvision does for CUDA tensors; 2 = int16 fixed-point two-pass scheme with a uint8 intermediate, what it does
+ * for CPU uint8 tensors -- both bit-exact with torchvision] -> rescale/normalise ->
  * bf16 patch rows [B*197, 768] (row b*197 is the zero CLS slot; column = c*256 + i*16 + j) */
 int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_resize, int do_rescale,
                      int do_normalize, const float* mean3, const float* std3, int tokens, int patch_off, void* stream);

@@ -687,10 +687,10 @@ attn_tc_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&sd_free[set]);
-          // the outputs of the key tile (item) that finished one sub-unit ago: their last MMAs were issued when that
-          // sub-unit's operands were published, they are complete (or nearly) by now, and the score registers of
-          // this sub-unit are already loaded -- the read-out costs no waiting
-          if (j == 0) {
+          // the outputs of the key tile (item) that finished two sub-units ago: their last MMAs were issued when that
+          // tile's last block was published, they are complete by now, and the score registers of this sub-unit are
+          // already loaded -- the read-out costs no waiting (the first output MMAs of the new tile wait for it)
+          if (j == 1) {
             if (u == 1) {
               drain_acc(0, item, 0u);  // key tile 2 it: even
             } else if (it > 0) {

@@ -579,12 +579,17 @@ struct ResizeTable {
   int xmin[256];
   int xsize[256];
   float w[256][5];
+  // torchvision's CPU uint8 path (ATen upsample_bicubic2d_aa on uint8, the Pillow-SIMD scheme): the same taps as
+  // int16 fixed-point weights with `prec` fractional bits; horizontal pass first, its result rounded and clamped to
+  // uint8, then the vertical pass
+  int wi[256][5];
+  int prec;
 };
 __constant__ ResizeTable c_rt;
 
 __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int NT, int P0,
                                                                 int B, int chw, float s0, float s1, float s2, float o0,
-                                                                float o1, float o2, uint8_t* __restrict__ dbg_u8) {
+                                                                float o1, float o2, uint8_t* __restrict__ dbg_u8, int fixed) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * NT * 96;
   if (t >= total) return;
@@ -613,6 +618,20 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* _
       const int ox = px * 16 + j + e + 16;
       const int xmin = c_rt.xmin[ox], xsize = c_rt.xsize[ox];
       float acc = 0.f;
+      if (fixed) {  // CPU-tensor semantics of the reference's processor: integer arithmetic, bit-exact
+        const int half = 1 << (c_rt.prec - 1);
+        int sv = half;
+        for (int y = 0; y < ysize; ++y) {
+          const uint8_t* src = base + (ymin + y) * row_stride + xmin * pix_stride;
+          int sh = half;
+          for (int x = 0; x < xsize; ++x) sh += static_cast<int>(src[x * pix_stride]) * c_rt.wi[ox][x];
+          sh >>= c_rt.prec;
+          sh = sh < 0 ? 0 : (sh > 255 ? 255 : sh);
+          sv += sh * c_rt.wi[oy][y];
+        }
+        sv >>= c_rt.prec;
+        acc = static_cast<float>(sv < 0 ? 0 : (sv > 255 ? 255 : sv));
+      } else {
       for (int y = 0; y < ysize; ++y) {
         const uint8_t* src = base + (ymin + y) * row_stride + xmin * pix_stride;
         float r = static_cast<float>(src[0]) * c_rt.w[ox][0];
@@ -621,6 +640,7 @@ __global__ void __launch_bounds__(256) preprocess_resize_kernel(const uint8_t* _
         else acc += r * c_rt.w[oy][y];
       }
       acc = rintf(fminf(fmaxf(acc, 0.f), 255.f));
+      }
       o[e] = (acc - of) * sc;
       // test hook: the resized + centre-cropped uint8 image [B,224,224,3] the reference's processor produces
       if (dbg_u8 != nullptr)
@@ -1117,6 +1137,41 @@ static int upload_resize_table() {
     rt.xsize[o] = xsize > 5 ? 5 : xsize;
     for (int j = 0; j < 5; ++j) rt.w[o][j] = w[j];
   }
+  {  // fixed-point weights (double arithmetic, as ATen's _compute_indices_int16_weights_aa)
+    static double wd[256][5];
+    double wt_max = 0.0;
+    const double dscale = 224.0 / 256.0;
+    for (int o = 0; o < 256; ++o) {
+      const double center = dscale * (o + 0.5);
+      double total = 0.0;
+      for (int j = 0; j < 5; ++j) wd[o][j] = 0.0;
+      for (int j = 0; j < rt.xsize[o]; ++j) {
+        double x = (j + rt.xmin[o] - center + 0.5);
+        if (x < 0.0) x = -x;
+        const double a = -0.5;
+        double wv = 0.0;
+        if (x < 1.0) wv = ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0;
+        else if (x < 2.0) wv = (((x - 5.0) * x + 8.0) * x - 4.0) * a;
+        wd[o][j] = wv;
+        total += wv;
+      }
+      for (int j = 0; j < rt.xsize[o]; ++j) {
+        wd[o][j] /= total;
+        if (wd[o][j] > wt_max) wt_max = wd[o][j];
+      }
+    }
+    int prec = 0;
+    for (; prec < 22; ++prec) {
+      const int next = static_cast<int>(0.5 + wt_max * (1 << (prec + 1)));
+      if (next >= (1 << 15)) break;
+    }
+    rt.prec = prec;
+    for (int o = 0; o < 256; ++o)
+      for (int j = 0; j < 5; ++j) {
+        const double v = wd[o][j];
+        rt.wi[o][j] = v < 0 ? static_cast<int>(-0.5 + v * (1 << prec)) : static_cast<int>(0.5 + v * (1 << prec));
+      }
+  }
   cudaError_t e = cudaMemcpyToSymbol(c_rt, &rt, sizeof(rt));
   if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "resize table upload: %s", cudaGetErrorString(e));
   done[dev] = true;
@@ -1155,7 +1210,8 @@ extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int
     if (rc) return rc;
     preprocess_resize_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), tokens, patch_off, B,
                                                           channels_first,
-                                                          sc[0], sc[1], sc[2], of[0], of[1], of[2], g_resize_dbg_u8);
+                                                          sc[0], sc[1], sc[2], of[0], of[1], of[2], g_resize_dbg_u8,
+                                                          do_resize == 2 ? 1 : 0);
   } else {
     preprocess_kernel<<<grid, 256, 0, S(stream)>>>(images, static_cast<bf16*>(patches), tokens, patch_off, B,
                                                    channels_first, sc[0],

@@ -425,6 +425,9 @@ class RobotVisionFM(nn.Module):
         # interpolate_pos_encoding=True is the identity for 224x224 inputs (hf:modeling_vit.py:74-76 returns the
         # stored table when the patch grid matches); other input sizes are rejected in _prep_images like the
         # reference rejects them without the flag (hf:modeling_vit.py:160-165)
+        # the reference's processor resizes CPU uint8 tensors (and PIL / numpy inputs) with torchvision's fixed-point
+        # path and CUDA tensors with the float path: reproduce whichever the caller would have got (2 / 1)
+        on_cpu = not (torch.is_tensor(x) and x.is_cuda)
         images, chw = self._prep_images(x, do_resize)
         B = images.shape[0]
         self._ensure(B)
@@ -441,7 +444,7 @@ class RobotVisionFM(nn.Module):
                     ptrs[i] = p.data_ptr()
         self._fwd_id += 1
         L.check(L.lib().theia_model_forward(
-            self._handle, images.data_ptr(), B, chw, int(bool(do_resize)), int(kw.get("do_rescale", True)),
+            self._handle, images.data_ptr(), B, chw, (2 if on_cpu else 1) if do_resize else 0, int(kw.get("do_rescale", True)),
             int(kw.get("do_normalize", True)), mean, std, int(run_heads), ptrs,
             0 if tokens_out is None else tokens_out.data_ptr(), L.stream_ptr()), "theia_model_forward")
         self._last_B = B
