@@ -55,7 +55,9 @@ enum {
   THEIA_EPI_POSCLS = 1 << 8,    /* token t = m % tokens: patch token (tok_p0 <= t < tok_p1) ? v + pos[t,n]
                                    : pos[t,n]   (pos = per-token table incl. CLS / register tokens)      */
   THEIA_EPI_STATS = 1 << 9,     /* per-image sum / sum-of-squares of the stored values -> stats     */
-  THEIA_EPI_COLSUM = 1 << 10    /* colsum[n] += sum over rows of the stored (bf16) values           */
+  THEIA_EPI_COLSUM = 1 << 10,   /* colsum[n] += sum over rows of the stored (bf16) values           */
+  THEIA_EPI_GELU_FWD = 1 << 11, /* v = gelu(v), no derivative output (inference: teacher ViTs)      */
+  THEIA_EPI_QUICK_GELU = 1 << 12 /* v = v * sigmoid(1.702 v)  (hf:activations.py QuickGELUActivation; CLIP) */
 };
 
 typedef struct theia_conv_geom {
@@ -251,6 +253,50 @@ int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channe
                         int do_rescale, int do_normalize, const float* mean3, const float* std3, int run_heads, float* const* preds,
                         void* tokens_bf16_out, void* stream);
 int theia_model_backward(theia_model* m, const void* const* dpreds, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Teacher ViT inference: the frozen foundation models the student is distilled from --
+ * hf Dinov2Model / CLIPVisionModel / ViTModel as called by src/theia/foundation_models/vision_models/dinov2.py:26-31,
+ * vision_language_models/clip.py:26-31 and vision_models/vit.py:23-28.  Forward only; weights are caller-owned
+ * device buffers (bf16 GEMM operands [out][in], fp32 biases / LayerNorm affines); head dim 64, <= 272 tokens,
+ * hidden <= 1024.  DINOv2's LayerScale is folded into w_o / b_o and w_fc2 / b_fc2 by the caller.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct theia_vit_layer {
+  const float *ln1_w, *ln1_b;
+  const void* w_qkv;   /* bf16 [3*hidden][hidden]: query | key | value rows */
+  const float* b_qkv;  /* [3*hidden] */
+  const void* w_o;     /* bf16 [hidden][hidden] */
+  const float* b_o;
+  const float *ln2_w, *ln2_b;
+  const void* w_fc1;   /* bf16 [mlp][hidden] */
+  const float* b_fc1;
+  const void* w_fc2;   /* bf16 [hidden][mlp] */
+  const float* b_fc2;
+} theia_vit_layer;
+typedef struct theia_vit_desc {
+  int hidden, heads, layers, mlp;
+  int tokens, patch_off, patch_tokens; /* tokens per image; index of the first patch token; number of patch tokens */
+  int patch_k;                         /* columns of the patch matrix: channels * patch^2 rounded up to 8 */
+  float ln_eps;
+  int act;                             /* 0 = gelu (erf), 1 = quick_gelu (CLIP) */
+  const void* w_patch;                 /* bf16 [hidden][patch_k] (zero in the padding columns) */
+  const float* b_patch;                /* [hidden] or NULL (CLIP's patch conv has no bias) */
+  const float* tok_table;              /* fp32 [tokens][hidden]: position embedding (+ class embedding in row 0) */
+  const float *pre_ln_w, *pre_ln_b;    /* CLIP pre_layrnorm, else NULL */
+  const float *final_ln_w, *final_ln_b;/* NULL = none */
+  int final_ln_mode;                   /* 1 = every token (Dinov2Model / ViTModel .layernorm): last_hidden is normalised,
+                                          pooled = its CLS rows.  2 = CLIP: last_hidden is the raw encoder output,
+                                          pooled = post_layernorm(CLS rows) */
+  const theia_vit_layer* layer;        /* HOST array [layers] */
+} theia_vit_desc;
+long long theia_vit_workspace_bytes(const theia_vit_desc* d, int B);
+/* patches: bf16 [B*tokens][patch_k] (theia_patchify_f32); last_hidden: bf16 [B*tokens][hidden]; pooled: bf16
+ * [B][hidden] or NULL */
+int theia_vit_forward(const theia_vit_desc* d, const void* patches, int B, void* workspace, void* last_hidden, void* pooled,
+                      void* stream);
+/* processor output pixel_values fp32 [B][C][H][W] -> the bf16 patch matrix (non-patch rows / padding columns zero) */
+int theia_patchify_f32(const float* pixel_values, void* patches, int B, int C, int H, int W, int patch, int tokens,
+                       int patch_off, int patch_k, void* stream);
 
 /* Per-launch CUDA-event timing of the GEMM kernel on its launching stream (bench.py roofline). */
 int theia_prof_enable(int on);

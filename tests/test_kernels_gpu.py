@@ -447,6 +447,25 @@ def test_attention_fwd_bwd(lib, Bn, H):
         assert relerr(got[:, i], g[:, i]) < 1.5e-2, nm
 
 
+@pytest.mark.parametrize("Bn,H,N", [(2, 16, 257), (20, 16, 257), (3, 12, 272), (2, 4, 209), (5, 16, 256)])
+def test_attention_fwd_long_sequences(lib, Bn, H, N):
+    """209..272 tokens: the 257-token (ViT-L/14 at 224) teacher forward (feature_extraction.py); forward only"""
+    D = H * 64
+    qkv = rnd(Bn * N, 3 * D, seed=3, scale=1.5)
+    out = torch.full((Bn * N, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(Bn, H, N, device=DEV)
+    L.check(lib.theia_attention_tc_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), Bn, N, H, S()))
+    x = qkv.float().view(Bn, N, 3, H, 64)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(2, 3)) * 0.125
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(Bn * N, D)
+    assert relerr(out.float(), ref) < 8e-3
+    torch.testing.assert_close(lse, torch.logsumexp(s, -1), rtol=1e-4, atol=1e-4)
+    L.check(lib.theia_attention_tc_fwd(qkv.data_ptr(), out.data_ptr(), 0, Bn, N, H, S()))  # lse optional
+    assert relerr(out.float(), ref) < 8e-3
+    assert lib.theia_attention_tc_fwd(qkv.data_ptr(), out.data_ptr(), 0, Bn, 273, H, S()) != 0
+
+
 # ----------------------------------------------------------------------------- packing / reductions
 def test_pack_and_reductions(lib):
     w = rnd(96, 160, seed=1, dtype=torch.float32)

@@ -1,0 +1,42 @@
+"""Host logic of the teacher path (no GPU): the weight conversion of `TeacherViT.from_hf` -- fused q|k|v, DINOv2
+LayerScale folded into the output projections, interpolated position table, padded patch matrix -- replayed through
+a plain fp32 torch restatement of `theia_vit_forward`'s launch sequence (csrc/vit_infer.cu) and compared with the
+HF model.  Only bf16 rounding of the GEMM weights separates the two."""
+import pytest
+import torch
+
+from tests._teacher_util import _build, _randomize, _replay
+
+
+@pytest.mark.parametrize("kind,arch", [("dinov2", (128, 2, 3, 14)), ("clip", (128, 2, 3, 14)), ("vit", (192, 3, 2, 16))])
+def test_weight_conversion_reproduces_the_hf_forward(kind, arch, monkeypatch):
+    from theia_b200 import teachers as T
+    hf = _randomize(_build(kind, arch), seed=4)
+    pv = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        out = hf(pixel_values=pv)
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    # (1) the conversion itself, weights kept in fp32: exact up to summation order
+    with monkeypatch.context() as mp:
+        mp.setattr(T, "_bf16", lambda t, dev: t.detach().float().contiguous())
+        t = T.TeacherViT.from_hf(hf, device="cpu", _convert_only=True)
+    assert t.cfg["tokens"] == 1 + (224 // arch[3]) ** 2 and t.cfg["patch_k"] % 8 == 0
+    with torch.no_grad():
+        hid, pooled = _replay(t, pv)
+    assert rel(hid, out.last_hidden_state) < 1e-4
+    if kind != "vit":  # ViTModel's pooler (dense + tanh) is not used by the reference (vit.py:29)
+        assert rel(pooled, out.pooler_output) < 1e-4
+    # (2) as shipped, GEMM weights rounded to bf16: the rounding alone costs ~1.5e-2 on these deliberately
+    # sensitive (peaky-attention) random weights
+    t = T.TeacherViT.from_hf(hf, device="cpu", _convert_only=True)
+    assert t._layers[0]["w_qkv"].dtype == torch.bfloat16 and t._t["w_patch"].dtype == torch.bfloat16
+    with torch.no_grad():
+        hid, _ = _replay(t, pv)
+    assert rel(hid, out.last_hidden_state) < 3e-2
+
+
+def test_cuda_only():
+    from theia_b200 import _lib as L
+    from theia_b200 import teachers as T
+    with pytest.raises(L.TheiaError, match="CUDA"):
+        T.TeacherViT.from_hf(_build("dinov2", (128, 2, 1, 14)), device="cpu")

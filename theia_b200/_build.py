@@ -12,7 +12,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libtheia_b200.so")
-SOURCES = ["host_util.cu", "gemm_tc.cu", "elementwise.cu", "attention_tc.cu", "model.cu"]
+SOURCES = ["host_util.cu", "gemm_tc.cu", "elementwise.cu", "attention_tc.cu", "model.cu", "vit_infer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

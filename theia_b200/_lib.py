@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("THEIA_B200_LIB") or os.path.join(_PKG, "libtheia_b200
 OP_K2D, OP_MN2D, OP_CONV_K, OP_CONV_MN = 0, 1, 2, 3
 EPI_GELU, EPI_RELU, EPI_RESID, EPI_OUT_F32, EPI_ATOMIC = 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5
 EPI_MUL_AUX, EPI_MUL_RELUMASK, EPI_POSCLS, EPI_STATS, EPI_COLSUM = 1 << 6, 1 << 7, 1 << 8, 1 << 9, 1 << 10
+EPI_GELU_FWD, EPI_QUICK_GELU = 1 << 11, 1 << 12
 MAX_TEACHERS = 8
 
 
@@ -44,6 +45,20 @@ class ModelConfig(C.Structure):
                 ("num_reg_tokens", C.c_int), ("num_teachers", C.c_int),
                 ("teacher_names", C.c_char_p * MAX_TEACHERS), ("teacher_c", C.c_int * MAX_TEACHERS),
                 ("teacher_hw", C.c_int * MAX_TEACHERS)]
+
+
+class VitLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln1_w", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_w", "ln2_b",
+                                          "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+
+
+class VitDesc(C.Structure):
+    _fields_ = [("hidden", C.c_int), ("heads", C.c_int), ("layers", C.c_int), ("mlp", C.c_int),
+                ("tokens", C.c_int), ("patch_off", C.c_int), ("patch_tokens", C.c_int), ("patch_k", C.c_int),
+                ("ln_eps", C.c_float), ("act", C.c_int),
+                ("w_patch", C.c_void_p), ("b_patch", C.c_void_p), ("tok_table", C.c_void_p),
+                ("pre_ln_w", C.c_void_p), ("pre_ln_b", C.c_void_p), ("final_ln_w", C.c_void_p), ("final_ln_b", C.c_void_p),
+                ("final_ln_mode", C.c_int), ("layer", C.POINTER(VitLayer))]
 
 
 # every symbol include/theia_b200.h declares: name -> (restype, argtypes)
@@ -96,6 +111,9 @@ SYMBOLS = {
     "theia_model_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i,
                                  C.POINTER(_vp), _vp, _vp]),
     "theia_model_backward": (_i, [_vp, C.POINTER(_vp), _vp]),
+    "theia_vit_workspace_bytes": (_ll, [C.POINTER(VitDesc), _i]),
+    "theia_vit_forward": (_i, [C.POINTER(VitDesc), _vp, _i, _vp, _vp, _vp, _vp]),
+    "theia_patchify_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -319,6 +319,199 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
 }
 
 
+// --------------------------------------------------------------------------------------------
+// forward for longer sequences (209 .. 272 tokens: the 257-token ViT-L/14 teachers of feature_extraction.py).
+// Same operand handling as above, simpler schedule: one 128-query tile at a time, four softmax warps (one thread per
+// query row, two streaming passes over the 272 score columns in TMEM), Q / K / V single buffered.  The 272-key score
+// row needs two MMAs per k-step (N = 256 + 16: the UMMA N limit is 256).
+//   TMEM: S 0-271 | O 272-335.   warps: 0 TMA, 1 TMEM alloc + MMA issue, 2-5 softmax (quarter = warp % 4).
+// --------------------------------------------------------------------------------------------
+constexpr int AL_ROWS = 272;
+constexpr int AL_TILE = AL_ROWS * 128;
+constexpr int AL_KSTEPS = AL_ROWS / 16;
+constexpr int AL_THREADS = 192;
+constexpr int AL_OFF_P = 3 * AL_TILE;                 // 5 blocks of [128 queries x 64 keys]
+constexpr int AL_OFF_BAR = AL_OFF_P + 5 * 16384;
+constexpr int AL_SMEM = AL_OFF_BAR + 256 + 1024;
+static_assert(AL_TILE % 1024 == 0 && AL_SMEM <= 232448, "attention (long): shared memory");
+
+__global__ void __launch_bounds__(AL_THREADS, 1)
+attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_constant__ CUtensorMap tm16,
+                        const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw_at[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_at) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + AL_TILE;
+  uint8_t* sV = smem + 2 * AL_TILE;
+  uint8_t* sP = smem + AL_OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AL_OFF_BAR);
+  uint64_t* in_full = bars + 0;
+  uint64_t* in_empty = bars + 1;
+  uint64_t* s_full = bars + 2;
+  uint64_t* p_full = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint64_t* t_free = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm256);
+    tma_prefetch_desc(&tm16);
+    mbar_init(in_full, 1);
+    mbar_init(in_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(t_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int D = p.D;
+  const int nqt = (p.N + 127) / 128;
+  const uint32_t T_O = tmem_base + AL_ROWS;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+        const int b = item / p.H, h = item - b * p.H;
+        const int row0 = b * p.N, col0 = h * AT_HD;
+        if (it > 0) mbar_wait(in_empty, (it - 1) & 1);
+        mbar_expect_tx(in_full, 3 * AL_TILE);
+        for (int m = 0; m < 3; ++m) {  // q, k, v column blocks of the fused qkv activation
+          tma_load_2d(&tm256, smem + m * AL_TILE, in_full, m * D + col0, row0);
+          tma_load_2d(&tm16, smem + m * AL_TILE + 256 * 128, in_full, m * D + col0, row0 + 256);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s256 = make_idesc_bf16(128, 256, 0, 0), idesc_s16 = make_idesc_bf16(128, 16, 0, 0);
+    const uint32_t idesc_pv = make_idesc_bf16(128, AT_HD, 0, 1);
+    const uint32_t k_lo = at_desc_lo(smem_u32(sK), 16), k2_lo = at_desc_lo(smem_u32(sK) + 256 * 128, 16);
+    const uint32_t v_lo = at_desc_lo(smem_u32(sV), 8192), p_lo = at_desc_lo(smem_u32(sP), 16);
+    int it = 0, g = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
+      mbar_wait(in_full, it & 1);
+      for (int t = 0; t < nqt; ++t, ++g) {
+        if (g > 0) mbar_wait(t_free, (g - 1) & 1);
+        tc_fence_after();
+        const uint32_t q_lo = at_desc_lo(smem_u32(sQ) + t * 16384, 16);
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc_mma_bf16(tmem_base, at_desc(q_lo + 2 * k), at_desc(k_lo + 2 * k), idesc_s256, k > 0 ? 1u : 0u);
+            tc_mma_bf16(tmem_base + 256, at_desc(q_lo + 2 * k), at_desc(k2_lo + 2 * k), idesc_s16, k > 0 ? 1u : 0u);
+          }
+          tc_commit(s_full);
+        }
+        __syncwarp();
+        mbar_wait(p_full, g & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int ks = 0; ks < AL_KSTEPS; ++ks)
+            tc_mma_bf16(T_O, at_desc(p_lo + (ks >> 2) * 1024 + (ks & 3) * 2), at_desc(v_lo + ks * 128), idesc_pv,
+                        ks > 0 ? 1u : 0u);
+          tc_commit(o_full);
+          if (t == nqt - 1) tc_commit(in_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    const float c2 = p.scale * 1.4426950408889634f;
+    const uint32_t prow = smem_u32(sP) + r * 128;
+    const int sw = r & 7;
+    int g = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int b = item / p.H, h = item - b * p.H;
+      for (int t = 0; t < nqt; ++t, ++g) {
+        const int q = t * 128 + r;
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        float m = -INFINITY;
+        {
+          uint32_t v[2][16];
+          tmem_ld16(trow, v[0]);
+#pragma unroll
+          for (int j = 0; j < AL_KSTEPS; ++j) {
+            tmem_ld_wait();
+            if (j + 1 < AL_KSTEPS) tmem_ld16(trow + (j + 1) * 16, v[(j + 1) & 1]);
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (j * 16 + e < p.N) m = fmaxf(m, __uint_as_float(v[j & 1][e]));
+          }
+        }
+        float l = 0.f;
+        const float mc = m * c2;
+        {
+          uint32_t v[2][16];
+          tmem_ld16(trow, v[0]);
+#pragma unroll
+          for (int j = 0; j < AL_KSTEPS; ++j) {
+            tmem_ld_wait();
+            if (j + 1 < AL_KSTEPS) tmem_ld16(trow + (j + 1) * 16, v[(j + 1) & 1]);
+            float pv[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              pv[e] = (j * 16 + e < p.N) ? ex2_approx_ftz(fmaf(__uint_as_float(v[j & 1][e]), c2, -mc)) : 0.f;
+              l += pv[e];
+            }
+            const uint32_t blk = prow + (j >> 2) * 16384;
+            const int ck = (j & 3) * 2;
+            sts128(blk + ((ck ^ sw) << 4), pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
+                   pack_bf16x2(pv[6], pv[7]));
+            sts128(blk + (((ck + 1) ^ sw) << 4), pack_bf16x2(pv[8], pv[9]), pack_bf16x2(pv[10], pv[11]),
+                   pack_bf16x2(pv[12], pv[13]), pack_bf16x2(pv[14], pv[15]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        mbar_wait(o_full, g & 1);
+        tc_fence_after();
+        uint32_t o[4][16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmem_ld16(trow + AL_ROWS + j * 16, o[j]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_free);
+        if (q < p.N) {
+          const float inv = 1.f / l;
+          bf16* dst = p.out + (static_cast<long long>(b) * p.N + q) * D + h * AT_HD;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              pk[e] = pack_bf16x2(__uint_as_float(o[j][2 * e]) * inv, __uint_as_float(o[j][2 * e + 1]) * inv);
+            *reinterpret_cast<uint4*>(dst + j * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + j * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.N + q] = m * p.scale + __logf(l);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 struct AttnBwdParams {
   const bf16* out;
   const bf16* dout;
@@ -779,8 +972,31 @@ static int encode_qkv_map(CUtensorMap* tm, const void* ptr, long long rows, long
 }
 
 extern "C" int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream) {
-  if (N > AT_ROWS - 0 || N < 1) return set_error(THEIA_ERR_UNSUPPORTED, "attention: sequence length %d > %d", N, AT_ROWS);
+  if (N > AL_ROWS || N < 1) return set_error(THEIA_ERR_UNSUPPORTED, "attention: sequence length %d > %d", N, AL_ROWS);
   const int D = H * AT_HD;
+  if (N > AT_ROWS) {  // 209 .. 272 tokens (ViT-L/14 teachers): the long-sequence forward kernel
+    CUtensorMap t256, t16;
+    int rc2 = encode_qkv_map(&t256, qkv, static_cast<long long>(B) * N, 3LL * D, 256);
+    if (rc2) return rc2;
+    rc2 = encode_qkv_map(&t16, qkv, static_cast<long long>(B) * N, 3LL * D, 16);
+    if (rc2) return rc2;
+    static bool donel = false;
+    if (!donel) {
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
+      if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc fwd long attr: %s", cudaGetErrorString(e));
+      donel = true;
+    }
+    AttnFwdParams pl;
+    pl.out = static_cast<bf16*>(out);
+    pl.lse = lse;
+    pl.B = B, pl.N = N, pl.H = H, pl.D = D;
+    pl.items = B * H;
+    pl.scale = 0.125f;
+    const int gridl = pl.items < num_sms() ? pl.items : num_sms();
+    attn_tc_fwd_long_kernel<<<gridl, AL_THREADS, AL_SMEM, static_cast<cudaStream_t>(stream)>>>(t256, t16, pl);
+    THEIA_CHECK_LAUNCH("attention_tc_fwd_long");
+    return THEIA_OK;
+  }
   CUtensorMap tm;
   int rc = encode_qkv_map(&tm, qkv, static_cast<long long>(B) * N, 3LL * D);
   if (rc) return rc;

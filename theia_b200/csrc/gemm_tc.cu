@@ -517,6 +517,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           store_bf16_row(reinterpret_cast<bf16*>(p.out2));
         }
+        if (epi & THEIA_EPI_GELU_FWD) {  // inference: gelu(x) = x Phi(x), no derivative output
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float xs[16], cdf[16], pdf[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) xs[k] = xv[16 * hh + k];
+            normal_cdf_pdf<16, false>(xs, cdf, pdf);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) xv[16 * hh + k] = xs[k] * cdf[k];
+          }
+        }
+        if (epi & THEIA_EPI_QUICK_GELU) {  // x sigmoid(1.702 x)  (hf:activations.py QuickGELUActivation; CLIP)
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            xv[k] = xv[k] * rcp_approx(1.0f + ex2_approx(xv[k] * (-1.702f * 1.4426950408889634f)));
+        }
         if (epi & THEIA_EPI_RELU) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) xv[k] = fmaxf(xv[k], 0.f);
@@ -723,6 +739,8 @@ static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK&
     THEIA_EPI_CASE(THEIA_EPI_POSCLS)
     THEIA_EPI_CASE(THEIA_EPI_STATS)
     THEIA_EPI_CASE(THEIA_EPI_RELU | THEIA_EPI_STATS)
+    THEIA_EPI_CASE(THEIA_EPI_GELU_FWD)
+    THEIA_EPI_CASE(THEIA_EPI_QUICK_GELU)
 #undef THEIA_EPI_CASE
     default:
       return launch<BN, -1, PAIR>(tmA, tmB, k, stream);
