@@ -447,7 +447,8 @@ def test_attention_fwd_bwd(lib, Bn, H):
         assert relerr(got[:, i], g[:, i]) < 1.5e-2, nm
 
 
-@pytest.mark.parametrize("Bn,H,N", [(2, 16, 257), (20, 16, 257), (3, 12, 272), (2, 4, 209), (5, 16, 256)])
+@pytest.mark.parametrize("Bn,H,N", [(2, 16, 257), (40, 16, 257), (3, 12, 272), (2, 4, 209), (5, 16, 256),
+                                    (11, 16, 258), (3, 6, 259)])  # 257 / 258: tail rows on the CUDA cores; 259: a third tile
 def test_attention_fwd_long_sequences(lib, Bn, H, N):
     """209..272 tokens: the 257-token (ViT-L/14 at 224) teacher forward (feature_extraction.py); forward only"""
     D = H * 64

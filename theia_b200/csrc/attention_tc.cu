@@ -321,20 +321,28 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
 
 // --------------------------------------------------------------------------------------------
 // forward for longer sequences (209 .. 272 tokens: the 257-token ViT-L/14 teachers of feature_extraction.py).
-// Same operand handling as above, simpler schedule: one 128-query tile at a time, four softmax warps (one thread per
-// query row, two streaming passes over the 272 score columns in TMEM), Q / K / V single buffered.  The 272-key score
-// row needs two MMAs per k-step (N = 256 + 16: the UMMA N limit is 256).
-//   TMEM: S 0-271 | O 272-335.   warps: 0 TMA, 1 TMEM alloc + MMA issue, 2-5 softmax (quarter = warp % 4).
+// Same operand handling as above, simpler schedule: one 128-query tile at a time, a single 272-column score buffer
+// (two MMAs per k-step, N = 256 + 16: the UMMA N limit is 256), Q / K / V single buffered (V on its own barrier: it is
+// not needed before the first P V).  Softmax: two warps per TMEM lane quarter, each owning half of the 17 column
+// chunks (9 / 8), two streaming passes over TMEM (row max, then exp / sum / bf16 P blocks to shared memory), row max
+// and row sum exchanged through shared memory with a 64-thread named barrier.  The MMA warp issues S of the next
+// query tile right behind P V of the current one (the score buffer is free once P is written), so the tensor pipe
+// works under the output epilogue.
+//   TMEM: S 0-271 | O 272-335.   warps: 0 TMA, 1 TMEM alloc + MMA issue, 2-9 softmax (quarter = warp % 4).
 // --------------------------------------------------------------------------------------------
 constexpr int AL_ROWS = 272;
 constexpr int AL_TILE = AL_ROWS * 128;
 constexpr int AL_KSTEPS = AL_ROWS / 16;
-constexpr int AL_THREADS = 192;
+constexpr int AL_THREADS = 320;
 constexpr int AL_OFF_P = 3 * AL_TILE;                 // 5 blocks of [128 queries x 64 keys]
-constexpr int AL_OFF_BAR = AL_OFF_P + 5 * 16384;
+constexpr int AL_OFF_X = AL_OFF_P + 5 * 16384;        // row max / row sum exchange: [2 kinds][2 halves][128] fp32
+constexpr int AL_OFF_T = AL_OFF_X + 2048;             // tail rows: scores / probabilities [272], reductions [32], partial outputs [8][64]
+constexpr int AL_OFF_BAR = AL_OFF_T + 4096;
+constexpr int AL_TAIL_MAX = 2;  // up to this many rows beyond the last full 128-query tile go through the CUDA-core path
 constexpr int AL_SMEM = AL_OFF_BAR + 256 + 1024;
 static_assert(AL_TILE % 1024 == 0 && AL_SMEM <= 232448, "attention (long): shared memory");
 
+template <int NFIX>
 __global__ void __launch_bounds__(AL_THREADS, 1)
 attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_constant__ CUtensorMap tm16,
                         const AttnFwdParams p) {
@@ -345,23 +353,25 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
   uint8_t* sV = smem + 2 * AL_TILE;
   uint8_t* sP = smem + AL_OFF_P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AL_OFF_BAR);
-  uint64_t* in_full = bars + 0;
-  uint64_t* in_empty = bars + 1;
-  uint64_t* s_full = bars + 2;
-  uint64_t* p_full = bars + 3;
-  uint64_t* o_full = bars + 4;
-  uint64_t* t_free = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* qk_full = bars + 0;
+  uint64_t* v_full = bars + 1;
+  uint64_t* in_empty = bars + 2;
+  uint64_t* s_full = bars + 3;
+  uint64_t* p_full = bars + 4;
+  uint64_t* o_full = bars + 5;
+  uint64_t* t_free = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm256);
     tma_prefetch_desc(&tm16);
-    mbar_init(in_full, 1);
-    mbar_init(in_empty, 1);
+    mbar_init(qk_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(in_empty, 1 + 8);  // tcgen05.commit of the last P V + the 8 softmax warps (tail rows read Q / K / V)
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(o_full, 1);
-    mbar_init(t_free, 4);
+    mbar_init(t_free, 8);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -373,7 +383,13 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int D = p.D;
-  const int nqt = (p.N + 127) / 128;
+  const int N = NFIX ? NFIX : p.N;
+  // query rows beyond the last full tile: one or two (the 257-token case: 2 x 128 + 1) are computed by the softmax
+  // warps on the CUDA cores from the shared-memory tiles while P V of the last tile runs -- a third tensor-core
+  // tile for a single row would cost as much as a full one.  More rows than that get a regular (partial) tile.
+  const int nfull = N / 128;
+  const int ntail = (nfull > 0 && N - nfull * 128 <= AL_TAIL_MAX) ? N - nfull * 128 : 0;
+  const int nqt = ntail ? nfull : (N + 127) / 128;
   const uint32_t T_O = tmem_base + AL_ROWS;
 
   if (warp == 0) {
@@ -381,13 +397,16 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
       int it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const int b = item / p.H, h = item - b * p.H;
-        const int row0 = b * p.N, col0 = h * AT_HD;
+        const int row0 = b * N, col0 = h * AT_HD;
         if (it > 0) mbar_wait(in_empty, (it - 1) & 1);
-        mbar_expect_tx(in_full, 3 * AL_TILE);
-        for (int m = 0; m < 3; ++m) {  // q, k, v column blocks of the fused qkv activation
-          tma_load_2d(&tm256, smem + m * AL_TILE, in_full, m * D + col0, row0);
-          tma_load_2d(&tm16, smem + m * AL_TILE + 256 * 128, in_full, m * D + col0, row0 + 256);
+        mbar_expect_tx(qk_full, 2 * AL_TILE);
+        for (int m = 0; m < 2; ++m) {  // q, k column blocks of the fused qkv activation
+          tma_load_2d(&tm256, smem + m * AL_TILE, qk_full, m * D + col0, row0);
+          tma_load_2d(&tm16, smem + m * AL_TILE + 256 * 128, qk_full, m * D + col0, row0 + 256);
         }
+        mbar_expect_tx(v_full, AL_TILE);
+        tma_load_2d(&tm256, sV, v_full, 2 * D + col0, row0);
+        tma_load_2d(&tm16, sV + 256 * 128, v_full, 2 * D + col0, row0 + 256);
       }
     }
   } else if (warp == 1) {
@@ -395,23 +414,28 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
     const uint32_t idesc_pv = make_idesc_bf16(128, AT_HD, 0, 1);
     const uint32_t k_lo = at_desc_lo(smem_u32(sK), 16), k2_lo = at_desc_lo(smem_u32(sK) + 256 * 128, 16);
     const uint32_t v_lo = at_desc_lo(smem_u32(sV), 8192), p_lo = at_desc_lo(smem_u32(sP), 16);
+    const uint32_t q_lo0 = at_desc_lo(smem_u32(sQ), 16);
+    auto issue_s = [&](int t) {  // S = Q_t K^T into TMEM columns 0-271
+      const uint32_t q_lo = q_lo0 + t * 1024;
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          tc_mma_bf16(tmem_base, at_desc(q_lo + 2 * k), at_desc(k_lo + 2 * k), idesc_s256, k > 0 ? 1u : 0u);
+          tc_mma_bf16(tmem_base + 256, at_desc(q_lo + 2 * k), at_desc(k2_lo + 2 * k), idesc_s16, k > 0 ? 1u : 0u);
+        }
+        tc_commit(s_full);
+      }
+      __syncwarp();
+    };
     int it = 0, g = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
-      mbar_wait(in_full, it & 1);
+      mbar_wait(qk_full, it & 1);
+      tc_fence_after();
+      issue_s(0);  // every softmax read of the previous item's last S finished before its p_full, waited below
       for (int t = 0; t < nqt; ++t, ++g) {
-        if (g > 0) mbar_wait(t_free, (g - 1) & 1);
-        tc_fence_after();
-        const uint32_t q_lo = at_desc_lo(smem_u32(sQ) + t * 16384, 16);
-        if (elect_one_sync()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc_mma_bf16(tmem_base, at_desc(q_lo + 2 * k), at_desc(k_lo + 2 * k), idesc_s256, k > 0 ? 1u : 0u);
-            tc_mma_bf16(tmem_base + 256, at_desc(q_lo + 2 * k), at_desc(k2_lo + 2 * k), idesc_s16, k > 0 ? 1u : 0u);
-          }
-          tc_commit(s_full);
-        }
-        __syncwarp();
-        mbar_wait(p_full, g & 1);
+        mbar_wait(p_full, g & 1);                   // P_t in shared memory, S buffer free
+        if (t == 0) mbar_wait(v_full, it & 1);
+        if (g > 0) mbar_wait(t_free, (g - 1) & 1);  // O of the previous tile has been read
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
@@ -422,15 +446,19 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
           if (t == nqt - 1) tc_commit(in_empty);
         }
         __syncwarp();
+        if (t + 1 < nqt) issue_s(t + 1);
       }
     }
   } else {
-    const int wq = warp & 3;
+    const int wq = warp & 3, hh = (warp - 2) >> 2;
     const int r = wq * 32 + lane;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     const float c2 = p.scale * 1.4426950408889634f;
     const uint32_t prow = smem_u32(sP) + r * 128;
     const int sw = r & 7;
+    float* xmax = reinterpret_cast<float*>(smem + AL_OFF_X);  // [2][128]
+    float* xsum = xmax + 256;
+    const int j0 = hh ? 9 : 0, j1 = hh ? AL_KSTEPS : 9;
     int g = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int b = item / p.H, h = item - b * p.H;
@@ -441,57 +469,148 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
         float m = -INFINITY;
         {
           uint32_t v[2][16];
-          tmem_ld16(trow, v[0]);
+          tmem_ld16(trow + j0 * 16, v[0]);
 #pragma unroll
-          for (int j = 0; j < AL_KSTEPS; ++j) {
-            tmem_ld_wait();
-            if (j + 1 < AL_KSTEPS) tmem_ld16(trow + (j + 1) * 16, v[(j + 1) & 1]);
+          for (int jj = 0; jj < 9; ++jj) {
+            const int j = j0 + jj;
+            if (j < j1) {
+              tmem_ld_wait();
+              if (j + 1 < j1) tmem_ld16(trow + (j + 1) * 16, v[(jj + 1) & 1]);
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (j * 16 + e < p.N) m = fmaxf(m, __uint_as_float(v[j & 1][e]));
+              for (int e = 0; e < 16; ++e)
+                if (j * 16 + e < N) m = fmaxf(m, __uint_as_float(v[jj & 1][e]));
+            }
           }
         }
+        xmax[hh * 128 + r] = m;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");
+        m = fmaxf(m, xmax[(hh ^ 1) * 128 + r]);
         float l = 0.f;
         const float mc = m * c2;
         {
           uint32_t v[2][16];
-          tmem_ld16(trow, v[0]);
+          tmem_ld16(trow + j0 * 16, v[0]);
 #pragma unroll
-          for (int j = 0; j < AL_KSTEPS; ++j) {
-            tmem_ld_wait();
-            if (j + 1 < AL_KSTEPS) tmem_ld16(trow + (j + 1) * 16, v[(j + 1) & 1]);
-            float pv[16];
+          for (int jj = 0; jj < 9; ++jj) {
+            const int j = j0 + jj;
+            if (j < j1) {
+              tmem_ld_wait();
+              if (j + 1 < j1) tmem_ld16(trow + (j + 1) * 16, v[(jj + 1) & 1]);
+              float pv[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              pv[e] = (j * 16 + e < p.N) ? ex2_approx_ftz(fmaf(__uint_as_float(v[j & 1][e]), c2, -mc)) : 0.f;
-              l += pv[e];
+              for (int e = 0; e < 16; ++e) {
+                pv[e] = (j * 16 + e < N) ? ex2_approx_ftz(fmaf(__uint_as_float(v[jj & 1][e]), c2, -mc)) : 0.f;
+                l += pv[e];
+              }
+              const uint32_t blk = prow + (j >> 2) * 16384;
+              const int ck = (j & 3) * 2;
+              sts128(blk + ((ck ^ sw) << 4), pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
+                     pack_bf16x2(pv[6], pv[7]));
+              sts128(blk + (((ck + 1) ^ sw) << 4), pack_bf16x2(pv[8], pv[9]), pack_bf16x2(pv[10], pv[11]),
+                     pack_bf16x2(pv[12], pv[13]), pack_bf16x2(pv[14], pv[15]));
             }
-            const uint32_t blk = prow + (j >> 2) * 16384;
-            const int ck = (j & 3) * 2;
-            sts128(blk + ((ck ^ sw) << 4), pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
-                   pack_bf16x2(pv[6], pv[7]));
-            sts128(blk + (((ck + 1) ^ sw) << 4), pack_bf16x2(pv[8], pv[9]), pack_bf16x2(pv[10], pv[11]),
-                   pack_bf16x2(pv[12], pv[13]), pack_bf16x2(pv[14], pv[15]));
           }
         }
+        xsum[hh * 128 + r] = l;
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        if (t == nqt - 1) {  // last tile of the item: tail rows, then release Q / K / V
+          for (int tr = 0; tr < ntail; ++tr) {
+            const int qrow = nfull * 128 + tr;
+            const int tid = threadIdx.x - 64, tw = tid >> 5;
+            float* ts = reinterpret_cast<float*>(smem + AL_OFF_T);  // [272] raw scores, then probabilities
+            float* red = ts + 272;                                  // [0,8) warp maxima, [8,16) warp sums
+            float* part = ts + 320;                                 // [8][64] partial outputs
+            float qf[64];
+            {
+              const uint32_t qa = smem_u32(sQ) + qrow * 128;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 u = lds128(qa + ((c ^ (qrow & 7)) << 4));
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_bf16x2(w4[e]);
+                  qf[c * 8 + 2 * e] = f.x, qf[c * 8 + 2 * e + 1] = f.y;
+                }
+              }
+            }
+            auto score = [&](int j) {
+              const uint32_t ka = smem_u32(sK) + j * 128;
+              float acc = 0.f;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 u = lds128(ka + ((c ^ (j & 7)) << 4));
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_bf16x2(w4[e]);
+                  acc = fmaf(qf[c * 8 + 2 * e], f.x, acc);
+                  acc = fmaf(qf[c * 8 + 2 * e + 1], f.y, acc);
+                }
+              }
+              return acc;
+            };
+            const float s0 = score(tid);  // keys 0 .. 255 (N >= 256 here)
+            const bool two = 256 + tid < N;
+            const float s1 = two ? score(256 + tid) : -INFINITY;
+            const float wm = warp_max(fmaxf(s0, s1));
+            if (lane == 0) red[tw] = wm;
+            asm volatile("bar.sync 5, 256;" ::: "memory");
+            float tm = red[0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) tm = fmaxf(tm, red[k]);
+            const float tmc = tm * c2;
+            const float p0 = ex2_approx_ftz(fmaf(s0, c2, -tmc));
+            const float p1 = two ? ex2_approx_ftz(fmaf(s1, c2, -tmc)) : 0.f;
+            ts[tid] = p0;
+            if (two) ts[256 + tid] = p1;
+            const float wsum = warp_sum(p0 + p1);
+            if (lane == 0) red[8 + tw] = wsum;
+            asm volatile("bar.sync 5, 256;" ::: "memory");
+            float tl = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tl += red[8 + k];
+            // out[d] = sum_j p_j V[j][d]: warp tw takes keys tw, tw + 8, ...; lane = dimension pair
+            float a0 = 0.f, a1 = 0.f;
+            const uint32_t va = smem_u32(sV) + (lane & 3) * 4;
+            for (int j = tw; j < N; j += 8) {
+              const float2 f = unpack_bf16x2(lds32(va + j * 128 + (((lane >> 2) ^ (j & 7)) << 4)));
+              const float pj = ts[j];
+              a0 = fmaf(pj, f.x, a0), a1 = fmaf(pj, f.y, a1);
+            }
+            part[tw * 64 + 2 * lane] = a0, part[tw * 64 + 2 * lane + 1] = a1;
+            asm volatile("bar.sync 5, 256;" ::: "memory");
+            if (tid < 64) {
+              float o = 0.f;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) o += part[k * 64 + tid];
+              p.out[(static_cast<long long>(b) * N + qrow) * D + h * AT_HD + tid] = __float2bfloat16(o / tl);
+              if (tid == 0 && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * N + qrow] = tm * p.scale + __logf(tl);
+            }
+            asm volatile("bar.sync 5, 256;" ::: "memory");  // ts / red / part are reused by the next tail row / item
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(in_empty);
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");  // the other half's row sum is in xsum
         mbar_wait(o_full, g & 1);
         tc_fence_after();
-        uint32_t o[4][16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tmem_ld16(trow + AL_ROWS + j * 16, o[j]);
+        uint32_t o[2][16];
+        tmem_ld16(trow + AL_ROWS + hh * 32, o[0]);
+        tmem_ld16(trow + AL_ROWS + hh * 32 + 16, o[1]);
         tmem_ld_wait();
+        l += xsum[(hh ^ 1) * 128 + r];
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(t_free);
-        if (q < p.N) {
+        if (q < N) {
           const float inv = 1.f / l;
-          bf16* dst = p.out + (static_cast<long long>(b) * p.N + q) * D + h * AT_HD;
+          bf16* dst = p.out + (static_cast<long long>(b) * N + q) * D + h * AT_HD + hh * 32;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             uint32_t pk[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e)
@@ -499,7 +618,7 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
             *reinterpret_cast<uint4*>(dst + j * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(dst + j * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          if (p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * p.N + q] = m * p.scale + __logf(l);
+          if (hh == 0 && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * N + q] = m * p.scale + __logf(l);
         }
       }
     }
@@ -982,7 +1101,9 @@ extern "C" int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, in
     if (rc2) return rc2;
     static bool donel = false;
     if (!donel) {
-      cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
+      cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel<257>, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
       if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc fwd long attr: %s", cudaGetErrorString(e));
       donel = true;
     }
@@ -993,7 +1114,10 @@ extern "C" int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, in
     pl.items = B * H;
     pl.scale = 0.125f;
     const int gridl = pl.items < num_sms() ? pl.items : num_sms();
-    attn_tc_fwd_long_kernel<<<gridl, AL_THREADS, AL_SMEM, static_cast<cudaStream_t>(stream)>>>(t256, t16, pl);
+    if (N == 257)  // CLS + 16 x 16 patches: compile-time length (the key masks fold away)
+      attn_tc_fwd_long_kernel<257><<<gridl, AL_THREADS, AL_SMEM, static_cast<cudaStream_t>(stream)>>>(t256, t16, pl);
+    else
+      attn_tc_fwd_long_kernel<0><<<gridl, AL_THREADS, AL_SMEM, static_cast<cudaStream_t>(stream)>>>(t256, t16, pl);
     THEIA_CHECK_LAUNCH("attention_tc_fwd_long");
     return THEIA_OK;
   }

@@ -1,10 +1,11 @@
-"""Attention micro-benchmark: python tools/bench_attn.py B H"""
+"""Attention micro-benchmark: python tools/bench_attn.py B H [N]   (N > 208: forward only, the teacher kernel)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from theia_b200 import _lib as L
 B, H = int(sys.argv[1]), int(sys.argv[2])
-N, D = 197, H * 64
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 197
+D = H * 64
 lib = L.lib()
 qkv = torch.randn(B * N, 3 * D, device="cuda").to(torch.bfloat16)
 out = torch.empty(B * N, D, dtype=torch.bfloat16, device="cuda")
@@ -21,10 +22,8 @@ def timeit(fn, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 fl = 4.0 * N * N * 64 * B * H
-for name in ("theia_attention_tc_fwd",):
-    ms = timeit(lambda: L.check(getattr(lib, name)(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, s)))
-    print(f"{name}: {ms:.4f} ms  {fl/ms/1e9:.1f} TFLOP/s (algorithmic)")
-for name in ("theia_attention_tc_bwd",):
-    if not hasattr(lib, name): continue
-    ms = timeit(lambda: L.check(getattr(lib, name)(qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, N, H, s)))
-    print(f"{name}: {ms:.4f} ms  {2.5*fl/ms/1e9:.1f} TFLOP/s (algorithmic, 2.5x fwd)")
+ms = timeit(lambda: L.check(lib.theia_attention_tc_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, s)))
+print(f"theia_attention_tc_fwd N={N}: {ms:.4f} ms  {fl/ms/1e9:.1f} TFLOP/s (algorithmic)")
+if N <= 208:
+    ms = timeit(lambda: L.check(lib.theia_attention_tc_bwd(qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, N, H, s)))
+    print(f"theia_attention_tc_bwd N={N}: {ms:.4f} ms  {2.5*fl/ms/1e9:.1f} TFLOP/s (algorithmic, 2.5x fwd)")
