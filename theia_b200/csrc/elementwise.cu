@@ -30,58 +30,77 @@ __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
 // ============================================================================================
 // Row LayerNorm.  One warp per row, D <= 1024, D % 8 == 0.  Two-pass statistics in registers.
 // ============================================================================================
-constexpr int LN_MAXC = 4;  // chunks of 8 per lane: D <= 32*8*4 = 1024
-
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, bf16* __restrict__ y,
-                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                            int M, int D, float eps) {
+// NCH = 16-byte chunks per lane (D <= 256 NCH), R = consecutive rows per warp: a warp keeps R rows in flight so that
+// narrow rows (D = 192: 384 B) still put enough bytes on the wire per SM to cover HBM latency
+template <int NCH, int R>
+__global__ void __launch_bounds__(256, 4)
+layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
+                     float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
+  const int row0 = warp * R;
+  if (row0 >= M) return;
   const int nch = D >> 3;
-  const bf16* xr = x + static_cast<long long>(warp) * D;
-  float v[LN_MAXC][8];
-  float s = 0.f;
+  uint4 raw[R][NCH];  // the rows stay packed (bf16) in registers; unpacked on the fly by each pass
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nch) {
-      load8(xr + ch * 8, v[c]);
+  for (int r = 0; r < R; ++r) {
+    const bf16* xr = x + static_cast<long long>(row0 + r) * D;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s += v[c][e];
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      raw[r][c] = make_uint4(0u, 0u, 0u, 0u);
+      if (ch < nch && row0 + r < M) raw[r][c] = *reinterpret_cast<const uint4*>(xr + ch * 8);
     }
   }
-  const float mean = warp_sum(s) / D;
-  float ss = 0.f;
+  auto unpack8 = [](const uint4& u, float (&f)[8]) {
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x, f[1] = a.y, f[2] = b.x, f[3] = b.y, f[4] = c.x, f[5] = c.y, f[6] = d.x, f[7] = d.y;
+  };
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nch) {
+  for (int r = 0; r < R; ++r) {
+    if (row0 + r >= M) break;
+    float s = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = v[c][e] - mean;
-        ss += d * d;
+    for (int c = 0; c < NCH; ++c) {  // chunks beyond the row are zero: no effect on the sum
+      float f[8];
+      unpack8(raw[r][c], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += f[e];
+    }
+    const float mean = warp_sum(s) / D;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (lane + 32 * c < nch) {
+        float f[8];
+        unpack8(raw[r][c], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = f[e] - mean;
+          ss += d * d;
+        }
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
-  bf16* yr = y + static_cast<long long>(warp) * D;
+    const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+    bf16* yr = y + static_cast<long long>(row0 + r) * D;
 #pragma unroll
-  for (int c = 0; c < LN_MAXC; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nch) {
-      float g[8], b[8], o[8];
-      load8f(gamma + ch * 8, g);
-      load8f(beta + ch * 8, b);
+    for (int c = 0; c < NCH; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        float f[8], g[8], b[8], o[8];
+        unpack8(raw[r][c], f);
+        load8f(gamma + ch * 8, g);
+        load8f(beta + ch * 8, b);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (v[c][e] - mean) * rstd * g[e] + b[e];
-      store8(yr + ch * 8, o);
+        for (int e = 0; e < 8; ++e) o[e] = (f[e] - mean) * rstd * g[e] + b[e];
+        store8(yr + ch * 8, o);
+      }
     }
-  }
-  if (lane == 0) {
-    if (mean_out) mean_out[warp] = mean;
-    if (rstd_out) rstd_out[warp] = rstd;
+    if (lane == 0) {
+      if (mean_out) mean_out[row0 + r] = mean;
+      if (rstd_out) rstd_out[row0 + r] = rstd;
+    }
   }
 }
 
@@ -102,8 +121,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// resident blocks per SM: narrow rows need more warps in flight (a warp works on one row at a time)
+constexpr int lnb_blocks_per_sm(int nch) { return nch == 1 ? 2 : 1; }
+
 template <int NCH, int LNB_STAGES>
-__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
+__global__ void __launch_bounds__(LNB_WARPS * 32, lnb_blocks_per_sm(NCH))
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const bf16* __restrict__ dadd, bf16* __restrict__ dx, float* __restrict__ dgamma,
@@ -995,8 +1017,14 @@ extern "C" int theia_layernorm_fwd(const void* x, const float* gamma, const floa
   if (D % 8 != 0 || D > 1024) return set_error(THEIA_ERR_ARG, "layernorm: D %% 8 == 0 and D <= 1024 required");
   if (M <= 0) return THEIA_OK;
   const int wpb = 8;
-  layernorm_fwd_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, S(stream)>>>(
-      static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y), mean, rstd, M, D, eps);
+#define LNF(NCH, R)                                                                                             \
+  layernorm_fwd_kernel<NCH, R><<<((M + R - 1) / R + wpb - 1) / wpb, wpb * 32, 0, S(stream)>>>(                  \
+      static_cast<const bf16*>(x), gamma, beta, static_cast<bf16*>(y), mean, rstd, M, D, eps)
+  if (D <= 256) LNF(1, 4);
+  else if (D <= 512) LNF(2, 2);
+  else if (D <= 768) LNF(3, 1);
+  else LNF(4, 1);
+#undef LNF
   THEIA_CHECK_LAUNCH("layernorm_fwd");
   return THEIA_OK;
 }
@@ -1006,7 +1034,7 @@ extern "C" int theia_layernorm_bwd(const void* dy, const void* x, const float* g
                                    float* dxsum, int M, int D, void* stream) {
   if (D % 8 != 0 || D > 1024) return set_error(THEIA_ERR_ARG, "layernorm: D %% 8 == 0 and D <= 1024 required");
   if (M <= 0) return THEIA_OK;
-  int grid = num_sms();  // one persistent block per SM
+  int grid = num_sms() * lnb_blocks_per_sm(D <= 256 ? 1 : (D <= 512 ? 2 : 3));  // persistent blocks
   if (grid > (M + LNB_WARPS - 1) / LNB_WARPS) grid = (M + LNB_WARPS - 1) / LNB_WARPS;
   if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dadd)) & 15)
     return set_error(THEIA_ERR_ARG, "layernorm_bwd: dy / x / dadd must be 16-byte aligned");
