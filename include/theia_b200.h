@@ -142,6 +142,14 @@ int theia_loss_bwd(const float* pred, const void* target, int target_is_bf16, co
  * bf16 patch rows [B*197, 768] (row b*197 is the zero CLS slot; column = c*256 + i*16 + j) */
 int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_first, int do_resize, int do_rescale,
                      int do_normalize, const float* mean3, const float* std3, int tokens, int patch_off, void* stream);
+/* the same for images of any extent (the reference's processor accepts whatever the caller has): do_resize != 0
+ * resizes in_h x in_w -> 256 x 256 (bicubic antialias; 1 / 2 = float / fixed-point arithmetic as above) and crops the
+ * centre 224; do_resize == 0 crops the centre 224 x 224, zero-padding images that are smaller
+ * (hf:image_processing_backends.py center_crop).  224 x 224 inputs take the kernels of theia_preprocess.  The per-axis
+ * tap tables are built on the first use of an extent (one cudaMalloc per new extent, cached per device). */
+int theia_preprocess_hw(const uint8_t* images, int in_h, int in_w, void* patches, int B, int channels_first, int do_resize,
+                        int do_rescale, int do_normalize, const float* mean3, const float* std3, int tokens, int patch_off,
+                        void* stream);
 /* test hook for the byte stage: resized_u8_out != NULL -> following do_resize calls also write the resized +
  * centre-cropped uint8 image [B,224,224,3] (what tvF.resize(..., antialias=True) + center_crop give the reference) */
 int theia_preprocess_debug_u8(void* resized_u8_out);
@@ -249,6 +257,8 @@ int theia_model_pack(theia_model* m, int skip_linear_cast, void* stream);
 /* device pointers of the pack table (one int per 64 floats of the flat parameter buffer) and of the bf16 pack
  * buffer, valid after theia_model_bind */
 int theia_model_pack_table(theia_model* m, const int** table, void** packbf);
+/* extent of the image batches handed to theia_model_forward from now on (default 224 x 224; see theia_preprocess_hw) */
+int theia_model_set_input_size(theia_model* m, int height, int width);
 int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channels_first, int do_resize,
                         int do_rescale, int do_normalize, const float* mean3, const float* std3, int run_heads, float* const* preds,
                         void* tokens_bf16_out, void* stream);

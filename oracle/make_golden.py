@@ -123,6 +123,8 @@ def main():
         print(f"{name}: oracle==reference (worst grad rel {worst:.2e}); main_loss {float(ml):.6f} -> {out} "
               f"({os.path.getsize(out) / 1024:.0f} KiB)")
 
+    if not only or "tiny_anysize" in only:
+        anysize(RobotVisionFM)
     if only and "readme_zeros" not in only:
         return
     # README quick-start (BASELINE config #1): zeros image through deit-tiny forward_feature
@@ -141,6 +143,40 @@ def main():
     torch.save({"case": "readme_zeros", "feature": summarize(f)},
                os.path.join(os.path.dirname(HERE), "tests", "golden", "readme_zeros.pt"))
     print("readme_zeros ok", tuple(f.shape))
+
+
+ANYSIZE = [  # (H, W, do_resize): the processor resizes to 256 x 256 and / or centre-crops / zero-pads to 224 x 224
+    (300, 240, True), (160, 200, True), (480, 640, True), (160, 200, False), (256, 320, False), (200, 300, False),
+]
+
+
+def anysize_images(H, W, B=2):
+    return torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(H * 1000 + W))
+
+
+def anysize(RobotVisionFM):
+    """images of other extents than 224 x 224 through the reference's forward_feature (CPU uint8 tensors: torchvision's
+    fixed-point resize); the oracle must agree, the summaries become tests/golden/anysize_tiny.pt"""
+    cfg = O.make_config("facebook/deit-tiny-patch16-224", "dinov2")
+    P = O.init_params(cfg, seed=0)
+    ref = RobotVisionFM(backbone="facebook/deit-tiny-patch16-224", pretrained=False, translator="lconv",
+                        target_feature_sizes=dict(cfg.teachers), translator_kwargs={"hidden_size_factor": 1.0})
+    ref.load_state_dict(P)
+    ref.eval()
+    out = []
+    for H, W, do_resize in ANYSIZE:
+        x = anysize_images(H, W)
+        with torch.no_grad():
+            f = ref.forward_feature(x, do_resize=do_resize, interpolate_pos_encoding=True)
+            f2 = ref.forward_feature(x, do_resize=do_resize)
+        assert torch.equal(f, f2) and tuple(f.shape) == (2, 196, 192)  # the flag is the identity on this path
+        fo = O.forward_feature(P, x, cfg, do_resize=do_resize)
+        torch.testing.assert_close(fo, f, rtol=1e-4, atol=1e-5)
+        out.append({"H": H, "W": W, "do_resize": do_resize, "feature": summarize(f)})
+        print(f"anysize {H}x{W} do_resize={do_resize}: oracle == reference, |f| = {float(f.abs().mean()):.4f}")
+    path = os.path.join(os.path.dirname(HERE), "tests", "golden", "anysize_tiny.pt")
+    torch.save({"case": "tiny_anysize", "cases": out}, path)
+    print("->", path, f"({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
 if __name__ == "__main__":

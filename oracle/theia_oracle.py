@@ -229,9 +229,11 @@ def preprocess(x, do_resize=True, do_rescale=True, do_normalize=True,
         from torchvision.transforms.v2 import functional as tvF
         x = tvF.resize(x, [256, 256], interpolation=tvF.InterpolationMode.BICUBIC, antialias=True)
     H, W = x.shape[-2:]
-    if H != 224 or W != 224:  # center_crop is applied regardless of do_resize
-        if H < 224 or W < 224:
-            raise ValueError("oracle: images smaller than the crop are not restated")
+    if H != 224 or W != 224:  # center_crop is applied regardless of do_resize (image_processing_backends.py center_crop)
+        if H < 224 or W < 224:  # smaller than the crop: zero padding, split (n // 2, (n + 1) // 2) per axis
+            ph, pw = max(224 - H, 0), max(224 - W, 0)
+            x = torch.nn.functional.pad(x, (pw // 2, (pw + 1) // 2, ph // 2, (ph + 1) // 2), value=0)
+            H, W = x.shape[-2:]
         top, left = int((H - 224) / 2.0), int((W - 224) / 2.0)
         x = x[..., top:top + 224, left:left + 224]
     if do_normalize:

@@ -421,6 +421,52 @@ def test_resize_byte_stage_exact(lib, chw):
           f"differ, max {int(diff.max())} levels (both reproduced bit for bit)")
 
 
+@pytest.mark.parametrize("H,W,chw", [(300, 240, 0), (160, 200, 1), (480, 640, 0), (256, 100, 0), (1000, 700, 1), (17, 33, 0),
+                                     (224, 320, 0), (231, 224, 1)])
+def test_resize_any_extent_byte_stage_exact(lib, H, W, chw):
+    """A1 for images of any extent (theia_preprocess_hw): the byte stage -- resize H x W -> 256 x 256 (up- and
+    down-sampling: the tap support widens with the scale), centre crop 224 -- equals torchvision bit for bit, in float
+    arithmetic (CUDA tensors) and in fixed point (CPU uint8 tensors); without resize: centre crop / zero padding as
+    hf center_crop does it."""
+    import torchvision.transforms.v2.functional as tvF
+    from oracle import theia_oracle as O
+    Bn = 2
+    g = torch.Generator().manual_seed(H * 7 + W)
+    img = torch.randint(0, 256, (Bn, H, W, 3), dtype=torch.uint8, generator=g)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    img[1] = ((yy[..., None] // 9 + xx[..., None] // 5) % 2 * 255).to(torch.uint8)  # hard edges: clamp + rounding
+    nchw = img.permute(0, 3, 1, 2).contiguous()
+    d = (nchw if chw else img).to(DEV)
+    dbg = torch.zeros(Bn, 224, 224, 3, dtype=torch.uint8, device=DEV)
+    out = torch.empty(Bn * 197, 768, dtype=torch.bfloat16, device=DEV)
+    mean, std = (C.c_float * 3)(*O.IMAGE_MEAN), (C.c_float * 3)(*O.IMAGE_STD)
+
+    def run(mode):
+        L.check(lib.theia_preprocess_debug_u8(dbg.data_ptr()))
+        try:
+            L.check(lib.theia_preprocess_hw(d.data_ptr(), H, W, out.data_ptr(), Bn, chw, mode, 1, 1, mean, std, 197, 1, S()))
+            torch.cuda.synchronize()
+        finally:
+            L.check(lib.theia_preprocess_debug_u8(0))
+        return dbg.permute(0, 3, 1, 2).clone()
+
+    rs = lambda t: tvF.resize(t, [256, 256], interpolation=tvF.InterpolationMode.BICUBIC, antialias=True)
+    crop = lambda t: t[..., 16:240, 16:240]
+    assert torch.equal(run(1), crop(rs(nchw.to(DEV))))      # float path = torchvision on CUDA tensors
+    assert torch.equal(run(2), crop(rs(nchw)).to(DEV))      # fixed-point path = torchvision on CPU uint8 tensors
+    # the patch rows carry the normalised values of exactly those bytes
+    u8 = run(2)
+    ref = ((u8.float() / 255.0 - torch.tensor(O.IMAGE_MEAN, device=DEV)[:, None, None]) /
+           torch.tensor(O.IMAGE_STD, device=DEV)[:, None, None])
+    pat = ref.unfold(2, 16, 16).unfold(3, 16, 16).permute(0, 2, 3, 1, 4, 5).reshape(Bn, 196, 768)
+    got = out.view(Bn, 197, 768)
+    assert torch.count_nonzero(got[:, 0]) == 0
+    assert relerr(got[:, 1:].float(), pat) < 4e-3
+    # no resize: centre crop, zero padding for the smaller axis (processor semantics, restated by the oracle)
+    want = O.preprocess(img, do_resize=False, do_rescale=False, do_normalize=False)  # uint8 [B,3,224,224]
+    assert want.dtype == torch.uint8 and torch.equal(run(0).cpu(), want)
+
+
 # ----------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("Bn,H", [(2, 3), (3, 12), (40, 6), (100, 12)])  # the last: 8 (image, head) items per CTA, every ring wraps
 def test_attention_fwd_bwd(lib, Bn, H):

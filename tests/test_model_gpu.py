@@ -329,6 +329,31 @@ def test_flat_adamw_frozen_translator_and_scheduler():
     assert opt2.param_groups[0]["lr"] == opt.param_groups[0]["lr"]
 
 
+def test_any_image_extent_against_reference_golden():
+    """images of other extents than 224 x 224 (A1): the reference's processor resizes them to 256 x 256 and / or
+    centre-crops / zero-pads to 224 x 224, so the ViT always sees 196 patches and `interpolate_pos_encoding` is the
+    identity; fixtures from the real reference on CPU uint8 tensors (fixed-point resize)"""
+    fx = torch.load(os.path.join(GOLDEN, "anysize_tiny.pt"), weights_only=False)
+    cfg, P, m = build("facebook/deit-tiny-patch16-224", "dinov2")
+    m.eval()
+    for c in fx["cases"]:
+        H, W = c["H"], c["W"]
+        x = torch.randint(0, 256, (2, H, W, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(H * 1000 + W))
+        with torch.no_grad():
+            f = m.forward_feature(x, do_resize=c["do_resize"], interpolate_pos_encoding=True)  # CPU images, as the fixture
+            f_chw = m.forward_feature(x.permute(0, 3, 1, 2).contiguous(), do_resize=c["do_resize"])
+            f_gpu = m.forward_feature(x.to(DEV), do_resize=c["do_resize"])  # CUDA images: float resize arithmetic
+            f_orc = O.forward_feature(P, x.to(DEV), cfg, do_resize=c["do_resize"])
+        assert tuple(f.shape) == (2, 196, 192)
+        assert relerr(_sl(f).cpu(), c["feature"]["sample"]) < 2e-2, (H, W)
+        assert torch.equal(f, f_chw)
+        assert relerr(f_gpu, f_orc) < 2e-2, (H, W)
+    # back to the default extent on the same context
+    images, _ = O.synthetic_batch(cfg, 2, seed=0, device=DEV)
+    with torch.no_grad():
+        assert relerr(m.forward_feature(images, do_resize=False), O.forward_feature(P, images, cfg, do_resize=False)) < 2e-2
+
+
 def test_flat_adamw_matches_torch_adamw():
     """the fused optimizer tail (two weight-decay groups of optimizers/utils.py:26-33, optional
     clip_grad_norm_) against torch.optim.AdamW on identical gradients."""

@@ -60,6 +60,21 @@ def test_readme_zeros_quickstart():
     torch.testing.assert_close(_sl(f), fx["feature"]["sample"], rtol=1e-4, atol=1e-5)
 
 
+def test_any_image_extent_against_reference_golden():
+    """the reference's processor takes images of any extent: resize to 256 x 256 and / or centre crop / zero pad to
+    224 x 224 (oracle/make_golden.py::anysize ran these through the real reference)"""
+    fx = torch.load(os.path.join(GOLDEN, "anysize_tiny.pt"), weights_only=False)
+    cfg = O.make_config("facebook/deit-tiny-patch16-224", "dinov2")
+    P = O.init_params(cfg, seed=0)
+    assert len(fx["cases"]) >= 6
+    for c in fx["cases"]:
+        H, W = c["H"], c["W"]
+        x = torch.randint(0, 256, (2, H, W, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(H * 1000 + W))
+        f = O.forward_feature(P, x, cfg, do_resize=c["do_resize"])
+        assert tuple(f.shape) == c["feature"]["shape"] == (2, 196, 192)
+        torch.testing.assert_close(_sl(f), c["feature"]["sample"], rtol=1e-4, atol=1e-5)
+
+
 def test_loss_restatement_against_torch_modules():
     """get_loss restated by hand == nn.MSELoss / SmoothL1Loss / CosineEmbeddingLoss (rvfm.py:71-74,153-168)."""
     import torch.nn as nn

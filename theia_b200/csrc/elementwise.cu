@@ -2,6 +2,10 @@
 // [C,H,W] used by the lconv heads (apply / bwd), fused loss reduction + gradient, image
 // pre-processing into patch rows, parameter packing, column reductions.
 // All are warp-shuffle reductions with 16-byte vector accesses; fp32 statistics, bf16 I/O.
+#include <math.h>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "host_util.h"
 #include "theia_b200.h"
@@ -1246,6 +1250,295 @@ extern "C" int theia_preprocess(const uint8_t* images, void* patches, int B, int
                                                    sc[1], sc[2], of[0], of[1], of[2]);
   }
   THEIA_CHECK_LAUNCH("preprocess");
+  return THEIA_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// Any input size (the reference's processor takes whatever the caller has: backbones.py:337-339).  do_resize: bicubic
+// antialias H x W -> 256 x 256 (per-axis tap tables as ATen builds them, support widened by the scale when
+// down-sampling), centre crop 224.  do_resize = 0: centre crop, zero padding when the image is smaller than 224
+// (hf:image_processing_backends.py center_crop).  The 224 x 224 kernels above stay the fast path.
+// --------------------------------------------------------------------------------------------
+namespace theia {
+struct AxisDev {
+  const int* xmin;   // float path (CUDA-tensor semantics): first tap, tap count, normalised weights [256][T]
+  const int* xsize;
+  const float* w;
+  int T;
+  const int* xmin_i;  // fixed-point path (CPU uint8 semantics): int16 weights with `prec` fractional bits [256][Ti]
+  const int* xsize_i;
+  const int* wi;
+  int Ti, prec;
+};
+
+__global__ void __launch_bounds__(256) preprocess_any_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int NT, int P0,
+                                                             int B, int chw, int in_h, int in_w, int mode, AxisDev ax, AxisDev ay,
+                                                             float s0, float s1, float s2, float o0, float o1, float o2,
+                                                             uint8_t* __restrict__ dbg_u8) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * NT * 96;
+  if (t >= total) return;
+  const int k8 = static_cast<int>(t % 96);
+  const long long row = t / 96;
+  const int tok = static_cast<int>(row % NT);
+  const int b = static_cast<int>(row / NT);
+  float o[8];
+  if (tok < P0 || tok >= P0 + 196) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  } else {
+    const int p = tok - P0, py = p / 14, px = p % 14;
+    const int k = k8 * 8;
+    const int c = k >> 8, i = (k >> 4) & 15, j = k & 15;
+    const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const float of = c == 0 ? o0 : (c == 1 ? o1 : o2);
+    const long long pix_stride = chw ? 1 : 3;
+    const long long row_stride = chw ? in_w : static_cast<long long>(in_w) * 3;
+    const uint8_t* base = chw ? img + (static_cast<long long>(b) * 3 + c) * in_h * in_w
+                              : img + static_cast<long long>(b) * in_h * in_w * 3 + c;
+    const int yy = py * 16 + i;
+#pragma unroll 1
+    for (int e = 0; e < 8; ++e) {
+      const int xx = px * 16 + j + e;
+      float acc;
+      if (mode == 0) {  // centre crop / zero pad
+        const int sy = yy + (in_h >= 224 ? (in_h - 224) / 2 : -((224 - in_h) / 2));
+        const int sx = xx + (in_w >= 224 ? (in_w - 224) / 2 : -((224 - in_w) / 2));
+        acc = (sy >= 0 && sy < in_h && sx >= 0 && sx < in_w) ? static_cast<float>(base[sy * row_stride + sx * pix_stride]) : 0.f;
+      } else if (mode == 2) {  // integer arithmetic: horizontal pass rounded and clamped to uint8, then the vertical one
+        const int oy = yy + 16, ox = xx + 16;
+        const int ymin = ay.xmin_i[oy], ysize = ay.xsize_i[oy], xmin = ax.xmin_i[ox], xsize = ax.xsize_i[ox];
+        const int* wx = ax.wi + ox * ax.Ti;
+        const int* wy = ay.wi + oy * ay.Ti;
+        int sv = 1 << (ay.prec - 1);
+        for (int y = 0; y < ysize; ++y) {
+          const uint8_t* src = base + (ymin + y) * row_stride + xmin * pix_stride;
+          int sh = 1 << (ax.prec - 1);
+          for (int x = 0; x < xsize; ++x) sh += static_cast<int>(src[x * pix_stride]) * wx[x];
+          sh >>= ax.prec;
+          sh = sh < 0 ? 0 : (sh > 255 ? 255 : sh);
+          sv += sh * wy[y];
+        }
+        sv >>= ay.prec;
+        acc = static_cast<float>(sv < 0 ? 0 : (sv > 255 ? 255 : sv));
+      } else {  // float arithmetic: horizontal taps first, then vertical, round-half-even to uint8 levels
+        const int oy = yy + 16, ox = xx + 16;
+        const int ymin = ay.xmin[oy], ysize = ay.xsize[oy], xmin = ax.xmin[ox], xsize = ax.xsize[ox];
+        const float* wx = ax.w + ox * ax.T;
+        const float* wy = ay.w + oy * ay.T;
+        acc = 0.f;
+        for (int y = 0; y < ysize; ++y) {
+          const uint8_t* src = base + (ymin + y) * row_stride + xmin * pix_stride;
+          float r = static_cast<float>(src[0]) * wx[0];
+          for (int x = 1; x < xsize; ++x) r += static_cast<float>(src[x * pix_stride]) * wx[x];
+          if (y == 0) acc = r * wy[0];
+          else acc += r * wy[y];
+        }
+        acc = rintf(fminf(fmaxf(acc, 0.f), 255.f));
+      }
+      o[e] = (acc - of) * sc;
+      if (dbg_u8 != nullptr) dbg_u8[((static_cast<long long>(b) * 224 + yy) * 224 + xx) * 3 + c] = static_cast<uint8_t>(acc);
+    }
+  }
+  store8(out + row * 768 + k8 * 8, o);
+}
+
+// Float tap table of one axis (in -> 256), built ON THE DEVICE with the expressions of ATen's CUDA kernel
+// (upsample_antialias::_compute_weights_span / _compute_weights / BicubicFilterFunctor, ATen/native/cuda/UpSample.cuh):
+// its cubic is evaluated in float with nvcc's FMA contraction, which a host restatement does not reproduce bit for
+// bit once the taps fall between pixel centres (down-sampling).
+__device__ __forceinline__ float aa_cubic_f32(float x) {
+  const float a = -0.5f;
+  if (x < 0) x = -x;
+  if (x < 1) return ((a + 2) * x - (a + 3)) * x * x + 1;
+  if (x < 2) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0;
+}
+__global__ void axis_float_table_kernel(int in, int T, int* __restrict__ xmin_out, int* __restrict__ xsize_out,
+                                        float* __restrict__ w_out) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= 256) return;
+  const float scale = static_cast<float>(in) / 256;
+  const float support = (scale >= 1.0) ? (4 * 0.5f) * scale : 4 * 0.5f;
+  const float center = scale * (o + 0.5f);
+  const int xmin = max(static_cast<int>(center - support + 0.5f), 0);
+  int xsize = min(static_cast<int>(center + support + 0.5f), in) - xmin;
+  if (xsize > T) xsize = T;
+  const float xmin_m_center = xmin - center;
+  const float invscale = (scale >= 1.0) ? 1.0 / scale : 1.0;
+  float total_w = 0.0;
+  float* wt = w_out + o * T;
+  int j = 0;
+  for (j = 0; j < xsize; j++) {
+    const float w = aa_cubic_f32((j + xmin_m_center + 0.5f) * invscale);
+    wt[j] = w;
+    total_w += w;
+  }
+  for (j = 0; j < xsize; j++)
+    if (total_w != 0.0) wt[j] /= total_w;
+  for (; j < T; j++) wt[j] = 0.f;
+  xmin_out[o] = xmin, xsize_out[o] = xsize;
+}
+
+}  // namespace theia
+namespace {
+
+struct AxisHost {
+  int in = 0;
+  uint8_t* blob = nullptr;  // device
+  AxisDev dev{};
+};
+
+// per-output tap tables of one axis (in -> 256), as ATen computes them: float (upsample_gen2d_aa_out_frame, CUDA) and
+// double -> int16 (_compute_indices_int16_weights_aa, CPU uint8)
+int build_axis(int in, AxisHost* ah) {
+  const int OUT = 256;
+  const float scale = static_cast<float>(in) / OUT;
+  const float support = scale >= 1.0f ? 2.0f * scale : 2.0f;
+  const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+  const int T = static_cast<int>(ceilf(support)) * 2 + 1;
+  const double dscale = static_cast<double>(in) / OUT;
+  const double dsupport = dscale >= 1.0 ? 2.0 * dscale : 2.0;
+  const double dinv = dscale >= 1.0 ? 1.0 / dscale : 1.0;
+  const int Ti = static_cast<int>(ceil(dsupport)) * 2 + 1;
+  std::vector<int> ints(4 * OUT + static_cast<size_t>(OUT) * Ti, 0);
+  std::vector<float> wf(static_cast<size_t>(OUT) * T, 0.f);
+  std::vector<double> wd(static_cast<size_t>(OUT) * Ti, 0.0);
+  int* xmin = ints.data();
+  int* xsize = xmin + OUT;
+  int* xmin_i = xsize + OUT;
+  int* xsize_i = xmin_i + OUT;
+  int* wi = xsize_i + OUT;
+  double wt_max = 0.0;
+  for (int o = 0; o < OUT; ++o) {
+    {
+      const float center = scale * (o + 0.5f);
+      int lo = static_cast<int>(center - support + 0.5f);
+      if (lo < 0) lo = 0;
+      int hi = static_cast<int>(center + support + 0.5f);
+      if (hi > in) hi = in;
+      int n = hi - lo;
+      if (n > T) n = T;
+      if (n < 0) n = 0;
+      const float lo_m_center = lo - center;
+      float total = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float wj = static_cast<float>(bicubic_aa_filter((j + lo_m_center + 0.5f) * invscale));
+        wf[static_cast<size_t>(o) * T + j] = wj;
+        total += wj;
+      }
+      if (total != 0.f)
+        for (int j = 0; j < n; ++j) wf[static_cast<size_t>(o) * T + j] /= total;
+      xmin[o] = lo, xsize[o] = n;
+    }
+    {
+      const double center = dscale * (o + 0.5);
+      long long lo = static_cast<long long>(center - dsupport + 0.5);
+      if (lo < 0) lo = 0;
+      long long hi = static_cast<long long>(center + dsupport + 0.5);
+      if (hi > in) hi = in;
+      long long n = hi - lo;
+      if (n > Ti) n = Ti;
+      if (n < 0) n = 0;
+      double total = 0.0;
+      for (int j = 0; j < n; ++j) {
+        double x = (j + lo - center + 0.5) * dinv;
+        if (x < 0.0) x = -x;
+        const double a = -0.5;
+        double wv = 0.0;
+        if (x < 1.0) wv = ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0;
+        else if (x < 2.0) wv = (((x - 5.0) * x + 8.0) * x - 4.0) * a;
+        wd[static_cast<size_t>(o) * Ti + j] = wv;
+        total += wv;
+      }
+      if (total != 0.0)
+        for (int j = 0; j < n; ++j) {
+          double& v = wd[static_cast<size_t>(o) * Ti + j];
+          v /= total;
+          if (v > wt_max) wt_max = v;
+        }
+      xmin_i[o] = static_cast<int>(lo), xsize_i[o] = static_cast<int>(n);
+    }
+  }
+  int prec = 0;
+  for (; prec < 22; ++prec) {
+    const int next = static_cast<int>(0.5 + wt_max * (1 << (prec + 1)));
+    if (next >= (1 << 15)) break;
+  }
+  for (size_t q = 0; q < wd.size(); ++q) {
+    const double v = wd[q];
+    wi[q] = v < 0 ? static_cast<int>(-0.5 + v * (1 << prec)) : static_cast<int>(0.5 + v * (1 << prec));
+  }
+  const size_t ibytes = ints.size() * sizeof(int), fbytes = wf.size() * sizeof(float);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ah->blob), ibytes + fbytes);  // first use of this size only
+  if (e == cudaSuccess) e = cudaMemcpy(ah->blob, ints.data(), ibytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(ah->blob + ibytes, wf.data(), fbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {  // float path: xmin / xsize / weights as the CUDA kernel of ATen computes them
+    int* dix = reinterpret_cast<int*>(ah->blob);
+    axis_float_table_kernel<<<1, 256>>>(in, T, dix, dix + OUT, reinterpret_cast<float*>(ah->blob + ibytes));
+    e = cudaDeviceSynchronize();
+  }
+  if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "resize table (%d -> 256): %s", in, cudaGetErrorString(e));
+  const int* di = reinterpret_cast<const int*>(ah->blob);
+  ah->in = in;
+  ah->dev.xmin = di, ah->dev.xsize = di + OUT, ah->dev.xmin_i = di + 2 * OUT, ah->dev.xsize_i = di + 3 * OUT, ah->dev.wi = di + 4 * OUT;
+  ah->dev.w = reinterpret_cast<const float*>(ah->blob + ibytes);
+  ah->dev.T = T, ah->dev.Ti = Ti, ah->dev.prec = prec;
+  return THEIA_OK;
+}
+
+// tap tables are cached per (device, input extent); a handful of extents per process in practice
+int axis_table(int in, AxisDev* out) {
+  static std::vector<AxisHost> cache[64];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const AxisHost& a : cache[dev])
+    if (a.in == in) {
+      *out = a.dev;
+      return THEIA_OK;
+    }
+  AxisHost ah;
+  const int rc = build_axis(in, &ah);
+  if (rc) return rc;
+  cache[dev].push_back(ah);
+  *out = ah.dev;
+  return THEIA_OK;
+}
+}  // namespace
+
+extern "C" int theia_preprocess_hw(const uint8_t* images, int in_h, int in_w, void* patches, int B, int channels_first,
+                                   int do_resize, int do_rescale, int do_normalize, const float* mean3, const float* std3,
+                                   int tokens, int patch_off, void* stream) {
+  if (in_h == 224 && in_w == 224)
+    return theia_preprocess(images, patches, B, channels_first, do_resize, do_rescale, do_normalize, mean3, std3, tokens,
+                            patch_off, stream);
+  if (tokens < patch_off + 196 || patch_off < 0) return set_error(THEIA_ERR_ARG, "preprocess: bad token layout");
+  if (in_h < 1 || in_w < 1 || in_h > 8192 || in_w > 8192) return set_error(THEIA_ERR_ARG, "preprocess: image %d x %d", in_h, in_w);
+  float sc[3], of[3];
+  for (int c = 0; c < 3; ++c) {
+    if (do_normalize) {
+      of[c] = do_rescale ? mean3[c] * 255.f : mean3[c];
+      sc[c] = 1.f / (do_rescale ? std3[c] * 255.f : std3[c]);
+    } else {
+      of[c] = 0.f;
+      sc[c] = do_rescale ? (1.f / 255.f) : 1.f;
+    }
+  }
+  AxisDev ax{}, ay{};
+  if (do_resize) {
+    int rc = axis_table(in_w, &ax);
+    if (rc) return rc;
+    rc = axis_table(in_h, &ay);
+    if (rc) return rc;
+  }
+  const long long total = static_cast<long long>(B) * tokens * 96;
+  preprocess_any_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, S(stream)>>>(
+      images, static_cast<bf16*>(patches), tokens, patch_off, B, channels_first, in_h, in_w, do_resize, ax, ay, sc[0], sc[1],
+      sc[2], of[0], of[1], of[2], g_resize_dbg_u8);
+  THEIA_CHECK_LAUNCH("preprocess_any");
   return THEIA_OK;
 }
 

@@ -118,6 +118,7 @@ struct theia_model {
   long long o_conv_pack = 0, o_conv_unpack = 0;
   long long pack_blocks = 0, unpack_blocks = 0;
   int last_B = 0;
+  int in_h = 224, in_w = 224;  // extent of the images theia_model_forward receives (theia_model_set_input_size)
 };
 
 namespace {
@@ -579,6 +580,13 @@ extern "C" int theia_model_set_grads(theia_model* m, float* grads) {
   return THEIA_OK;
 }
 
+extern "C" int theia_model_set_input_size(theia_model* m, int height, int width) {
+  if (!m || height < 1 || width < 1 || height > 8192 || width > 8192)
+    return set_error(THEIA_ERR_ARG, "theia_model_set_input_size: %d x %d", height, width);
+  m->in_h = height, m->in_w = width;
+  return THEIA_OK;
+}
+
 extern "C" int theia_model_pack_table(theia_model* m, const int** table, void** packbf) {
   if (!m->master || !m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
   *table = reinterpret_cast<const int*>(m->ws + m->o_table);
@@ -879,8 +887,8 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
   const int NT = m->N;
   const int M = B * NT, P = B * 256;
   m->last_B = B;
-  TRY(theia_preprocess(images, c.AB(m->patches), B, channels_first, do_resize, do_rescale, do_normalize, mean3, std3,
-                       NT, m->p0, c.s));
+  TRY(theia_preprocess_hw(images, m->in_h, m->in_w, c.AB(m->patches), B, channels_first, do_resize, do_rescale, do_normalize,
+                          mean3, std3, NT, m->p0, c.s));
   {  // patch embedding + CLS + position embeddings (hf:modeling_vit.py:100-128,153-168)
     theia_gemm_desc d = gemm_base(M, D, 768);
     d.A = c.AB(m->patches), d.lda = 768, d.B = c.PB(m->wpe), d.ldb = 768;

@@ -196,6 +196,7 @@ class RobotVisionFM(nn.Module):
         self._teachers = list(target_feature_sizes.keys()) if target_feature_sizes else []
         self._max_batch = int(kwargs.pop("max_batch", 0))
         self._handle = None
+        self._input_hw = (224, 224)
         self._handle_batch = 0
         self._workspace = None
         self._gbufs = [None, None]
@@ -310,6 +311,7 @@ class RobotVisionFM(nn.Module):
         if self._handle is not None:
             L.lib().theia_model_destroy(self._handle)
         self._handle = None
+        self._input_hw = (224, 224)  # a new context starts at the default extent
         self._workspace = None
         self._gbufs = [None, None]
         self._pack_table = (0, 0)
@@ -415,16 +417,17 @@ class RobotVisionFM(nn.Module):
         if x.dtype != torch.uint8:
             raise NotImplementedError("theia_b200 takes uint8 images in [0,255] (the reference's training input)")
         chw = 1 if (x.shape[1] in (1, 3) and x.shape[-1] not in (1, 3)) else 0
-        H, W = (x.shape[2], x.shape[3]) if chw else (x.shape[1], x.shape[2])
-        if H != 224 or W != 224:
-            raise ValueError(f"Input image size ({H}*{W}) doesn't match model (224*224).")  # hf:modeling_vit.py:160-165
+        if x.shape[1 if chw else 3] != 3:
+            raise NotImplementedError("theia_b200 takes 3-channel images")
+        # any extent is accepted, as by the reference's processor: it resizes to 256 x 256 (do_resize) and ALWAYS
+        # centre-crops / zero-pads to 224 x 224 (hf:image_processing_backends.py center_crop), so the ViT sees 196 patches
+        # whatever came in (and `interpolate_pos_encoding` is the identity: hf:modeling_vit.py:74-76)
         return x.to(self._flat.device, non_blocking=True).contiguous(), chw
 
     def _run_backbone(self, x, kw, run_heads: bool, names, tokens_out=None):
         do_resize = kw.get("do_resize", True)
-        # interpolate_pos_encoding=True is the identity for 224x224 inputs (hf:modeling_vit.py:74-76 returns the
-        # stored table when the patch grid matches); other input sizes are rejected in _prep_images like the
-        # reference rejects them without the flag (hf:modeling_vit.py:160-165)
+        # interpolate_pos_encoding is the identity on this path: the processor always hands the ViT 224 x 224 pixels
+        # (see _prep_images), and hf:modeling_vit.py:74-76 returns the stored table when the patch grid matches
         # the reference's processor resizes CPU uint8 tensors (and PIL / numpy inputs) with torchvision's fixed-point
         # path and CUDA tensors with the float path: reproduce whichever the caller would have got (2 / 1)
         on_cpu = not (torch.is_tensor(x) and x.is_cuda)
@@ -443,6 +446,10 @@ class RobotVisionFM(nn.Module):
                     preds.append(p)
                     ptrs[i] = p.data_ptr()
         self._fwd_id += 1
+        H, W = (images.shape[2], images.shape[3]) if chw else (images.shape[1], images.shape[2])
+        if (H, W) != self._input_hw:
+            L.check(L.lib().theia_model_set_input_size(self._handle, H, W), "theia_model_set_input_size")
+            self._input_hw = (H, W)
         L.check(L.lib().theia_model_forward(
             self._handle, images.data_ptr(), B, chw, (2 if on_cpu else 1) if do_resize else 0, int(kw.get("do_rescale", True)),
             int(kw.get("do_normalize", True)), mean, std, int(run_heads), ptrs,
