@@ -37,7 +37,7 @@ __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
 // NCH = 16-byte chunks per lane (D <= 256 NCH), R = consecutive rows per warp: a warp keeps R rows in flight so that
 // narrow rows (D = 192: 384 B) still put enough bytes on the wire per SM to cover HBM latency
 template <int NCH, int R>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, (NCH * R >= 6) ? 3 : 4)
 layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
                      float eps) {
