@@ -115,6 +115,15 @@ def test_teacher_is_deterministic_and_batch_invariant():
     assert torch.equal(h1, h2) and torch.equal(p1, p2)
     h3, _ = teacher(pv[2:5])
     assert torch.equal(h3, h1[2:5])  # images do not interact; same launch geometry per row tile is not required
+    # a loaded HF model can be handed to the wrappers as is, like in the reference: converted once, then reused
+    hf = hf.to("cuda")
+    imgs = [np.full((224, 224, 3), 7 * i, np.uint8) for i in range(3)]
+    a = T.get_dinov2_feature(hf, _processors()["dinov2"], imgs)
+    conv = hf._theia_b200_teacher
+    b = T.get_dinov2_feature(hf, _processors()["dinov2"], imgs)
+    assert hf._theia_b200_teacher is conv and all(torch.equal(x, y) for x, y in zip(a, b))
+    c = T.get_dinov2_feature(teacher, _processors()["dinov2"], imgs)
+    assert all(torch.equal(x, y) for x, y in zip(a, c))
 
 
 def test_unsupported_teachers_fail_loudly():

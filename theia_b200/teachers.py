@@ -209,10 +209,16 @@ class TeacherViT:
 
 
 def _as_teacher(model, device=None) -> TeacherViT:
+    """a loaded HF model is converted on first use and the converted teacher kept on the module (teachers are frozen:
+    `feature_extraction.py` never updates them)"""
     if isinstance(model, TeacherViT):
         return model
-    dev = device if device is not None else next(model.parameters()).device
-    return TeacherViT.from_hf(model, device=dev)
+    cached = getattr(model, "_theia_b200_teacher", None)
+    dev = torch.device(device) if device is not None else next(model.parameters()).device
+    if cached is None or cached.device != dev:
+        cached = TeacherViT.from_hf(model, device=dev)
+        object.__setattr__(model, "_theia_b200_teacher", cached)
+    return cached
 
 
 def _tokens_to_bchw(visual_tokens: torch.Tensor) -> torch.Tensor:
