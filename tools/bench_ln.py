@@ -30,3 +30,21 @@ for M, D in ((50432, 192), (50432, 384), (50432, 768), (32896, 1024)):
     tf, tb = timeit(fwd) - t0, timeit(bwd) - t0
     by = M * D * 2
     print(f"M={M} D={D}: fwd {tf*1e3:.1f} us ({2*by/tf/1e9:.2f} TB/s)   bwd {tb*1e3:.1f} us ({4*by/tb/1e9:.2f} TB/s)")
+# LayerNorm[C,16,16] of the heads (NHWC): apply + two-pass backward
+for B, C in ((256, 768), (256, 192)):
+    n = 256 * C
+    x = torch.relu(torch.randn(B, n, device="cuda")).to(torch.bfloat16); dy = torch.randn(B, n, device="cuda").to(torch.bfloat16)
+    y = torch.empty_like(x); dx = torch.empty_like(x)
+    g = torch.ones(n, device="cuda"); b = torch.zeros(n, device="cuda")
+    stats = torch.stack([x.float().sum(1), (x.float() ** 2).sum(1)], 1).contiguous()
+    red = torch.zeros(B, 2, device="cuda"); dg = torch.zeros(n, device="cuda"); db = torch.zeros(n, device="cuda")
+    def app():
+        flush.zero_()
+        L.check(lib.theia_ln3d_apply(x.data_ptr(), stats.data_ptr(), g.data_ptr(), b.data_ptr(), y.data_ptr(), B, n, 1e-5, C, 0, 0, s))
+    def bwd3():
+        flush.zero_()
+        L.check(lib.theia_ln3d_bwd(dy.data_ptr(), x.data_ptr(), stats.data_ptr(), g.data_ptr(), red.data_ptr(), dx.data_ptr(), dg.data_ptr(), db.data_ptr(), B, n, 1e-5, 1, C, 0, 0, s))
+    t0 = timeit(lambda: flush.zero_())
+    ta, tb = timeit(app) - t0, timeit(bwd3) - t0
+    by = B * n * 2
+    print(f"ln3d B={B} C={C}: apply {ta*1e3:.1f} us ({2*by/ta/1e9:.2f} TB/s)   bwd (reduce + apply) {tb*1e3:.1f} us ({5*by/tb/1e9:.2f} TB/s)")
