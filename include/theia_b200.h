@@ -160,6 +160,10 @@ int theia_preprocess_debug_u8(void* resized_u8_out);
 int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream);
 int theia_attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B,
                            int N, int H, void* stream);
+/* head dim 80 (google/vit-huge-patch14-224-in21k, src/theia/foundation_models/vision_models/vit.py:36): forward only,
+ * qkv [B*N, 3*H*80] -> out [B*N, H*80], scale 1/sqrt(80), N <= 272; dims 64..79 of a head travel as a second
+ * 32-byte-swizzled operand tile */
+int theia_attention_fwd_hd80(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream);
 /* parameter packing helpers */
 int theia_gather4(const void* in, void* out, int in_is_f32, int out_is_f32, int n0, int n1, int n2, int n3,
                   long long s0, long long s1, long long s2, long long s3, long long base, void* stream);
@@ -268,8 +272,8 @@ int theia_model_backward(theia_model* m, const void* const* dpreds, void* stream
  * Teacher ViT inference: the frozen foundation models the student is distilled from --
  * hf Dinov2Model / CLIPVisionModel / ViTModel as called by src/theia/foundation_models/vision_models/dinov2.py:26-31,
  * vision_language_models/clip.py:26-31 and vision_models/vit.py:23-28.  Forward only; weights are caller-owned
- * device buffers (bf16 GEMM operands [out][in], fp32 biases / LayerNorm affines); head dim 64, <= 272 tokens,
- * hidden <= 1024.  DINOv2's LayerScale is folded into w_o / b_o and w_fc2 / b_fc2 by the caller.
+ * device buffers (bf16 GEMM operands [out][in], fp32 biases / LayerNorm affines); head dim 64 or 80, <= 272 tokens,
+ * hidden <= 1280.  DINOv2's LayerScale is folded into w_o / b_o and w_fc2 / b_fc2 by the caller.
  * ------------------------------------------------------------------------------------------ */
 typedef struct theia_vit_layer {
   const float *ln1_w, *ln1_b;

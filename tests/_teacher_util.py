@@ -71,8 +71,8 @@ def _replay(t, pixel_values):
         x = ln(x, W["pre_ln_w"], W["pre_ln_b"])
     for ly in t._layers:
         qkv = ln(x, ly["ln1_w"], ly["ln1_b"]) @ ly["w_qkv"].float().t() + ly["b_qkv"]
-        q, k, v = (qkv[..., i * D:(i + 1) * D].reshape(B, -1, H, 64).transpose(1, 2) for i in range(3))
-        a = (torch.softmax(q @ k.transpose(2, 3) * 0.125, -1) @ v).transpose(1, 2).reshape(B, -1, D)
+        q, k, v = (qkv[..., i * D:(i + 1) * D].reshape(B, -1, H, D // H).transpose(1, 2) for i in range(3))
+        a = (torch.softmax(q @ k.transpose(2, 3) * (D // H) ** -0.5, -1) @ v).transpose(1, 2).reshape(B, -1, D)
         x = x + a @ ly["w_o"].float().t() + ly["b_o"]
         h = ln(x, ly["ln2_w"], ly["ln2_b"]) @ ly["w_fc1"].float().t() + ly["b_fc1"]
         h = h * torch.sigmoid(1.702 * h) if c["act"] == 1 else F.gelu(h)

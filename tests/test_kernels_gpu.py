@@ -513,6 +513,28 @@ def test_attention_fwd_long_sequences(lib, Bn, H, N):
     assert lib.theia_attention_tc_fwd(qkv.data_ptr(), out.data_ptr(), 0, Bn, 273, H, S()) != 0
 
 
+@pytest.mark.parametrize("Bn,H,N", [(2, 16, 257), (20, 16, 257), (3, 5, 272), (4, 16, 197), (7, 3, 258), (2, 2, 130)])
+def test_attention_fwd_head_dim_80(lib, Bn, H, N):
+    """google/vit-huge-patch14-224-in21k (vit.py:36): 16 heads of 80 dims, 257 tokens; dims 64..79 ride in a second,
+    32-byte-swizzled operand tile"""
+    hd, D = 80, H * 80
+    qkv = rnd(Bn * N, 3 * D, seed=5, scale=1.5)
+    out = torch.full((Bn * N, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(Bn, H, N, device=DEV)
+    L.check(lib.theia_attention_fwd_hd80(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), Bn, N, H, S()))
+    x = qkv.float().view(Bn, N, 3, H, hd)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(2, 3)) * hd ** -0.5
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(Bn * N, D)
+    assert relerr(out.float(), ref) < 8e-3
+    # per 16-column group: a wrong extra tile would show up in columns 64..79 of every head only
+    gn = lambda t: t.view(Bn * N, H, 5, 16).double().pow(2).sum(dim=(0, 1, 3)).sqrt()
+    g = gn(out.float() - ref) / gn(ref)
+    assert g.max().item() < 1e-2, g.tolist()
+    torch.testing.assert_close(lse, torch.logsumexp(s, -1), rtol=1e-4, atol=1e-4)
+    assert lib.theia_attention_fwd_hd80(qkv.data_ptr(), out.data_ptr(), 0, Bn, 273, H, S()) != 0
+
+
 # ----------------------------------------------------------------------------- packing / reductions
 def test_pack_and_reductions(lib):
     w = rnd(96, 160, seed=1, dtype=torch.float32)

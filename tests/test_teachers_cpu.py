@@ -8,7 +8,8 @@ import torch
 from tests._teacher_util import _build, _randomize, _replay
 
 
-@pytest.mark.parametrize("kind,arch", [("dinov2", (128, 2, 3, 14)), ("clip", (128, 2, 3, 14)), ("vit", (192, 3, 2, 16))])
+@pytest.mark.parametrize("kind,arch", [("dinov2", (128, 2, 3, 14)), ("clip", (128, 2, 3, 14)), ("vit", (192, 3, 2, 16)),
+                                       ("vit", (160, 2, 2, 14))])
 def test_weight_conversion_reproduces_the_hf_forward(kind, arch, monkeypatch):
     from theia_b200 import teachers as T
     hf = _randomize(_build(kind, arch), seed=4)

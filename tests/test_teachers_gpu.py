@@ -50,6 +50,7 @@ CASES = [
     ("clip", (768, 12, 12, 16), 4),     # openai/clip-vit-base-patch16: 197 tokens (the student's attention kernel)
     ("vit", (768, 12, 12, 16), 3),      # google/vit-base-patch16-224-in21k
     ("vit", (1024, 16, 4, 14), 2),      # ViT-L/14 geometry, shortened
+    ("vit", (1280, 16, 32, 14), 2),     # google/vit-huge-patch14-224-in21k (the reference's default): head dim 80
 ]
 
 
@@ -96,7 +97,7 @@ def test_teacher_features_match_the_reference(kind, arch, B):
     print(f"   vs fp32 replay of the same bf16 weights: {rel(hid_k, hid_r):.3e} / pooled {rel(pooled_k, pooled_r):.3e}")
     assert rel(hid_k, hid_r) < TOL and rel(pooled_k, pooled_r) < TOL
     # the dict the extraction script writes (feature_extraction_core/models.py:55-95)
-    name = {"dinov2": "facebook_dinov2-large", "clip": "openai_clip-vit-large-patch14", "vit": "google_vit-base"}[kind]
+    name = {"dinov2": "facebook_dinov2-large", "clip": "openai_clip-vit-large-patch14", "vit": "google_vit-huge-patch14-224-in21k"}[kind]
     feats = T.get_feature_outputs(name, teacher, proc, images)[name]
     assert feats["embedding"].dtype == torch.bfloat16 and feats["embedding"].device.type == "cpu"
     g = 224 // arch[3]
@@ -129,9 +130,9 @@ def test_teacher_is_deterministic_and_batch_invariant():
 def test_unsupported_teachers_fail_loudly():
     from theia_b200 import _lib as L
     from theia_b200 import teachers as T
-    vith = _build("vit", (1280, 16, 1, 14))  # google/vit-huge-patch14-224-in21k: head dim 80
-    with pytest.raises(L.TheiaError, match="head dim 64"):
-        T.TeacherViT.from_hf(vith, device="cuda")
+    odd = _build("vit", (768, 8, 1, 16))  # head dim 96
+    with pytest.raises(L.TheiaError, match="head dim 64 and 80"):
+        T.TeacherViT.from_hf(odd, device="cuda")
     small = T.TeacherViT.from_hf(_build("dinov2", (128, 2, 1, 14)), device="cuda")
     with pytest.raises(NotImplementedError):
         T.get_dinov2_feature(small, _processors()["dinov2"], [np.zeros((224, 224, 3), np.uint8)], requires_grad=True)

@@ -92,6 +92,7 @@ SYMBOLS = {
     "theia_preprocess_debug_u8": (_i, [_vp]),
     "theia_attention_tc_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_attention_tc_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "theia_attention_fwd_hd80": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_gather4": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _vp]),
     "theia_cast_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "theia_transpose_cast_bf16": (_i, [_vp, _vp, _i, _i, _vp]),

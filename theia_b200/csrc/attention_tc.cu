@@ -334,25 +334,40 @@ constexpr int AL_ROWS = 272;
 constexpr int AL_TILE = AL_ROWS * 128;
 constexpr int AL_KSTEPS = AL_ROWS / 16;
 constexpr int AL_THREADS = 320;
-constexpr int AL_OFF_P = 3 * AL_TILE;                 // 5 blocks of [128 queries x 64 keys]
-constexpr int AL_OFF_X = AL_OFF_P + 5 * 16384;        // row max / row sum exchange: [2 kinds][2 halves][128] fp32
-constexpr int AL_OFF_T = AL_OFF_X + 2048;             // tail rows: scores / probabilities [272], reductions [32], partial outputs [8][64]
-constexpr int AL_OFF_BAR = AL_OFF_T + 4096;
+constexpr int AL_XTILE = AL_ROWS * 32;                // head dim 80: dims 64..79 as a second [272 x 16] tile (32-byte swizzle)
 constexpr int AL_TAIL_MAX = 2;  // up to this many rows beyond the last full 128-query tile go through the CUDA-core path
-constexpr int AL_SMEM = AL_OFF_BAR + 256 + 1024;
-static_assert(AL_TILE % 1024 == 0 && AL_SMEM <= 232448, "attention (long): shared memory");
+// per-head-dim shared-memory map: Q | K | V operand slots (main tile [+ extra tile]), P (5 blocks of [128 queries x 64
+// keys]), row max / row sum exchange [2][2][128] fp32, tail-row scratch (scores [272], reductions [32], partial
+// outputs [8][80]), barriers
+template <int HD>
+struct AlMap {
+  static constexpr int SLOT = HD > 64 ? ((AL_TILE + AL_XTILE + 1023) / 1024) * 1024 : AL_TILE;
+  static constexpr int OFF_P = 3 * SLOT;
+  static constexpr int OFF_X = OFF_P + 5 * 16384;
+  static constexpr int OFF_T = OFF_X + 2048;
+  static constexpr int OFF_BAR = OFF_T + 4096;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024;
+  static_assert(AL_TILE % 1024 == 0 && SLOT % 1024 == 0 && SMEM <= 232448, "attention (long): shared memory");
+};
+// 32-byte-swizzle descriptors of the extra tiles (SBO = 8 rows x 32 B, version 1, layout type 6)
+constexpr uint32_t AL_DESC32_HI = (256u >> 4) | (1u << 14) | (6u << 29);
+__device__ __forceinline__ uint64_t al_desc32(uint32_t lo) { return (static_cast<uint64_t>(AL_DESC32_HI) << 32) | lo; }
 
-template <int NFIX>
+template <int NFIX, int HD>
 __global__ void __launch_bounds__(AL_THREADS, 1)
 attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_constant__ CUtensorMap tm16,
+                        const __grid_constant__ CUtensorMap tx256, const __grid_constant__ CUtensorMap tx16,
                         const AttnFwdParams p) {
+  using MAP = AlMap<HD>;
+  constexpr bool XT = HD > 64;  // head dim 80 (ViT-H): the last 16 dims live in the extra tiles
+  static_assert(HD == 64 || HD == 80, "head dim 64 or 80");
   extern __shared__ uint8_t smem_raw_at[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_at) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + AL_TILE;
-  uint8_t* sV = smem + 2 * AL_TILE;
-  uint8_t* sP = smem + AL_OFF_P;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AL_OFF_BAR);
+  uint8_t* sK = smem + MAP::SLOT;
+  uint8_t* sV = smem + 2 * MAP::SLOT;
+  uint8_t* sP = smem + MAP::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MAP::OFF_BAR);
   uint64_t* qk_full = bars + 0;
   uint64_t* v_full = bars + 1;
   uint64_t* in_empty = bars + 2;
@@ -365,6 +380,10 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm256);
     tma_prefetch_desc(&tm16);
+    if (XT) {
+      tma_prefetch_desc(&tx256);
+      tma_prefetch_desc(&tx16);
+    }
     mbar_init(qk_full, 1);
     mbar_init(v_full, 1);
     mbar_init(in_empty, 1 + 8);  // tcgen05.commit of the last P V + the 8 softmax warps (tail rows read Q / K / V)
@@ -397,24 +416,35 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
       int it = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++it) {
         const int b = item / p.H, h = item - b * p.H;
-        const int row0 = b * N, col0 = h * AT_HD;
+        const int row0 = b * N, col0 = h * HD;
         if (it > 0) mbar_wait(in_empty, (it - 1) & 1);
-        mbar_expect_tx(qk_full, 2 * AL_TILE);
+        mbar_expect_tx(qk_full, 2 * (AL_TILE + (XT ? AL_XTILE : 0)));
         for (int m = 0; m < 2; ++m) {  // q, k column blocks of the fused qkv activation
-          tma_load_2d(&tm256, smem + m * AL_TILE, qk_full, m * D + col0, row0);
-          tma_load_2d(&tm16, smem + m * AL_TILE + 256 * 128, qk_full, m * D + col0, row0 + 256);
+          tma_load_2d(&tm256, smem + m * MAP::SLOT, qk_full, m * D + col0, row0);
+          tma_load_2d(&tm16, smem + m * MAP::SLOT + 256 * 128, qk_full, m * D + col0, row0 + 256);
+          if (XT) {
+            tma_load_2d(&tx256, smem + m * MAP::SLOT + AL_TILE, qk_full, m * D + col0 + 64, row0);
+            tma_load_2d(&tx16, smem + m * MAP::SLOT + AL_TILE + 256 * 32, qk_full, m * D + col0 + 64, row0 + 256);
+          }
         }
-        mbar_expect_tx(v_full, AL_TILE);
+        mbar_expect_tx(v_full, AL_TILE + (XT ? AL_XTILE : 0));
         tma_load_2d(&tm256, sV, v_full, 2 * D + col0, row0);
         tma_load_2d(&tm16, sV + 256 * 128, v_full, 2 * D + col0, row0 + 256);
+        if (XT) {
+          tma_load_2d(&tx256, sV + AL_TILE, v_full, 2 * D + col0 + 64, row0);
+          tma_load_2d(&tx16, sV + AL_TILE + 256 * 32, v_full, 2 * D + col0 + 64, row0 + 256);
+        }
       }
     }
   } else if (warp == 1) {
     const uint32_t idesc_s256 = make_idesc_bf16(128, 256, 0, 0), idesc_s16 = make_idesc_bf16(128, 16, 0, 0);
-    const uint32_t idesc_pv = make_idesc_bf16(128, AT_HD, 0, 1);
+    const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1), idesc_pvx = make_idesc_bf16(128, 16, 0, 1);
     const uint32_t k_lo = at_desc_lo(smem_u32(sK), 16), k2_lo = at_desc_lo(smem_u32(sK) + 256 * 128, 16);
     const uint32_t v_lo = at_desc_lo(smem_u32(sV), 8192), p_lo = at_desc_lo(smem_u32(sP), 16);
     const uint32_t q_lo0 = at_desc_lo(smem_u32(sQ), 16);
+    // extra tiles (dims 64..79): one 16-element k-step for S, a 16-column B operand for P V
+    const uint32_t qx_lo0 = at_desc_lo(smem_u32(sQ) + AL_TILE, 16), kx_lo = at_desc_lo(smem_u32(sK) + AL_TILE, 16);
+    const uint32_t kx2_lo = at_desc_lo(smem_u32(sK) + AL_TILE + 256 * 32, 16), vx_lo = at_desc_lo(smem_u32(sV) + AL_TILE, 16);
     auto issue_s = [&](int t) {  // S = Q_t K^T into TMEM columns 0-271
       const uint32_t q_lo = q_lo0 + t * 1024;
       if (elect_one_sync()) {
@@ -422,6 +452,11 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
         for (int k = 0; k < 4; ++k) {
           tc_mma_bf16(tmem_base, at_desc(q_lo + 2 * k), at_desc(k_lo + 2 * k), idesc_s256, k > 0 ? 1u : 0u);
           tc_mma_bf16(tmem_base + 256, at_desc(q_lo + 2 * k), at_desc(k2_lo + 2 * k), idesc_s16, k > 0 ? 1u : 0u);
+        }
+        if (XT) {
+          const uint32_t qx_lo = qx_lo0 + t * 256;  // 128 rows x 32 B
+          tc_mma_bf16(tmem_base, al_desc32(qx_lo), al_desc32(kx_lo), idesc_s256, 1u);
+          tc_mma_bf16(tmem_base + 256, al_desc32(qx_lo), al_desc32(kx2_lo), idesc_s16, 1u);
         }
         tc_commit(s_full);
       }
@@ -439,9 +474,11 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
-          for (int ks = 0; ks < AL_KSTEPS; ++ks)
-            tc_mma_bf16(T_O, at_desc(p_lo + (ks >> 2) * 1024 + (ks & 3) * 2), at_desc(v_lo + ks * 128), idesc_pv,
-                        ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < AL_KSTEPS; ++ks) {
+            const uint64_t pd = at_desc(p_lo + (ks >> 2) * 1024 + (ks & 3) * 2);
+            tc_mma_bf16(T_O, pd, at_desc(v_lo + ks * 128), idesc_pv, ks > 0 ? 1u : 0u);
+            if (XT) tc_mma_bf16(T_O + 64, pd, al_desc32(vx_lo + ks * 32), idesc_pvx, ks > 0 ? 1u : 0u);  // 16 keys x 32 B
+          }
           tc_commit(o_full);
           if (t == nqt - 1) tc_commit(in_empty);
         }
@@ -456,7 +493,7 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
     const float c2 = p.scale * 1.4426950408889634f;
     const uint32_t prow = smem_u32(sP) + r * 128;
     const int sw = r & 7;
-    float* xmax = reinterpret_cast<float*>(smem + AL_OFF_X);  // [2][128]
+    float* xmax = reinterpret_cast<float*>(smem + MAP::OFF_X);  // [2][128]
     float* xsum = xmax + 256;
     const int j0 = hh ? 9 : 0, j1 = hh ? AL_KSTEPS : 9;
     int g = 0;
@@ -520,10 +557,23 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
           for (int tr = 0; tr < ntail; ++tr) {
             const int qrow = nfull * 128 + tr;
             const int tid = threadIdx.x - 64, tw = tid >> 5;
-            float* ts = reinterpret_cast<float*>(smem + AL_OFF_T);  // [272] raw scores, then probabilities
+            float* ts = reinterpret_cast<float*>(smem + MAP::OFF_T);  // [272] raw scores, then probabilities
             float* red = ts + 272;                                  // [0,8) warp maxima, [8,16) warp sums
-            float* part = ts + 320;                                 // [8][64] partial outputs
-            float qf[64];
+            float* part = ts + 320;                                 // [8][HD] partial outputs
+            float qf[HD];
+            if (XT) {  // dims 64..79: [row][32 B], 16-byte chunk c at (c ^ ((row >> 2) & 1))
+              const uint32_t qa = smem_u32(sQ) + AL_TILE + qrow * 32;
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const uint4 u = lds128(qa + ((c ^ ((qrow >> 2) & 1)) << 4));
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = unpack_bf16x2(w4[e]);
+                  qf[64 + c * 8 + 2 * e] = f.x, qf[64 + c * 8 + 2 * e + 1] = f.y;
+                }
+              }
+            }
             {
               const uint32_t qa = smem_u32(sQ) + qrow * 128;
 #pragma unroll
@@ -551,9 +601,24 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
                   acc = fmaf(qf[c * 8 + 2 * e + 1], f.y, acc);
                 }
               }
+              if (XT) {
+                const uint32_t kx = smem_u32(sK) + AL_TILE + j * 32;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  const uint4 u = lds128(kx + ((c ^ ((j >> 2) & 1)) << 4));
+                  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16x2(w4[e]);
+                    acc = fmaf(qf[64 + c * 8 + 2 * e], f.x, acc);
+                    acc = fmaf(qf[64 + c * 8 + 2 * e + 1], f.y, acc);
+                  }
+                }
+              }
               return acc;
             };
-            const float s0 = score(tid);  // keys 0 .. 255 (N >= 256 here)
+            const bool one = tid < N;  // keys 0 .. 255 (all valid when N >= 256: the 257-token case)
+            const float s0 = one ? score(tid) : -INFINITY;
             const bool two = 256 + tid < N;
             const float s1 = two ? score(256 + tid) : -INFINITY;
             const float wm = warp_max(fmaxf(s0, s1));
@@ -563,7 +628,7 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
 #pragma unroll
             for (int k = 1; k < 8; ++k) tm = fmaxf(tm, red[k]);
             const float tmc = tm * c2;
-            const float p0 = ex2_approx_ftz(fmaf(s0, c2, -tmc));
+            const float p0 = one ? ex2_approx_ftz(fmaf(s0, c2, -tmc)) : 0.f;
             const float p1 = two ? ex2_approx_ftz(fmaf(s1, c2, -tmc)) : 0.f;
             ts[tid] = p0;
             if (two) ts[256 + tid] = p1;
@@ -574,20 +639,26 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
 #pragma unroll
             for (int k = 0; k < 8; ++k) tl += red[8 + k];
             // out[d] = sum_j p_j V[j][d]: warp tw takes keys tw, tw + 8, ...; lane = dimension pair
-            float a0 = 0.f, a1 = 0.f;
+            float a0 = 0.f, a1 = 0.f, ax0 = 0.f, ax1 = 0.f;
             const uint32_t va = smem_u32(sV) + (lane & 3) * 4;
+            const uint32_t vxa = smem_u32(sV) + AL_TILE + (lane & 3) * 4;  // lanes 0..7: dims 64 + 2 lane, 65 + 2 lane
             for (int j = tw; j < N; j += 8) {
               const float2 f = unpack_bf16x2(lds32(va + j * 128 + (((lane >> 2) ^ (j & 7)) << 4)));
               const float pj = ts[j];
               a0 = fmaf(pj, f.x, a0), a1 = fmaf(pj, f.y, a1);
+              if (XT && lane < 8) {
+                const float2 g = unpack_bf16x2(lds32(vxa + j * 32 + ((((lane >> 2) & 1) ^ ((j >> 2) & 1)) << 4)));
+                ax0 = fmaf(pj, g.x, ax0), ax1 = fmaf(pj, g.y, ax1);
+              }
             }
-            part[tw * 64 + 2 * lane] = a0, part[tw * 64 + 2 * lane + 1] = a1;
+            if (XT && lane < 8) part[tw * HD + 64 + 2 * lane] = ax0, part[tw * HD + 64 + 2 * lane + 1] = ax1;
+            part[tw * HD + 2 * lane] = a0, part[tw * HD + 2 * lane + 1] = a1;
             asm volatile("bar.sync 5, 256;" ::: "memory");
-            if (tid < 64) {
+            if (tid < HD) {
               float o = 0.f;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) o += part[k * 64 + tid];
-              p.out[(static_cast<long long>(b) * N + qrow) * D + h * AT_HD + tid] = __float2bfloat16(o / tl);
+              for (int k = 0; k < 8; ++k) o += part[k * HD + tid];
+              p.out[(static_cast<long long>(b) * N + qrow) * D + h * HD + tid] = __float2bfloat16(o / tl);
               if (tid == 0 && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * N + qrow] = tm * p.scale + __logf(tl);
             }
             asm volatile("bar.sync 5, 256;" ::: "memory");  // ts / red / part are reused by the next tail row / item
@@ -598,9 +669,13 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
         asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");  // the other half's row sum is in xsum
         mbar_wait(o_full, g & 1);
         tc_fence_after();
-        uint32_t o[2][16];
-        tmem_ld16(trow + AL_ROWS + hh * 32, o[0]);
-        tmem_ld16(trow + AL_ROWS + hh * 32 + 16, o[1]);
+        // output columns of this half-row warp: head dim 64: 32 + 32; head dim 80: 48 + 32
+        constexpr int OC1 = XT ? 48 : 32;
+        const int oc0 = hh ? OC1 : 0, onch = (XT && hh == 0) ? 3 : 2;
+        uint32_t o[3][16];
+        tmem_ld16(trow + AL_ROWS + oc0, o[0]);
+        tmem_ld16(trow + AL_ROWS + oc0 + 16, o[1]);
+        if (XT && hh == 0) tmem_ld16(trow + AL_ROWS + 32, o[2]);
         tmem_ld_wait();
         l += xsum[(hh ^ 1) * 128 + r];
         tc_fence_before();
@@ -608,15 +683,17 @@ attn_tc_fwd_long_kernel(const __grid_constant__ CUtensorMap tm256, const __grid_
         if (lane == 0) mbar_arrive(t_free);
         if (q < N) {
           const float inv = 1.f / l;
-          bf16* dst = p.out + (static_cast<long long>(b) * N + q) * D + h * AT_HD + hh * 32;
+          bf16* dst = p.out + (static_cast<long long>(b) * N + q) * D + h * HD + oc0;
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint32_t pk[8];
+          for (int j = 0; j < 3; ++j) {
+            if (j < onch) {
+              uint32_t pk[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              pk[e] = pack_bf16x2(__uint_as_float(o[j][2 * e]) * inv, __uint_as_float(o[j][2 * e + 1]) * inv);
-            *reinterpret_cast<uint4*>(dst + j * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(dst + j * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              for (int e = 0; e < 8; ++e)
+                pk[e] = pack_bf16x2(__uint_as_float(o[j][2 * e]) * inv, __uint_as_float(o[j][2 * e + 1]) * inv);
+              *reinterpret_cast<uint4*>(dst + j * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(dst + j * 16 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
           }
           if (hh == 0 && p.lse) p.lse[(static_cast<long long>(b) * p.H + h) * N + q] = m * p.scale + __logf(l);
         }
@@ -1090,37 +1167,63 @@ static int encode_qkv_map(CUtensorMap* tm, const void* ptr, long long rows, long
   return encode_tensor_map(tm, ptr, 2, dims, strides, box);
 }
 
+// extra tiles of head dim 80: columns 64..79 of a head, 32-byte swizzle
+static int encode_qkv_map_x(CUtensorMap* tm, const void* ptr, long long rows, long long cols, int box_rows) {
+  uint64_t dims[2] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(rows)};
+  uint64_t strides[1] = {static_cast<uint64_t>(cols) * 2};
+  uint32_t box[2] = {16, static_cast<uint32_t>(box_rows)};
+  return encode_tensor_map(tm, ptr, 2, dims, strides, box, nullptr, 32);
+}
+
+template <int HD>
+static int launch_attn_long(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream) {
+  const int D = H * HD;
+  CUtensorMap t256, t16, x256, x16;
+  int rc2 = encode_qkv_map(&t256, qkv, static_cast<long long>(B) * N, 3LL * D, 256);
+  if (rc2) return rc2;
+  rc2 = encode_qkv_map(&t16, qkv, static_cast<long long>(B) * N, 3LL * D, 16);
+  if (rc2) return rc2;
+  x256 = t256, x16 = t16;
+  if (HD > 64) {
+    rc2 = encode_qkv_map_x(&x256, qkv, static_cast<long long>(B) * N, 3LL * D, 256);
+    if (rc2) return rc2;
+    rc2 = encode_qkv_map_x(&x16, qkv, static_cast<long long>(B) * N, 3LL * D, 16);
+    if (rc2) return rc2;
+  }
+  static bool donel = false;
+  if (!donel) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel<257, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AlMap<HD>::SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel<0, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AlMap<HD>::SMEM);
+    if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc fwd long attr: %s", cudaGetErrorString(e));
+    donel = true;
+  }
+  AttnFwdParams pl;
+  pl.out = static_cast<bf16*>(out);
+  pl.lse = lse;
+  pl.B = B, pl.N = N, pl.H = H, pl.D = D;
+  pl.items = B * H;
+  pl.scale = HD == 64 ? 0.125f : 1.0f / sqrtf(static_cast<float>(HD));
+  const int gridl = pl.items < num_sms() ? pl.items : num_sms();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (N == 257)  // CLS + 16 x 16 patches: compile-time length (the key masks fold away)
+    attn_tc_fwd_long_kernel<257, HD><<<gridl, AL_THREADS, AlMap<HD>::SMEM, st>>>(t256, t16, x256, x16, pl);
+  else
+    attn_tc_fwd_long_kernel<0, HD><<<gridl, AL_THREADS, AlMap<HD>::SMEM, st>>>(t256, t16, x256, x16, pl);
+  THEIA_CHECK_LAUNCH("attention_tc_fwd_long");
+  return THEIA_OK;
+}
+
+// head dim 80 (ViT-H/14 teacher): forward only, through the long-sequence kernel whatever the length (<= 272 tokens)
+extern "C" int theia_attention_fwd_hd80(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream) {
+  if (N > AL_ROWS || N < 1) return set_error(THEIA_ERR_UNSUPPORTED, "attention (head dim 80): %d tokens outside [1, %d]", N, AL_ROWS);
+  return launch_attn_long<80>(qkv, out, lse, B, N, H, stream);
+}
+
 extern "C" int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, int B, int N, int H, void* stream) {
   if (N > AL_ROWS || N < 1) return set_error(THEIA_ERR_UNSUPPORTED, "attention: sequence length %d > %d", N, AL_ROWS);
   const int D = H * AT_HD;
-  if (N > AT_ROWS) {  // 209 .. 272 tokens (ViT-L/14 teachers): the long-sequence forward kernel
-    CUtensorMap t256, t16;
-    int rc2 = encode_qkv_map(&t256, qkv, static_cast<long long>(B) * N, 3LL * D, 256);
-    if (rc2) return rc2;
-    rc2 = encode_qkv_map(&t16, qkv, static_cast<long long>(B) * N, 3LL * D, 16);
-    if (rc2) return rc2;
-    static bool donel = false;
-    if (!donel) {
-      cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel<257>, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AL_SMEM);
-      if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc fwd long attr: %s", cudaGetErrorString(e));
-      donel = true;
-    }
-    AttnFwdParams pl;
-    pl.out = static_cast<bf16*>(out);
-    pl.lse = lse;
-    pl.B = B, pl.N = N, pl.H = H, pl.D = D;
-    pl.items = B * H;
-    pl.scale = 0.125f;
-    const int gridl = pl.items < num_sms() ? pl.items : num_sms();
-    if (N == 257)  // CLS + 16 x 16 patches: compile-time length (the key masks fold away)
-      attn_tc_fwd_long_kernel<257><<<gridl, AL_THREADS, AL_SMEM, static_cast<cudaStream_t>(stream)>>>(t256, t16, pl);
-    else
-      attn_tc_fwd_long_kernel<0><<<gridl, AL_THREADS, AL_SMEM, static_cast<cudaStream_t>(stream)>>>(t256, t16, pl);
-    THEIA_CHECK_LAUNCH("attention_tc_fwd_long");
-    return THEIA_OK;
-  }
+  if (N > AT_ROWS) return launch_attn_long<64>(qkv, out, lse, B, N, H, stream);  // 209 .. 272 tokens (ViT-L/14 teachers)
   CUtensorMap tm;
   int rc = encode_qkv_map(&tm, qkv, static_cast<long long>(B) * N, 3LL * D);
   if (rc) return rc;

@@ -1018,7 +1018,7 @@ static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
 extern "C" int theia_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                                    float* rstd, int M, int D, float eps, void* stream) {
-  if (D % 8 != 0 || D > 1024) return set_error(THEIA_ERR_ARG, "layernorm: D %% 8 == 0 and D <= 1024 required");
+  if (D % 8 != 0 || D > 1280) return set_error(THEIA_ERR_ARG, "layernorm: D %% 8 == 0 and D <= 1280 required");
   if (M <= 0) return THEIA_OK;
   const int wpb = 8;
 #define LNF(NCH, R)                                                                                             \
@@ -1027,7 +1027,8 @@ extern "C" int theia_layernorm_fwd(const void* x, const float* gamma, const floa
   if (D <= 256) LNF(1, 4);
   else if (D <= 512) LNF(2, 2);
   else if (D <= 768) LNF(3, 1);
-  else LNF(4, 1);
+  else if (D <= 1024) LNF(4, 1);
+  else LNF(5, 1);  // ViT-H teacher (D = 1280): forward only
 #undef LNF
   THEIA_CHECK_LAUNCH("layernorm_fwd");
   return THEIA_OK;

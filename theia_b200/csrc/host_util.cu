@@ -50,7 +50,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int encode_tensor_map(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return set_error(THEIA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return set_error(THEIA_ERR_ARG, "TMA base not 16-byte aligned");
@@ -69,7 +69,8 @@ int encode_tensor_map(CUtensorMap* tm, const void* ptr, int rank, const uint64_t
     if (strides_bytes[i] % 16 != 0) return set_error(THEIA_ERR_ARG, "TMA stride %d not a multiple of 16 bytes", i);
   }
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdims, gstr, gbox,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(THEIA_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
   return 0;

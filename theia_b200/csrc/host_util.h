@@ -13,10 +13,11 @@ void count_launch(int n = 1);
 int num_sms();
 // CTAs per MMA the GEMM launcher uses for an N tile of bn and m_tiles 128-row tiles (gemm_tc.cu): 2 = CTA pair
 int gemm_pair_mode(int bn, int m_tiles, int a_mode);
-// rank-D bf16 tensor map, 128-byte swizzle, zero OOB fill. dims[0] is the contiguous dim,
+// rank-D bf16 tensor map, 128-byte (default) or 32-byte swizzle, zero OOB fill. dims[0] is the contiguous dim,
 // strides_bytes has rank-1 entries (dims 1..rank-1).
 int encode_tensor_map(CUtensorMap* tm, const void* ptr, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
+                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr,
+                      int swizzle_bytes = 128);  // 128 or 32
 
 #define THEIA_CHECK_LAUNCH(what)                                                                   \
   do {                                                                                             \

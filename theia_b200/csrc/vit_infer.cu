@@ -36,10 +36,11 @@ VitWs carve(const theia_vit_desc* d, int B) {
 int check_desc(const theia_vit_desc* d, int B) {
   if (!d || !d->layer || !d->w_patch || !d->tok_table) return set_error(THEIA_ERR_ARG, "vit: null descriptor field");
   if (B < 1) return set_error(THEIA_ERR_ARG, "vit: batch %d", B);
-  if (d->hidden != d->heads * 64)
-    return set_error(THEIA_ERR_UNSUPPORTED, "vit: head dim %d (hidden %d / heads %d); the attention kernel is built for 64",
-                     d->heads ? d->hidden / d->heads : 0, d->hidden, d->heads);
-  if (d->hidden > 1024 || d->hidden % 64 != 0) return set_error(THEIA_ERR_UNSUPPORTED, "vit: hidden %d (<= 1024, %% 64)", d->hidden);
+  const int hd = d->heads > 0 ? d->hidden / d->heads : 0;
+  if (d->heads < 1 || d->hidden != d->heads * hd || (hd != 64 && hd != 80))
+    return set_error(THEIA_ERR_UNSUPPORTED, "vit: head dim %d (hidden %d / heads %d); the attention kernels are built for 64 and 80",
+                     hd, d->hidden, d->heads);
+  if (d->hidden > 1280 || d->hidden % 64 != 0) return set_error(THEIA_ERR_UNSUPPORTED, "vit: hidden %d (<= 1280, %% 64)", d->hidden);
   if (d->tokens < 1 || d->tokens > 272) return set_error(THEIA_ERR_UNSUPPORTED, "vit: %d tokens per image (<= 272)", d->tokens);
   if (d->patch_k % 8 != 0 || d->mlp % 8 != 0) return set_error(THEIA_ERR_ARG, "vit: patch_k / mlp must be multiples of 8");
   if (d->patch_off < 0 || d->patch_off + d->patch_tokens > d->tokens) return set_error(THEIA_ERR_ARG, "vit: patch token range");
@@ -140,7 +141,10 @@ extern "C" int theia_vit_forward(const theia_vit_desc* d, const void* patches, i
     const theia_vit_layer& p = d->layer[l];
     TRY(theia_layernorm_fwd(x0, p.ln1_w, p.ln1_b, ln, nullptr, nullptr, M, D, d->ln_eps, s));
     TRY(lin(s, ln, p.w_qkv, p.b_qkv, qkv, M, 3 * D, D, 0));
-    TRY(theia_attention_tc_fwd(qkv, attn, nullptr, B, NT, d->heads, s));
+    if (d->hidden == d->heads * 80)
+      TRY(theia_attention_fwd_hd80(qkv, attn, nullptr, B, NT, d->heads, s));
+    else
+      TRY(theia_attention_tc_fwd(qkv, attn, nullptr, B, NT, d->heads, s));
     TRY(lin(s, attn, p.w_o, p.b_o, x1, M, D, D, THEIA_EPI_RESID, x0));
     TRY(theia_layernorm_fwd(x1, p.ln2_w, p.ln2_b, ln, nullptr, nullptr, M, D, d->ln_eps, s));
     TRY(lin(s, ln, p.w_fc1, p.b_fc1, act, M, d->mlp, D, act_epi));

@@ -10,8 +10,8 @@ the HF one the reference uses (CPU, PIL), its `pixel_values` are patchified on t
 `TeacherViT.from_hf(model)` converts a loaded `Dinov2Model` / `CLIPVisionModel` / `ViTModel` once: bf16 GEMM operands
 (q | k | v fused), fp32 biases and LayerNorm affines, DINOv2's LayerScale folded into the output projections, the
 position table interpolated to the working resolution by the HF module's own `interpolate_pos_encoding`.
-Supported: head dim 64, hidden <= 1024, <= 272 tokens (DINOv2-S/B/L, CLIP ViT-B/L, ViT-B/L at 224 px).  Anything else
-(ViT-H: head dim 80; SAM; Depth-Anything) raises -- there is no PyTorch fallback.  Inference only."""
+Supported: head dim 64 or 80, hidden <= 1280, <= 272 tokens (DINOv2-S/B/L, CLIP ViT-B/L, ViT-B/L/H at 224 px).
+Anything else (SAM, LLaVA, Depth-Anything) raises -- there is no PyTorch fallback.  Inference only."""
 from __future__ import annotations
 
 import ctypes as C
@@ -147,9 +147,9 @@ class TeacherViT:
                     fc2=(sd[b + "output.dense.weight"], sd[b + "output.dense.bias"]))
         else:
             raise L.TheiaError(f"{name}: no CUDA teacher path (supported: Dinov2Model, CLIPVisionModel, ViTModel)")
-        if D != H * 64 or D > 1024:
-            raise L.TheiaError(f"{name}: hidden {D} / heads {H} -- the attention kernel is built for head dim 64, hidden <= 1024 "
-                               "(google/vit-huge-patch14-224-in21k has head dim 80)")
+        if D % H != 0 or D // H not in (64, 80) or D > 1280:
+            raise L.TheiaError(f"{name}: hidden {D} / heads {H} -- the attention kernels are built for head dim 64 and 80, "
+                               "hidden <= 1280")
         g = size // p
         tokens = 1 + g * g
         if tokens > 272 or table.shape[0] != tokens:
@@ -268,8 +268,8 @@ def get_clip_model(model_name: str = "openai/clip-vit-large-patch14", device: An
     return _load("CLIPVisionModel", "AutoProcessor", model_name, device)
 
 
-def get_vit_model(model_name: str = "google/vit-large-patch16-224-in21k", device: Any = "cuda"):
-    """vit.py:36-50 (the reference's default, vit-huge-patch14, has head dim 80: unsupported, raises)"""
+def get_vit_model(model_name: str = "google/vit-huge-patch14-224-in21k", device: Any = "cuda"):
+    """vit.py:36-50"""
     return _load("ViTModel", "AutoImageProcessor", model_name, device)
 
 

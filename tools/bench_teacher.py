@@ -1,4 +1,4 @@
-"""Teacher inference throughput: python tools/bench_teacher.py [dinov2|clip] [B] [--hf]
+"""Teacher inference throughput: python tools/bench_teacher.py [dinov2|clip|vith] [B] [--hf]
 DINOv2-L / CLIP ViT-L/14 architecture, seeded random weights, pixel_values resident on the GPU.
 Prints one JSON line; --hf also times the HF model (fp32 and autocast bf16) the reference would run."""
 import json
@@ -20,7 +20,8 @@ if WORLD > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
 kind = sys.argv[1] if len(sys.argv) > 1 else "dinov2"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-hf = _randomize(_build(kind, (1024, 16, 24, 14)), seed=1)
+ARCH = {"dinov2": ("dinov2", (1024, 16, 24, 14)), "clip": ("clip", (1024, 16, 24, 14)), "vith": ("vit", (1280, 16, 32, 14))}[kind]
+hf = _randomize(_build(*ARCH), seed=1)
 teacher = T.TeacherViT.from_hf(hf, device=torch.device("cuda", LOCAL))
 pv = torch.randn(B, 3, 224, 224, device="cuda")
 
@@ -47,9 +48,9 @@ if WORLD > 1:  # slowest rank
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
 launches = (L.lib().theia_launch_count() - l0) // 7
-N, D, Ly = 257, 1024, 24
+N, D, Ly = 257, ARCH[1][0], ARCH[1][2]
 flops = B * Ly * (2.0 * N * D * D * 12 + 4.0 * N * N * D) + B * 2.0 * N * 592 * D
-out = {"teacher": kind + "-L/14", "n_gpus": WORLD, "batch_per_gpu": B, "ms": ms, "img_per_s": WORLD * B / ms * 1e3,
+out = {"teacher": {"dinov2": "dinov2-L/14", "clip": "clip-L/14", "vith": "vit-H/14"}[kind], "n_gpus": WORLD, "batch_per_gpu": B, "ms": ms, "img_per_s": WORLD * B / ms * 1e3,
        "tflops_per_gpu": flops / ms / 1e9, "launches_per_forward": launches, "scaling": "weak (independent replicas)"}
 if "--hf" in sys.argv:
     hf = hf.to("cuda")
