@@ -140,3 +140,48 @@ def test_unsupported_teachers_fail_loudly():
         small(torch.zeros(1, 3, 196, 196))
     with pytest.raises(NotImplementedError):
         T.get_model("facebook/sam-vit-huge")
+
+
+def test_online_distillation_composes():
+    """teacher forward -> target ingest -> student step, everything on the GPU (what f3 is for: the precomputed
+    feature shards of the reference become optional).  DINOv2 geometry teacher (1024 x 16 x 16 features) feeding a
+    deit-tiny student with the matching lconv head; the targets must equal the reference wrapper's features after the
+    dataloader's rearrange + z-score (data_utils.py:152-153,342-355)."""
+    from oracle import theia_oracle as O
+    from theia_b200 import RobotVisionFM
+    from theia_b200 import teachers as T
+    from theia_b200.data import ingest_targets
+    from theia_b200.optim import FlatAdamW
+    torch.backends.cuda.matmul.allow_tf32 = False
+    name = "facebook/dinov2-large"
+    hf = _randomize(_build("dinov2", (1024, 16, 2, 14)), seed=3).to("cuda")
+    teacher = T.TeacherViT.from_hf(hf)
+    proc = _processors()["dinov2"]
+    cfg = O.make_config("facebook/deit-tiny-patch16-224", "dinov2")
+    student = RobotVisionFM(backbone="facebook/deit-tiny-patch16-224", translator="lconv",
+                            target_feature_sizes=dict(cfg.teachers), translator_kwargs={"hidden_size_factor": 1.0})
+    student.load_state_dict(O.init_params(cfg, seed=0))
+    student = student.to("cuda")
+    opt = FlatAdamW(student, lr=1e-3, weight_decay=0.01)
+    rng = np.random.default_rng(0)
+    images = [rng.integers(0, 256, (224, 224, 3), dtype=np.uint8) for _ in range(4)]
+    _, visual, _ = T.get_dinov2_feature(teacher, proc, images)                  # [B, 1024, 16, 16] fp32
+    mean = visual.mean(dim=(0, 2, 3)).to(torch.bfloat16)
+    std = visual.std(dim=(0, 2, 3)).to(torch.bfloat16)
+    targets = {name: ingest_targets(visual.to(torch.bfloat16), mean, std)}     # bf16 [B, 256, 1024], z-scored
+    with torch.no_grad():                                                      # the reference's route to the same tensor
+        want = hf(**proc(images=images, return_tensors="pt").to("cuda")).last_hidden_state[:, 1:]
+        want = (want.to(torch.bfloat16) - mean) / std
+    assert tuple(targets[name].shape) == (4, 256, 1024)
+    assert rel(targets[name].float(), want.float()) < 2e-2
+    batch = torch.from_numpy(np.stack(images)).to("cuda")
+    losses = []
+    for _ in range(4):
+        pred = student(batch, do_resize=False)
+        out = student.get_loss(pred, targets)
+        opt.zero_grad(set_to_none=True)
+        (0.9 * out["cos_loss"] + 0.1 * out["l1_loss"]).backward()
+        opt.step()
+        losses.append(float(out["cos_loss"].detach()))
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
