@@ -57,7 +57,9 @@ enum {
   THEIA_EPI_STATS = 1 << 9,     /* per-image sum / sum-of-squares of the stored values -> stats     */
   THEIA_EPI_COLSUM = 1 << 10,   /* colsum[n] += sum over rows of the stored (bf16) values           */
   THEIA_EPI_GELU_FWD = 1 << 11, /* v = gelu(v), no derivative output (inference: teacher ViTs)      */
-  THEIA_EPI_QUICK_GELU = 1 << 12 /* v = v * sigmoid(1.702 v)  (hf:activations.py QuickGELUActivation; CLIP) */
+  THEIA_EPI_QUICK_GELU = 1 << 12,/* v = v * sigmoid(1.702 v)  (hf:activations.py QuickGELUActivation; CLIP) */
+  THEIA_EPI_RESID_F32 = 1 << 13 /* v += aux[m,n] with aux in fp32 (with OUT_F32: the fp32 residual stream of the
+                                   teacher path; aux may alias out) */
 };
 
 typedef struct theia_conv_geom {
@@ -113,6 +115,10 @@ int theia_gemm(const theia_gemm_desc* d, void* stream);
 /* nn.LayerNorm(D) rows (hf:modeling_vit.py:325-326,333,340,455).  y = (x-mean)*rstd*gamma+beta */
 int theia_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                         int M, int D, float eps, void* stream);
+/* the same over fp32 rows (the fp32 residual stream of the teacher path); y is bf16, or fp32 when y_is_f32;
+ * D % 4 == 0, D <= 1280 */
+int theia_layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, void* y, int y_is_f32, int M, int D,
+                            float eps, void* stream);
 /* dx = LN'(dy) (+ dadd); dgamma/dbeta are ACCUMULATED (+=) */
 int theia_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                         const void* dadd, void* dx, float* dgamma, float* dbeta, float* dxsum, int M, int D,
@@ -302,6 +308,9 @@ typedef struct theia_vit_desc {
                                           pooled = its CLS rows.  2 = CLIP: last_hidden is the raw encoder output,
                                           pooled = post_layernorm(CLS rows) */
   const theia_vit_layer* layer;        /* HOST array [layers] */
+  int residual_f32;                    /* != 0: the residual stream x is kept in fp32 between the blocks (the bf16
+                                          stream is the largest single error term of a 24-layer forward: 8e-3 of
+                                          the 1e-2 total, measured); costs ~6 % time */
 } theia_vit_desc;
 long long theia_vit_workspace_bytes(const theia_vit_desc* d, int B);
 /* patches: bf16 [B*tokens][patch_k] (theia_patchify_f32); last_hidden: bf16 [B*tokens][hidden]; pooled: bf16

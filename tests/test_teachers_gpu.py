@@ -5,9 +5,10 @@ the real architectures (DINOv2-L, CLIP ViT-L/14, ...) with seeded random weights
 (non-uniform attention, non-trivial LayerScale / LayerNorm affines / biases) without making the network chaotic: with
 much larger q / k gains bf16 rounding of the WEIGHTS alone moves a 12-layer output by 12 % (measured on CPU).
 
-Tolerance: the CUDA path keeps bf16 GEMM operands and a bf16 residual stream (fp32 accumulation, fp32 softmax and
-LayerNorm statistics); against the fp32 reference that is <= 2e-2 relative L2 after 24 layers.  The extraction script
-stores these features as bf16 (feature_extraction_core/models.py:56)."""
+Tolerance: the CUDA path keeps bf16 GEMM operands (fp32 accumulation, fp32 softmax and LayerNorm statistics) and, by
+default, an fp32 residual stream; the bar is 2e-2 relative L2 against the fp32 reference after 24-32 layers (measured:
+~5e-3 with the fp32 stream, ~1.2e-2 with the optional bf16 stream).  The extraction script stores these features as
+bf16 (feature_extraction_core/models.py:56)."""
 import math
 import os
 import sys
@@ -96,6 +97,11 @@ def test_teacher_features_match_the_reference(kind, arch, B):
     hid_k, pooled_k = teacher(pv)
     print(f"   vs fp32 replay of the same bf16 weights: {rel(hid_k, hid_r):.3e} / pooled {rel(pooled_k, pooled_r):.3e}")
     assert rel(hid_k, hid_r) < TOL and rel(pooled_k, pooled_r) < TOL
+    # the bf16 residual stream variant (residual_fp32=False: ~6 % faster, about twice the error) stays within the bar
+    lean = T.TeacherViT.from_hf(hf, residual_fp32=False)
+    hid_b, pooled_b = lean(pv)
+    print(f"   bf16 residual stream: {rel(hid_b, hid_r):.3e} / pooled {rel(pooled_b, pooled_r):.3e}")
+    assert rel(hid_b, hid_r) < TOL and rel(pooled_b, pooled_r) < TOL and teacher.residual_fp32 and not lean.residual_fp32
     # the dict the extraction script writes (feature_extraction_core/models.py:55-95)
     name = {"dinov2": "facebook_dinov2-large", "clip": "openai_clip-vit-large-patch14", "vit": "google_vit-huge-patch14-224-in21k"}[kind]
     feats = T.get_feature_outputs(name, teacher, proc, images)[name]

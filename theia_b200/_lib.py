@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("THEIA_B200_LIB") or os.path.join(_PKG, "libtheia_b200
 OP_K2D, OP_MN2D, OP_CONV_K, OP_CONV_MN = 0, 1, 2, 3
 EPI_GELU, EPI_RELU, EPI_RESID, EPI_OUT_F32, EPI_ATOMIC = 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5
 EPI_MUL_AUX, EPI_MUL_RELUMASK, EPI_POSCLS, EPI_STATS, EPI_COLSUM = 1 << 6, 1 << 7, 1 << 8, 1 << 9, 1 << 10
-EPI_GELU_FWD, EPI_QUICK_GELU = 1 << 11, 1 << 12
+EPI_GELU_FWD, EPI_QUICK_GELU, EPI_RESID_F32 = 1 << 11, 1 << 12, 1 << 13
 MAX_TEACHERS = 8
 
 
@@ -58,7 +58,7 @@ class VitDesc(C.Structure):
                 ("ln_eps", C.c_float), ("act", C.c_int),
                 ("w_patch", C.c_void_p), ("b_patch", C.c_void_p), ("tok_table", C.c_void_p),
                 ("pre_ln_w", C.c_void_p), ("pre_ln_b", C.c_void_p), ("final_ln_w", C.c_void_p), ("final_ln_b", C.c_void_p),
-                ("final_ln_mode", C.c_int), ("layer", C.POINTER(VitLayer))]
+                ("final_ln_mode", C.c_int), ("layer", C.POINTER(VitLayer)), ("residual_f32", C.c_int)]
 
 
 # every symbol include/theia_b200.h declares: name -> (restype, argtypes)
@@ -74,6 +74,7 @@ SYMBOLS = {
     "theia_prof_record": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i)]),
     "theia_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "theia_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "theia_layernorm_fwd_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "theia_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "theia_ln3d_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _vp]),
     "theia_ln3d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _i, _i, _i, _vp]),

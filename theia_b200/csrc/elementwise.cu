@@ -108,6 +108,51 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma
   }
 }
 
+// fp32 rows in (the fp32 residual stream of the teacher path), bf16 or fp32 rows out.  NV = float4 per lane.
+template <int NV, bool OUT_F32>
+__global__ void __launch_bounds__(256, 4)
+layernorm_fwd_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         void* __restrict__ y, int M, int D, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int nv = D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int i = lane + 32 * c;
+    v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nv) v[c] = xr[i];
+    s += (v[c].x + v[c].y) + (v[c].z + v[c].w);
+  }
+  const float mean = warp_sum(s) / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    if (lane + 32 * c < nv) {
+      const float a = v[c].x - mean, b = v[c].y - mean, cc = v[c].z - mean, d = v[c].w - mean;
+      ss += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int i = lane + 32 * c;
+    if (i < nv) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[i], b = reinterpret_cast<const float4*>(beta)[i];
+      const float o0 = (v[c].x - mean) * rstd * g.x + b.x, o1 = (v[c].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[c].z - mean) * rstd * g.z + b.z, o3 = (v[c].w - mean) * rstd * g.w + b.w;
+      if (OUT_F32)
+        reinterpret_cast<float4*>(static_cast<float*>(y) + static_cast<long long>(row) * D)[i] = make_float4(o0, o1, o2, o3);
+      else
+        reinterpret_cast<uint2*>(static_cast<bf16*>(y) + static_cast<long long>(row) * D)[i] =
+            make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+  }
+}
+
 // dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma;  optional + dadd (residual grad).
 // dgamma/dbeta (and optionally the column sums of dx = bias gradient of the producer Linear): per-lane
 // register partials over the rows a warp visits, block-reduced in shared memory, one atomic per column
@@ -1031,6 +1076,24 @@ extern "C" int theia_layernorm_fwd(const void* x, const float* gamma, const floa
   else LNF(5, 1);  // ViT-H teacher (D = 1280): forward only
 #undef LNF
   THEIA_CHECK_LAUNCH("layernorm_fwd");
+  return THEIA_OK;
+}
+
+extern "C" int theia_layernorm_fwd_f32(const float* x, const float* gamma, const float* beta, void* y, int y_is_f32, int M,
+                                       int D, float eps, void* stream) {
+  if (D % 4 != 0 || D > 1280) return set_error(THEIA_ERR_ARG, "layernorm (fp32 rows): D %% 4 == 0 and D <= 1280 required");
+  if (M <= 0) return THEIA_OK;
+  const unsigned grid = static_cast<unsigned>((M + 7) / 8);
+#define LNF32(NV)                                                                                     \
+  do {                                                                                                \
+    if (y_is_f32) layernorm_fwd_f32_kernel<NV, true><<<grid, 256, 0, S(stream)>>>(x, gamma, beta, y, M, D, eps);  \
+    else layernorm_fwd_f32_kernel<NV, false><<<grid, 256, 0, S(stream)>>>(x, gamma, beta, y, M, D, eps);          \
+  } while (0)
+  if (D <= 512) LNF32(4);
+  else if (D <= 1024) LNF32(8);
+  else LNF32(10);
+#undef LNF32
+  THEIA_CHECK_LAUNCH("layernorm_fwd_f32");
   return THEIA_OK;
 }
 

@@ -565,6 +565,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (epi & THEIA_EPI_RESID_F32) {  // fp32 residual stream (teacher inference): aux is fp32, indexed like out
+          if (rok) {
+            const float* a32 = reinterpret_cast<const float*>(p.aux) + rowoff + nbase;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (4 * j < ncols) {
+                const float4 q4 = __ldg(reinterpret_cast<const float4*>(a32 + 4 * j));
+                xv[4 * j + 0] += q4.x, xv[4 * j + 1] += q4.y, xv[4 * j + 2] += q4.z, xv[4 * j + 3] += q4.w;
+              }
+            }
+          }
+        }
         if (RING) {  // aux of this chunk is consumed: refill the slot with the chunk AUX_SLOTS ahead
           ring_issue(slot);
           slot = (slot + 1 == AUX_SLOTS) ? 0 : slot + 1;
@@ -741,6 +753,8 @@ static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK&
     THEIA_EPI_CASE(THEIA_EPI_RELU | THEIA_EPI_STATS)
     THEIA_EPI_CASE(THEIA_EPI_GELU_FWD)
     THEIA_EPI_CASE(THEIA_EPI_QUICK_GELU)
+    THEIA_EPI_CASE(THEIA_EPI_RESID_F32 | THEIA_EPI_OUT_F32)
+    THEIA_EPI_CASE(THEIA_EPI_POSCLS | THEIA_EPI_OUT_F32)
 #undef THEIA_EPI_CASE
     default:
       return launch<BN, -1, PAIR>(tmA, tmB, k, stream);
@@ -856,7 +870,9 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   k.splits = d->splits > 0 ? d->splits : 1;
   if (k.splits > 1 && !(d->epi & THEIA_EPI_ATOMIC)) return set_error(THEIA_ERR_ARG, "split-K needs EPI_ATOMIC");
   if ((d->epi & THEIA_EPI_GELU) && !d->out2) return set_error(THEIA_ERR_ARG, "EPI_GELU needs out2");
-  if ((d->epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_AUX | THEIA_EPI_MUL_RELUMASK)) && !d->aux)
+  if ((d->epi & THEIA_EPI_RESID_F32) && (!(d->epi & THEIA_EPI_OUT_F32) || (d->epi & AUXF) || (d->ldo & 3)))
+    return set_error(THEIA_ERR_ARG, "RESID_F32 goes with OUT_F32 only (fp32 aux, no bf16 aux flag)");
+  if ((d->epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_AUX | THEIA_EPI_MUL_RELUMASK | THEIA_EPI_RESID_F32)) && !d->aux)
     return set_error(THEIA_ERR_ARG, "epilogue needs aux");
   if ((d->epi & THEIA_EPI_POSCLS) && !d->pos) return set_error(THEIA_ERR_ARG, "POSCLS needs the token table (pos)");
   if ((d->epi & THEIA_EPI_COLSUM) && !d->colsum) return set_error(THEIA_ERR_ARG, "COLSUM needs colsum");

@@ -27,8 +27,9 @@ VitWs carve(const theia_vit_desc* d, int B) {
     o += align256(elems * 2);
     return at;
   };
-  w.x0 = take(M * D), w.x1 = take(M * D), w.ln = take(M * D), w.qkv = take(3 * M * D), w.attn = take(M * D);
-  w.act = take(M * d->mlp), w.cls = take(static_cast<long long>(B) * D);
+  const long long xs = d->residual_f32 ? 2 : 1;  // fp32 residual stream: 4-byte elements
+  w.x0 = take(xs * M * D), w.x1 = take(xs * M * D), w.ln = take(M * D), w.qkv = take(3 * M * D), w.attn = take(M * D);
+  w.act = take(M * d->mlp), w.cls = take(xs * static_cast<long long>(B) * D);
   w.total = o;
   return w;
 }
@@ -115,14 +116,24 @@ extern "C" int theia_vit_forward(const theia_vit_desc* d, const void* patches, i
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const VitWs w = carve(d, B);
   uint8_t* base = static_cast<uint8_t*>(workspace);
-  bf16* x0 = reinterpret_cast<bf16*>(base + w.x0);
-  bf16* x1 = reinterpret_cast<bf16*>(base + w.x1);
+  void* x0 = base + w.x0;  // residual stream, bf16 or fp32 (residual_f32)
+  void* x1 = base + w.x1;
   bf16* ln = reinterpret_cast<bf16*>(base + w.ln);
   bf16* qkv = reinterpret_cast<bf16*>(base + w.qkv);
   bf16* attn = reinterpret_cast<bf16*>(base + w.attn);
   bf16* act = reinterpret_cast<bf16*>(base + w.act);
-  bf16* cls = reinterpret_cast<bf16*>(base + w.cls);
+  void* cls = base + w.cls;
   const int D = d->hidden, NT = d->tokens, M = B * NT;
+  const bool F = d->residual_f32 != 0;  // residual stream x0 / x1 in fp32
+  // LayerNorm of the residual stream into a bf16 GEMM operand (or, CLIP pre_layrnorm, into the stream itself)
+  auto ln_x = [&](const void* x, const float* g, const float* bta, void* y, bool y_stream, int rows) -> int {
+    if (F) return theia_layernorm_fwd_f32(static_cast<const float*>(x), g, bta, y, y_stream ? 1 : 0, rows, D, d->ln_eps, s);
+    return theia_layernorm_fwd(x, g, bta, y, nullptr, nullptr, rows, D, d->ln_eps, s);
+  };
+  // x_out = x_in + a W^T + b
+  auto resid = [&](const void* a, const void* wt, const float* bias, void* x_out, const void* x_in, int K) -> int {
+    return lin(s, a, wt, bias, x_out, M, D, K, F ? (THEIA_EPI_RESID_F32 | THEIA_EPI_OUT_F32) : THEIA_EPI_RESID, x_in);
+  };
   {  // patch embedding + CLS / position table (hf:modeling_dinov2.py Dinov2Embeddings.forward; modeling_clip.py
      // CLIPVisionEmbeddings.forward; modeling_vit.py:100-128)
     theia_gemm_desc g;
@@ -130,39 +141,39 @@ extern "C" int theia_vit_forward(const theia_vit_desc* d, const void* patches, i
     g.M = M, g.N = D, g.K = d->patch_k, g.a_mode = THEIA_OP_K2D, g.b_mode = THEIA_OP_K2D, g.splits = 1, g.batch_z = 1;
     g.A = patches, g.lda = d->patch_k, g.B = d->w_patch, g.ldb = d->patch_k;
     g.out = d->pre_ln_w ? x1 : x0, g.ldo = D, g.bias = d->b_patch;
-    g.epi = THEIA_EPI_POSCLS, g.pos = d->tok_table, g.tokens = NT, g.tok_p0 = d->patch_off,
+    g.epi = THEIA_EPI_POSCLS | (F ? THEIA_EPI_OUT_F32 : 0), g.pos = d->tok_table, g.tokens = NT, g.tok_p0 = d->patch_off,
     g.tok_p1 = d->patch_off + d->patch_tokens;
     TRY(theia_gemm(&g, s));
-    if (d->pre_ln_w)  // CLIPVisionTransformer.pre_layrnorm
-      TRY(theia_layernorm_fwd(x1, d->pre_ln_w, d->pre_ln_b, x0, nullptr, nullptr, M, D, d->ln_eps, s));
+    if (d->pre_ln_w) TRY(ln_x(x1, d->pre_ln_w, d->pre_ln_b, x0, true, M));  // CLIPVisionTransformer.pre_layrnorm
   }
   const int act_epi = d->act == 1 ? THEIA_EPI_QUICK_GELU : THEIA_EPI_GELU_FWD;
   for (int l = 0; l < d->layers; ++l) {  // pre-norm block: x += Wo attn(LN1 x);  x += W2 act(W1 LN2 x)
     const theia_vit_layer& p = d->layer[l];
-    TRY(theia_layernorm_fwd(x0, p.ln1_w, p.ln1_b, ln, nullptr, nullptr, M, D, d->ln_eps, s));
+    TRY(ln_x(x0, p.ln1_w, p.ln1_b, ln, false, M));
     TRY(lin(s, ln, p.w_qkv, p.b_qkv, qkv, M, 3 * D, D, 0));
     if (d->hidden == d->heads * 80)
       TRY(theia_attention_fwd_hd80(qkv, attn, nullptr, B, NT, d->heads, s));
     else
       TRY(theia_attention_tc_fwd(qkv, attn, nullptr, B, NT, d->heads, s));
-    TRY(lin(s, attn, p.w_o, p.b_o, x1, M, D, D, THEIA_EPI_RESID, x0));
-    TRY(theia_layernorm_fwd(x1, p.ln2_w, p.ln2_b, ln, nullptr, nullptr, M, D, d->ln_eps, s));
+    TRY(resid(attn, p.w_o, p.b_o, x1, x0, D));
+    TRY(ln_x(x1, p.ln2_w, p.ln2_b, ln, false, M));
     TRY(lin(s, ln, p.w_fc1, p.b_fc1, act, M, d->mlp, D, act_epi));
-    TRY(lin(s, act, p.w_fc2, p.b_fc2, x0, M, D, d->mlp, THEIA_EPI_RESID, x1));
+    TRY(resid(act, p.w_fc2, p.b_fc2, x0, x1, d->mlp));
   }
-  const size_t row = sizeof(bf16) * D;
+  const size_t row = sizeof(bf16) * D, xrow = (F ? sizeof(float) : sizeof(bf16)) * static_cast<size_t>(D);
   cudaError_t e = cudaSuccess;
   if (d->final_ln_w && d->final_ln_mode == 1) {  // Dinov2Model.layernorm / ViTModel.layernorm over every token
-    TRY(theia_layernorm_fwd(x0, d->final_ln_w, d->final_ln_b, last_hidden, nullptr, nullptr, M, D, d->ln_eps, s));
+    TRY(ln_x(x0, d->final_ln_w, d->final_ln_b, last_hidden, false, M));
     if (pooled) e = cudaMemcpy2DAsync(pooled, row, last_hidden, row * NT, row, B, cudaMemcpyDeviceToDevice, s);
   } else {
-    e = cudaMemcpyAsync(last_hidden, x0, row * M, cudaMemcpyDeviceToDevice, s);
+    if (F) TRY(theia_cast_bf16(reinterpret_cast<const float*>(x0), last_hidden, static_cast<long long>(M) * D, s));
+    else e = cudaMemcpyAsync(last_hidden, x0, row * M, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess && pooled) {
       if (d->final_ln_w) {  // CLIPVisionTransformer: pooler_output = post_layernorm(last_hidden_state[:, 0])
-        e = cudaMemcpy2DAsync(cls, row, x0, row * NT, row, B, cudaMemcpyDeviceToDevice, s);
-        if (e == cudaSuccess) TRY(theia_layernorm_fwd(cls, d->final_ln_w, d->final_ln_b, pooled, nullptr, nullptr, B, D, d->ln_eps, s));
+        e = cudaMemcpy2DAsync(cls, xrow, x0, xrow * NT, xrow, B, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) TRY(ln_x(cls, d->final_ln_w, d->final_ln_b, pooled, false, B));
       } else {
-        e = cudaMemcpy2DAsync(pooled, row, x0, row * NT, row, B, cudaMemcpyDeviceToDevice, s);
+        e = cudaMemcpy2DAsync(pooled, row, last_hidden, row * NT, row, B, cudaMemcpyDeviceToDevice, s);
       }
     }
   }

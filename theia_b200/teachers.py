@@ -35,7 +35,7 @@ class TeacherViT:
     """A frozen ViT teacher bound to one CUDA device.  `__call__(pixel_values)` returns
     (last_hidden_state [B, tokens, D], pooler_output [B, D]) as the HF model's output of the same names."""
 
-    def __init__(self, kind: str, cfg: dict, tensors: dict, layers: list[dict], device):
+    def __init__(self, kind: str, cfg: dict, tensors: dict, layers: list[dict], device, residual_fp32: bool = True):
         self.kind, self.cfg, self.device = kind, dict(cfg), torch.device(device)
         self._t, self._layers = tensors, layers  # keep every device buffer alive
         self.lib = L.lib()
@@ -51,6 +51,10 @@ class TeacherViT:
         for k in ("w_patch", "b_patch", "tok_table", "pre_ln_w", "pre_ln_b", "final_ln_w", "final_ln_b"):
             setattr(d, k, L.ptr(tensors.get(k)))
         d.layer = self._layer_arr
+        # fp32 residual stream between the blocks: these features are distillation TARGETS; with a bf16 stream the
+        # stream's rounding alone is 8e-3 of the 1e-2 total error of a 24-layer forward (tools / DESIGN section 6)
+        d.residual_f32 = 1 if residual_fp32 else 0
+        self.residual_fp32 = bool(residual_fp32)
         self._desc = d
         self._ws = None
         # what the reference reads off the HF model
@@ -59,7 +63,7 @@ class TeacherViT:
     # ---- conversion -------------------------------------------------------------------------------------------
     @classmethod
     def from_hf(cls, model: torch.nn.Module, device: Any = "cuda", image_size: int | None = None,
-                _convert_only: bool = False) -> "TeacherViT":
+                _convert_only: bool = False, residual_fp32: bool = True) -> "TeacherViT":
         """_convert_only: build the converted buffers on a non-CUDA device (weight-conversion unit tests; such an
         object cannot run a forward)"""
         name = type(model).__name__
@@ -172,7 +176,7 @@ class TeacherViT:
                            "w_fc2": _bf16(ly["fc2"][0], dev), "b_fc2": _f32(ly["fc2"][1], dev)})
         cfg = dict(hidden=D, heads=H, layers=nl, mlp=mlp, tokens=tokens, patch_off=1, patch_tokens=g * g, patch_k=k_pad,
                    ln_eps=eps, act=act, final_ln_mode=fin[2], patch=p, image=size, hf_config=hc)
-        return cls(name, cfg, tensors, layers, dev)
+        return cls(name, cfg, tensors, layers, dev, residual_fp32=residual_fp32)
 
     # ---- forward ----------------------------------------------------------------------------------------------
     def _workspace(self, B: int) -> torch.Tensor:

@@ -22,7 +22,7 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "dinov2"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 ARCH = {"dinov2": ("dinov2", (1024, 16, 24, 14)), "clip": ("clip", (1024, 16, 24, 14)), "vith": ("vit", (1280, 16, 32, 14))}[kind]
 hf = _randomize(_build(*ARCH), seed=1)
-teacher = T.TeacherViT.from_hf(hf, device=torch.device("cuda", LOCAL))
+teacher = T.TeacherViT.from_hf(hf, device=torch.device("cuda", LOCAL), residual_fp32="--bf16-residual" not in sys.argv)
 pv = torch.randn(B, 3, 224, 224, device="cuda")
 
 
@@ -51,7 +51,8 @@ launches = (L.lib().theia_launch_count() - l0) // 7
 N, D, Ly = 257, ARCH[1][0], ARCH[1][2]
 flops = B * Ly * (2.0 * N * D * D * 12 + 4.0 * N * N * D) + B * 2.0 * N * 592 * D
 out = {"teacher": {"dinov2": "dinov2-L/14", "clip": "clip-L/14", "vith": "vit-H/14"}[kind], "n_gpus": WORLD, "batch_per_gpu": B, "ms": ms, "img_per_s": WORLD * B / ms * 1e3,
-       "tflops_per_gpu": flops / ms / 1e9, "launches_per_forward": launches, "scaling": "weak (independent replicas)"}
+       "tflops_per_gpu": flops / ms / 1e9, "launches_per_forward": launches, "scaling": "weak (independent replicas)",
+       "residual_stream": "fp32" if teacher.residual_fp32 else "bf16"}
 if "--hf" in sys.argv:
     hf = hf.to("cuda")
     with torch.no_grad():
