@@ -16,3 +16,29 @@ def test_ddp_two_ranks_match_single_gpu_double_batch():
            "127.0.0.1", "--master-port", "29541", os.path.join(here, "ddp_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DDP_CHECK_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_devices_in_one_process():
+    """One process driving two GPUs: kernels launch on the MODEL's device whatever the current one is, and the
+    per-device state of the library (dynamic shared-memory limits, resize tables, SM count) is set up on each."""
+    from oracle import theia_oracle as O
+    from theia_b200 import RobotVisionFM
+    cfg = O.make_config("facebook/deit-tiny-patch16-224", "dinov2")
+    P = O.init_params(cfg, seed=0)
+    images, targets = O.synthetic_batch(cfg, 3, seed=0)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        m = RobotVisionFM(backbone="facebook/deit-tiny-patch16-224", translator="lconv",
+                          target_feature_sizes=dict(cfg.teachers), translator_kwargs={"hidden_size_factor": 1.0})
+        m.load_state_dict(P)
+        m = m.to(dev)
+        torch.cuda.set_device(0)  # the current device stays cuda:0 throughout
+        pred = m(images.to(dev))  # default do_resize=True: the resize tables too
+        loss = m.get_loss(pred, {k: v.to(dev) for k, v in targets.items()})
+        (0.9 * loss["cos_loss"] + 0.1 * loss["l1_loss"]).backward()
+        torch.cuda.synchronize(dev)
+        g = m.get_parameter("backbone.model.encoder.layer.0.attention.attention.query.weight").grad
+        outs.append((float(loss["cos_loss"]), g.float().cpu()))
+    assert abs(outs[0][0] - outs[1][0]) < 1e-5
+    assert ((outs[0][1] - outs[1][1]).norm() / outs[0][1].norm()).item() < 1e-3  # atomics order only

@@ -1190,13 +1190,12 @@ static int launch_attn_long(const void* qkv, void* out, float* lse, int B, int N
     rc2 = encode_qkv_map_x(&x16, qkv, static_cast<long long>(B) * N, 3LL * D, 16);
     if (rc2) return rc2;
   }
-  static bool donel = false;
-  if (!donel) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel<257, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AlMap<HD>::SMEM);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_tc_fwd_long_kernel<0, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AlMap<HD>::SMEM);
     if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc fwd long attr: %s", cudaGetErrorString(e));
-    donel = true;
   }
   AttnFwdParams pl;
   pl.out = static_cast<bf16*>(out);
@@ -1235,12 +1234,11 @@ extern "C" int theia_attention_tc_fwd(const void* qkv, void* out, float* lse, in
   p.scale = 0.125f;
   const int grid = p.items < num_sms() ? p.items : num_sms();
   {
-    static bool done2 = false;
-    if (!done2) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first_use()) {
       cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd2_kernel<197>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM);
       if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc fwd2 attr: %s", cudaGetErrorString(e));
-      done2 = true;
     }
     // 197 tokens (DeiT: CLS + 196 patches) gets the compile-time sequence length; DeiTNoCLS / DeiTReg run the generic one
     if (N == 197) attn_tc_fwd2_kernel<197><<<grid, AF_THREADS, AF_SMEM, static_cast<cudaStream_t>(stream)>>>(tm, p);
@@ -1274,11 +1272,10 @@ extern "C" int theia_attention_tc_bwd(const void* qkv, const void* out, const vo
     if (rc) return rc;
     rc = encode_qkv_map(&tmk1, qkv, static_cast<long long>(B) * N, 3LL * D, AT_ROWS - 128);
     if (rc) return rc;
-    static bool done2 = false;
-    if (!done2) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first_use()) {
       cudaError_t e = cudaFuncSetAttribute(attn_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
       if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "attn_tc bwd2 attr: %s", cudaGetErrorString(e));
-      done2 = true;
     }
     attn_tc_bwd2_kernel<<<grid, AB_THREADS, AB_SMEM, static_cast<cudaStream_t>(stream)>>>(tmq, tmk0, tmk1, tmd, p);
     THEIA_CHECK_LAUNCH("attention_tc_bwd2");

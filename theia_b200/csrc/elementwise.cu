@@ -1109,11 +1109,9 @@ extern "C" int theia_layernorm_bwd(const void* dy, const void* x, const float* g
 #define LNB(N, ST)                                                                                                   \
   do {                                                                                                               \
     const size_t sm = 3 * D * sizeof(float) + LNB_WARPS * ST * 8 + static_cast<size_t>(LNB_WARPS) * ST * 6 * D;      \
-    static bool attr_done = false;                                                                                   \
-    if (!attr_done) {                                                                                                \
+    static PerDeviceOnce attr_once;                                                                                  \
+    if (attr_once.first_use())                                                                                       \
       cudaFuncSetAttribute(layernorm_bwd_kernel<N, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);    \
-      attr_done = true;                                                                                              \
-    }                                                                                                                \
     layernorm_bwd_kernel<N, ST><<<grid, LNB_WARPS * 32, sm, S(stream)>>>(                                            \
         static_cast<const bf16*>(dy), static_cast<const bf16*>(x), gamma, mean, rstd, static_cast<const bf16*>(dadd), \
         static_cast<bf16*>(dx), dgamma, dbeta, dxsum, M, D);                                                         \

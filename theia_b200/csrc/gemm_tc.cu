@@ -696,12 +696,11 @@ static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
 template <int BN, int EPI_CT, int PAIR>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k, cudaStream_t stream) {
   using C = Cfg<BN, (EPI_CT >= 0) && ((EPI_CT & AUXF) != 0), PAIR>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_CT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(THEIA_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
-    attr_done = true;
   }
   const int max_units = num_sms() / PAIR;
   const int grid = (k.total_items < max_units ? k.total_items : max_units) * PAIR;

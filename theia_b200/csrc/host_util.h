@@ -19,6 +19,19 @@ int encode_tensor_map(CUtensorMap* tm, const void* ptr, int rank, const uint64_t
                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr,
                       int swizzle_bytes = 128);  // 128 or 32
 
+// Once-per-DEVICE latch (function attributes such as the dynamic shared-memory limit are per device: a process that
+// drives several GPUs has to set them on each).  `if (flag.first_use()) { cudaFuncSetAttribute(...); }`
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first_use() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;  // unknown device: always (re)apply
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 #define THEIA_CHECK_LAUNCH(what)                                                                   \
   do {                                                                                             \
     theia::count_launch();                                                                         \
