@@ -58,8 +58,13 @@ enum {
   THEIA_EPI_COLSUM = 1 << 10,   /* colsum[n] += sum over rows of the stored (bf16) values           */
   THEIA_EPI_GELU_FWD = 1 << 11, /* v = gelu(v), no derivative output (inference: teacher ViTs)      */
   THEIA_EPI_QUICK_GELU = 1 << 12,/* v = v * sigmoid(1.702 v)  (hf:activations.py QuickGELUActivation; CLIP) */
-  THEIA_EPI_RESID_F32 = 1 << 13 /* v += aux[m,n] with aux in fp32 (with OUT_F32: the fp32 residual stream of the
+  THEIA_EPI_RESID_F32 = 1 << 13,/* v += aux[m,n] with aux in fp32 (with OUT_F32: the fp32 residual stream of the
                                    teacher path; aux may alias out) */
+  THEIA_EPI_AUX_U8 = 1 << 14    /* modifier: the saved GELU derivative is an 8-bit code, q = rint((g' + 0.129) * 255 /
+                                   1.258) (g' lies in [-0.1289, 1.1289]; step 4.9e-3, below bf16's own step near 1).
+                                   With GELU: out2 is uint8 [M][ldo]; with MUL_AUX: aux is that tensor.  The fc1 GEMM
+                                   is bound by HBM write bandwidth: 3 instead of 4 bytes written per element.
+                                   N and ldo must be multiples of 32 */
 };
 
 typedef struct theia_conv_geom {

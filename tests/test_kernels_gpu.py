@@ -75,6 +75,21 @@ def test_gemm_epilogues(lib, cta_mode):
     F.gelu(xg).sum().backward()
     assert relerr(out2.float(), xg.grad) < 6e-3  # out2 = gelu'(pre-activation), saved for the backward pass
     assert relerr(out.float(), F.gelu(acc)) < 8e-3
+    # the same with the derivative saved as an 8-bit code (EPI_AUX_U8): q = rint((g' + 0.129) * 255 / 1.258)
+    out8 = torch.zeros(M, N, dtype=torch.uint8, device=DEV)
+    outg = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=outg, ldo=N, bias=bias, out2=out8, epi=L.EPI_GELU | L.EPI_AUX_U8)
+    assert torch.equal(outg, out)
+    dec = out8.float() * (1.258 / 255.0) - 0.129
+    assert (dec - xg.grad).abs().max().item() < 3.5e-3  # half a code step (2.5e-3) + the erf approximation
+    assert out8.min().item() >= 0 and xg.grad.min().item() > -0.129 and xg.grad.max().item() < 1.129
+    # ... and consumed by the dgrad epilogue: v *= decode(aux)
+    cs8 = torch.zeros(N, device=DEV)
+    o8 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=o8, ldo=N, aux=out8, epi=L.EPI_MUL_AUX | L.EPI_COLSUM | L.EPI_AUX_U8,
+         colsum=cs8)
+    assert relerr(o8.float(), (acc - bias) * dec) < 6e-3
+    assert relerr(cs8, o8.float().sum(0)) < 1e-4
     # residual
     gemm(lib, M=M, N=N, K=K, A=a, lda=K, B=b, ldb=K, out=out, ldo=N, bias=bias, aux=aux, epi=L.EPI_RESID)
     assert relerr(out.float(), acc + aux.float()) < 6e-3

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("THEIA_B200_LIB") or os.path.join(_PKG, "libtheia_b200
 OP_K2D, OP_MN2D, OP_CONV_K, OP_CONV_MN = 0, 1, 2, 3
 EPI_GELU, EPI_RELU, EPI_RESID, EPI_OUT_F32, EPI_ATOMIC = 1 << 1, 1 << 2, 1 << 3, 1 << 4, 1 << 5
 EPI_MUL_AUX, EPI_MUL_RELUMASK, EPI_POSCLS, EPI_STATS, EPI_COLSUM = 1 << 6, 1 << 7, 1 << 8, 1 << 9, 1 << 10
-EPI_GELU_FWD, EPI_QUICK_GELU, EPI_RESID_F32 = 1 << 11, 1 << 12, 1 << 13
+EPI_GELU_FWD, EPI_QUICK_GELU, EPI_RESID_F32, EPI_AUX_U8 = 1 << 11, 1 << 12, 1 << 13, 1 << 14
 MAX_TEACHERS = 8
 
 

@@ -70,6 +70,12 @@ constexpr int SMEM_LIMIT = 232448;  // 227 KB
 constexpr int AUX_SLOTS = 3;                                  // per-warp ring depth (32x32 bf16 chunks)
 constexpr int AUX_RING_BYTES = EPI_WARPS * AUX_SLOTS * 2048;  // 48 KB
 constexpr int AUXF = THEIA_EPI_RESID | THEIA_EPI_MUL_AUX | THEIA_EPI_MUL_RELUMASK;
+// 8-bit code of gelu'(x) in [-0.1289, 1.1289] (THEIA_EPI_AUX_U8): q = rint((g + 0.129) * 255 / 1.258), step 4.9e-3.
+// The fc1 GEMM writes two [M, 4D] tensors and is bound by HBM WRITE bandwidth (K / 2 = 384 flop per byte written);
+// one byte instead of two for the derivative lifts that bound by a third and halves the dgrad's aux read.
+constexpr float GD_SCALE = 255.0f / 1.258f, GD_BIAS = 0.129f * GD_SCALE, GD_ISCALE = 1.258f / 255.0f, GD_IBIAS = -0.129f;
+// aux operands that go through the per-warp cp.async ring (the u8 codes are 32 bytes per row chunk: direct loads)
+__host__ __device__ constexpr bool epi_uses_ring(int e) { return e >= 0 && (e & AUXF) != 0 && (e & THEIA_EPI_AUX_U8) == 0; }
 
 // PAIR = CTAs per MMA: 1 = cta_group::1 (128 x BN tile per CTA), 2 = cta_group::2 (a cluster of two CTAs on
 // one TPC computes a 256 x BN tile; each CTA stages its own 128 A rows and HALF of the B tile, so the operand
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmK p) {
   // compile-time specialised kernels that read an aux operand stage it through a cp.async ring in shared
   // memory (48 KB in flight per SM: registers alone cannot keep enough HBM reads outstanding)
-  constexpr bool RING = (EPI_CT >= 0) && ((EPI_CT & AUXF) != 0);
+  constexpr bool RING = epi_uses_ring(EPI_CT);
   using C = Cfg<BN, RING, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -437,6 +443,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
       uint32_t vbuf[2][32];  // TMEM loads are software pipelined: chunk ci+1 is in flight while ci is processed
       tmem_ld32(tacc + hsel * 32, vbuf[0]);
+      // 8-bit aux codes (32 bytes per lane and chunk) are fetched one chunk ahead as well
+      uint4 a8[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)}, a8n[2] = {a8[0], a8[0]};
+      auto load_a8 = [&](int ch, uint4 (&dst)[2]) {
+        const int nb = it.n_blk * BN + ch * 32;
+        if (rok && nb + 32 <= p.N) {
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.aux) + rowoff + nb);
+          dst[0] = __ldg(src), dst[1] = __ldg(src + 1);
+        }
+      };
+      if ((epi & THEIA_EPI_MUL_AUX) && (epi & THEIA_EPI_AUX_U8)) load_a8(hsel, a8n);
 #pragma unroll
       for (int ci = 0; ci < NCHUNK / 2; ++ci) {
         const int ch = hsel + 2 * ci;
@@ -452,6 +468,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive_cluster(acc ? te1 : te0);
         }
         if (RING) asm volatile("cp.async.wait_group %0;" ::"n"(AUX_SLOTS - 1) : "memory");  // this chunk's aux landed
+        if ((epi & THEIA_EPI_MUL_AUX) && (epi & THEIA_EPI_AUX_U8)) {
+          a8[0] = a8n[0], a8[1] = a8n[1];
+          if (!last) load_a8(ch + 2, a8n);
+        }
         const int ncols = max(0, min(32, p.N - nbase));  // multiple of 8; 0 = nothing to store in this chunk
         float xv[32];
 #pragma unroll
@@ -508,14 +528,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 16; ++k) xs[k] = xv[16 * hh + k];
             normal_cdf_pdf<16, true>(xs, cdf, pdf);
+            if (epi & THEIA_EPI_AUX_U8) {  // four 8-bit codes per word: pk[4 hh .. 4 hh + 3]
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              pk[8 * hh + k] = pack_bf16x2(fmaf(xs[2 * k], pdf[2 * k], cdf[2 * k]),
-                                           fmaf(xs[2 * k + 1], pdf[2 * k + 1], cdf[2 * k + 1]));
+              for (int k4 = 0; k4 < 4; ++k4) {
+                uint32_t c[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float g = fmaf(xs[4 * k4 + e], pdf[4 * k4 + e], cdf[4 * k4 + e]);
+                  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(c[e]) : "f"(fmaf(g, GD_SCALE, GD_BIAS)));
+                }
+                pk[4 * hh + k4] = __byte_perm(__byte_perm(c[0], c[1], 0x0040), __byte_perm(c[2], c[3], 0x0040), 0x5410);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                pk[8 * hh + k] = pack_bf16x2(fmaf(xs[2 * k], pdf[2 * k], cdf[2 * k]),
+                                             fmaf(xs[2 * k + 1], pdf[2 * k + 1], cdf[2 * k + 1]));
+            }
 #pragma unroll
             for (int k = 0; k < 16; ++k) xv[16 * hh + k] = xs[k] * cdf[k];
           }
-          store_bf16_row(reinterpret_cast<bf16*>(p.out2));
+          if (epi & THEIA_EPI_AUX_U8) {  // 32 bytes per lane: one full sector (N % 32 == 0 is checked by the launcher)
+            if (rok && ncols == 32) {
+              uint8_t* d8 = reinterpret_cast<uint8_t*>(p.out2) + rowoff + nbase;
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d8), "r"(pk[0]), "r"(pk[1]),
+                           "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                           : "memory");
+            }
+          } else {
+            store_bf16_row(reinterpret_cast<bf16*>(p.out2));
+          }
         }
         if (epi & THEIA_EPI_GELU_FWD) {  // inference: gelu(x) = x Phi(x), no derivative output
 #pragma unroll
@@ -537,7 +579,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < 32; ++k) xv[k] = fmaxf(xv[k], 0.f);
         }
-        if (epi & AUXF) {
+        if ((epi & THEIA_EPI_MUL_AUX) && (epi & THEIA_EPI_AUX_U8)) {  // v *= gelu' decoded from the 8-bit codes
+          const uint32_t w8[8] = {a8[0].x, a8[0].y, a8[0].z, a8[0].w, a8[1].x, a8[1].y, a8[1].z, a8[1].w};
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float code = static_cast<float>((w8[k >> 2] >> (8 * (k & 3))) & 0xffu);
+            xv[k] *= fmaf(code, GD_ISCALE, GD_IBIAS);
+          }
+        }
+        if ((epi & AUXF) && !(epi & THEIA_EPI_AUX_U8)) {
           uint32_t au[16];
           if (RING) {
 #pragma unroll
@@ -695,7 +745,7 @@ static int encode_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t 
 
 template <int BN, int EPI_CT, int PAIR>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK& k, cudaStream_t stream) {
-  using C = Cfg<BN, (EPI_CT >= 0) && ((EPI_CT & AUXF) != 0), PAIR>;
+  using C = Cfg<BN, epi_uses_ring(EPI_CT), PAIR>;
   static PerDeviceOnce attr_once;
   if (attr_once.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_CT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -752,6 +802,8 @@ static int dispatch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmK&
     THEIA_EPI_CASE(THEIA_EPI_RELU | THEIA_EPI_STATS)
     THEIA_EPI_CASE(THEIA_EPI_GELU_FWD)
     THEIA_EPI_CASE(THEIA_EPI_QUICK_GELU)
+    THEIA_EPI_CASE(THEIA_EPI_GELU | THEIA_EPI_AUX_U8)
+    THEIA_EPI_CASE(THEIA_EPI_MUL_AUX | THEIA_EPI_COLSUM | THEIA_EPI_AUX_U8)
     THEIA_EPI_CASE(THEIA_EPI_RESID_F32 | THEIA_EPI_OUT_F32)
     THEIA_EPI_CASE(THEIA_EPI_POSCLS | THEIA_EPI_OUT_F32)
 #undef THEIA_EPI_CASE
@@ -869,6 +921,10 @@ extern "C" int theia_gemm(const theia_gemm_desc* d, void* stream_) {
   k.splits = d->splits > 0 ? d->splits : 1;
   if (k.splits > 1 && !(d->epi & THEIA_EPI_ATOMIC)) return set_error(THEIA_ERR_ARG, "split-K needs EPI_ATOMIC");
   if ((d->epi & THEIA_EPI_GELU) && !d->out2) return set_error(THEIA_ERR_ARG, "EPI_GELU needs out2");
+  if ((d->epi & THEIA_EPI_AUX_U8) &&
+      (!(d->epi & (THEIA_EPI_GELU | THEIA_EPI_MUL_AUX)) || (d->epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_RELUMASK)) || d->N % 32 != 0 ||
+       d->ldo % 32 != 0))
+    return set_error(THEIA_ERR_ARG, "AUX_U8 goes with GELU (out2) or MUL_AUX (aux) only, N and ldo multiples of 32");
   if ((d->epi & THEIA_EPI_RESID_F32) && (!(d->epi & THEIA_EPI_OUT_F32) || (d->epi & AUXF) || (d->ldo & 3)))
     return set_error(THEIA_ERR_ARG, "RESID_F32 goes with OUT_F32 only (fp32 aux, no bf16 aux flag)");
   if ((d->epi & (THEIA_EPI_RESID | THEIA_EPI_MUL_AUX | THEIA_EPI_MUL_RELUMASK | THEIA_EPI_RESID_F32)) && !d->aux)

@@ -344,7 +344,7 @@ extern "C" int theia_model_create(const theia_model_config* cfg, theia_model** o
     a.attn = ab.take(M * D, AL);
     a.xmid = ab.take(M * D, AL);
     a.ln2 = ab.take(M * D, AL);
-    a.h = ab.take(M * 4 * D, AL);
+    a.h = ab.take(M * 2 * D, AL);  // gelu'(pre-activation) as 8-bit codes (THEIA_EPI_AUX_U8): M * 4 D bytes
     a.a = ab.take(M * 4 * D, AL);
     a.mean1 = af.take(M, AL);
     a.rstd1 = af.take(M, AL);
@@ -492,7 +492,7 @@ extern "C" int theia_model_debug_ptr(theia_model* m, const char* name, int i, vo
     if (n == "attn") { *ptr = AB(a.attn); *elems = M * D; return 0; }
     if (n == "xmid") { *ptr = AB(a.xmid); *elems = M * D; return 0; }
     if (n == "ln2") { *ptr = AB(a.ln2); *elems = M * D; return 0; }
-    if (n == "h") { *ptr = AB(a.h); *elems = M * 4 * D; return 0; }
+    if (n == "h") { *ptr = AB(a.h); *elems = M * 2 * D; return 0; }  // uint8 codes, M * 4 D bytes
     if (n == "a") { *ptr = AB(a.a); *elems = M * 4 * D; return 0; }
   }
   if (i >= 0 && i < m->T) {
@@ -907,7 +907,7 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
     TRY(linear(c, c.AB(a.attn), c.PB(w.wo), c.W(p.ob), c.AB(a.xmid), M, D, D, THEIA_EPI_RESID, c.AB(m->x[l])));
     TRY(theia_layernorm_fwd(c.AB(a.xmid), c.W(p.ln2w), c.W(p.ln2b), c.AB(a.ln2), c.AF(a.mean2), c.AF(a.rstd2), M, D,
                             m->cfg.ln_eps, c.s));
-    TRY(linear(c, c.AB(a.ln2), c.PB(w.w1), c.W(p.f1b), c.AB(a.a), M, 4 * D, D, THEIA_EPI_GELU, nullptr, c.AB(a.h)));
+    TRY(linear(c, c.AB(a.ln2), c.PB(w.w1), c.W(p.f1b), c.AB(a.a), M, 4 * D, D, THEIA_EPI_GELU | THEIA_EPI_AUX_U8, nullptr, c.AB(a.h)));
     TRY(linear(c, c.AB(a.a), c.PB(w.w2), c.W(p.f2b), c.AB(m->x[l + 1]), M, D, 4 * D, THEIA_EPI_RESID, c.AB(a.xmid)));
   }
   TRY(theia_layernorm_fwd(c.AB(m->x[L]), c.W(m->lnfw), c.W(m->lnfb), c.AB(m->tokens), c.AF(m->meanf), c.AF(m->rstdf), M,
@@ -1067,7 +1067,7 @@ extern "C" int theia_model_backward(theia_model* m, const void* const* dpreds, v
     const LayerA& a = m->la[l];
     // MLP
     TRY(wgrad(c, dx, c.AB(a.a), c.G(p.f2w), M, D, 4 * D));
-    TRY(linear_dgrad(c, dx, c.PB(w.w2), c.AB(m->dh), M, 4 * D, D, THEIA_EPI_MUL_AUX | THEIA_EPI_COLSUM, c.AB(a.h),
+    TRY(linear_dgrad(c, dx, c.PB(w.w2), c.AB(m->dh), M, 4 * D, D, THEIA_EPI_MUL_AUX | THEIA_EPI_COLSUM | THEIA_EPI_AUX_U8, c.AB(a.h),
                      c.G(p.f1b)));
     TRY(wgrad(c, c.AB(m->dh), c.AB(a.ln2), c.G(p.f1w), M, 4 * D, D));
     TRY(linear_dgrad(c, c.AB(m->dh), c.PB(w.w1), c.AB(m->dln), M, D, 4 * D, 0));
