@@ -94,3 +94,42 @@ def test_cpu_model_refuses_to_compute():
                       target_feature_sizes={"facebook/dinov2-large": (1024, 16, 16)})
     with pytest.raises(_lib.TheiaError):
         m.forward_feature(torch.zeros((1, 224, 224, 3), dtype=torch.uint8), do_resize=False)
+
+
+def test_header_is_plain_c():
+    """include/theia_b200.h is the boundary a C / cgo / JNI binding would include: it must compile as C99."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "theia_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_teacher_descriptor_host_logic(lib):
+    """theia_vit_* host-side checks (no GPU work): workspace carving and the unsupported-geometry errors"""
+    from theia_b200 import _lib as L
+    layers = (L.VitLayer * 2)()
+    d = L.VitDesc()
+    d.hidden, d.heads, d.layers, d.mlp = 1024, 16, 2, 4096
+    d.tokens, d.patch_off, d.patch_tokens, d.patch_k = 257, 1, 256, 592
+    d.ln_eps, d.act, d.final_ln_mode = 1e-6, 0, 1
+    d.layer = layers
+    B, M = 8, 8 * 257
+    lean = lib.theia_vit_workspace_bytes(C.byref(d), B)
+    assert 2 * M * (4 * 1024 + 3 * 1024 + 4096) <= lean < 2 * M * (4 * 1024 + 3 * 1024 + 4096) + (1 << 20)  # x0, x1, ln, attn | qkv | act (bf16) + cls rows
+    d.residual_f32 = 1
+    wide = lib.theia_vit_workspace_bytes(C.byref(d), B)
+    assert wide - lean >= 2 * M * 1024 * 2  # the two stream buffers double
+    assert lib.theia_vit_workspace_bytes(C.byref(d), 0) < 0
+    # geometry the kernels do not cover: rejected before anything is launched
+    d.w_patch, d.tok_table = 1, 1  # non-null placeholders: the checks below come first
+    for field, value, msg in (("heads", 8, b"head dim"), ("tokens", 300, b"tokens"), ("hidden", 2048, b"")):
+        old = getattr(d, field)
+        setattr(d, field, value)
+        rc = lib.theia_vit_forward(C.byref(d), 1, 1, 1, 1, 0, 0)
+        assert rc == 3, (field, rc)  # THEIA_ERR_UNSUPPORTED
+        assert msg in lib.theia_last_error()
+        setattr(d, field, old)
