@@ -161,6 +161,10 @@ int theia_preprocess(const uint8_t* images, void* patches, int B, int channels_f
 int theia_preprocess_hw(const uint8_t* images, int in_h, int in_w, void* patches, int B, int channels_first, int do_resize,
                         int do_rescale, int do_normalize, const float* mean3, const float* std3, int tokens, int patch_off,
                         void* stream);
+/* float pixels (the processor also accepts float tensors: [0, 255] values, or [0, 1] with do_rescale = 0): centre crop /
+ * zero pad to 224 x 224 and the same fused rescale / normalise; no resize on this path */
+int theia_preprocess_f32(const float* images, int in_h, int in_w, void* patches, int B, int channels_first, int do_rescale,
+                         int do_normalize, const float* mean3, const float* std3, int tokens, int patch_off, void* stream);
 /* test hook for the byte stage: resized_u8_out != NULL -> following do_resize calls also write the resized +
  * centre-cropped uint8 image [B,224,224,3] (what tvF.resize(..., antialias=True) + center_crop give the reference) */
 int theia_preprocess_debug_u8(void* resized_u8_out);
@@ -274,6 +278,8 @@ int theia_model_pack(theia_model* m, int skip_linear_cast, void* stream);
 int theia_model_pack_table(theia_model* m, const int** table, void** packbf);
 /* extent of the image batches handed to theia_model_forward from now on (default 224 x 224; see theia_preprocess_hw) */
 int theia_model_set_input_size(theia_model* m, int height, int width);
+/* pixel type of those batches: 0 = uint8 (default), 1 = fp32 (theia_preprocess_f32; do_resize must then be 0) */
+int theia_model_set_input_dtype(theia_model* m, int is_f32);
 int theia_model_forward(theia_model* m, const uint8_t* images, int B, int channels_first, int do_resize,
                         int do_rescale, int do_normalize, const float* mean3, const float* std3, int run_heads, float* const* preds,
                         void* tokens_bf16_out, void* stream);

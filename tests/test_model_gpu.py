@@ -354,6 +354,30 @@ def test_any_image_extent_against_reference_golden():
         assert relerr(m.forward_feature(images, do_resize=False), O.forward_feature(P, images, cfg, do_resize=False)) < 2e-2
 
 
+def test_float_images():
+    """the reference's processor also takes float tensors: values in [0, 255] (default do_rescale) or in [0, 1] with
+    do_rescale=False; same fused arithmetic as for uint8.  Resizing float images is not restated: it raises."""
+    cfg, P, m = build("facebook/deit-tiny-patch16-224", "dinov2")
+    m.eval()
+    images, _ = O.synthetic_batch(cfg, 3, seed=5, device=DEV)
+    with torch.no_grad():
+        f_u8 = m.forward_feature(images, do_resize=False)
+        f_f = m.forward_feature(images.float(), do_resize=False)
+        assert torch.equal(f_u8, f_f)  # identical arithmetic, identical bits
+        f_h = m.forward_feature(images.to(torch.float16), do_resize=False)
+        assert torch.equal(f_u8, f_h)  # 0..255 are exact in fp16
+        x01 = images.float() / 255.0
+        f01 = m.forward_feature(x01, do_resize=False, do_rescale=False)
+        assert relerr(f01, O.forward_feature(P, x01, cfg, do_resize=False, do_rescale=False)) < 2e-2
+        # other extents, channels-first, from the CPU
+        xc = torch.rand(2, 3, 200, 260, generator=torch.Generator().manual_seed(1)) * 255.0
+        fc = m.forward_feature(xc, do_resize=False)
+        assert relerr(fc, O.forward_feature(P, xc.to(DEV), cfg, do_resize=False)) < 2e-2
+        assert torch.equal(m.forward_feature(images, do_resize=False), f_u8)  # and back to uint8 on the same context
+    with pytest.raises(NotImplementedError):
+        m.forward_feature(images.float())  # default do_resize=True
+
+
 def test_flat_adamw_matches_torch_adamw():
     """the fused optimizer tail (two weight-decay groups of optimizers/utils.py:26-33, optional
     clip_grad_norm_) against torch.optim.AdamW on identical gradients."""

@@ -90,6 +90,7 @@ SYMBOLS = {
     "theia_loss_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "theia_preprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _vp]),
     "theia_preprocess_hw": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _vp]),
+    "theia_preprocess_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i, _i, _vp]),
     "theia_preprocess_debug_u8": (_i, [_vp]),
     "theia_attention_tc_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "theia_attention_tc_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -112,6 +113,7 @@ SYMBOLS = {
     "theia_model_pack_table": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "theia_model_set_grads": (_i, [_vp, _vp]),
     "theia_model_set_input_size": (_i, [_vp, _i, _i]),
+    "theia_model_set_input_dtype": (_i, [_vp, _i]),
     "theia_model_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _i,
                                  C.POINTER(_vp), _vp, _vp]),
     "theia_model_backward": (_i, [_vp, C.POINTER(_vp), _vp]),

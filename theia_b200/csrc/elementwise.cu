@@ -1405,6 +1405,43 @@ __global__ void __launch_bounds__(256) preprocess_any_kernel(const uint8_t* __re
   store8(out + row * 768 + k8 * 8, o);
 }
 
+// float images (the processor also takes float tensors: values in [0, 255], or in [0, 1] with do_rescale = 0): centre crop /
+// zero pad to 224 x 224 and the same fused (x - offset) * scale; no resize on this path
+__global__ void __launch_bounds__(256) preprocess_f32_kernel(const float* __restrict__ img, bf16* __restrict__ out, int NT, int P0, int B,
+                                                             int chw, int in_h, int in_w, float s0, float s1, float s2, float o0,
+                                                             float o1, float o2) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * NT * 96;
+  if (t >= total) return;
+  const int k8 = static_cast<int>(t % 96);
+  const long long row = t / 96;
+  const int tok = static_cast<int>(row % NT);
+  const int b = static_cast<int>(row / NT);
+  float o[8];
+  if (tok < P0 || tok >= P0 + 196) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  } else {
+    const int p = tok - P0, py = p / 14, px = p % 14;
+    const int k = k8 * 8;
+    const int c = k >> 8, i = (k >> 4) & 15, j = k & 15;
+    const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const float of = c == 0 ? o0 : (c == 1 ? o1 : o2);
+    const long long pix_stride = chw ? 1 : 3;
+    const long long row_stride = chw ? in_w : static_cast<long long>(in_w) * 3;
+    const float* base = chw ? img + (static_cast<long long>(b) * 3 + c) * in_h * in_w
+                            : img + static_cast<long long>(b) * in_h * in_w * 3 + c;
+    const int sy = py * 16 + i + (in_h >= 224 ? (in_h - 224) / 2 : -((224 - in_h) / 2));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int sx = px * 16 + j + e + (in_w >= 224 ? (in_w - 224) / 2 : -((224 - in_w) / 2));
+      const float v = (sy >= 0 && sy < in_h && sx >= 0 && sx < in_w) ? base[sy * row_stride + sx * pix_stride] : 0.f;
+      o[e] = (v - of) * sc;
+    }
+  }
+  store8(out + row * 768 + k8 * 8, o);
+}
+
 // Float tap table of one axis (in -> 256), built ON THE DEVICE with the expressions of ATen's CUDA kernel
 // (upsample_antialias::_compute_weights_span / _compute_weights / BicubicFilterFunctor, ATen/native/cuda/UpSample.cuh):
 // its cubic is evaluated in float with nvcc's FMA contraction, which a host restatement does not reproduce bit for
@@ -1601,6 +1638,29 @@ extern "C" int theia_preprocess_hw(const uint8_t* images, int in_h, int in_w, vo
       images, static_cast<bf16*>(patches), tokens, patch_off, B, channels_first, in_h, in_w, do_resize, ax, ay, sc[0], sc[1],
       sc[2], of[0], of[1], of[2], g_resize_dbg_u8);
   THEIA_CHECK_LAUNCH("preprocess_any");
+  return THEIA_OK;
+}
+
+extern "C" int theia_preprocess_f32(const float* images, int in_h, int in_w, void* patches, int B, int channels_first,
+                                    int do_rescale, int do_normalize, const float* mean3, const float* std3, int tokens,
+                                    int patch_off, void* stream) {
+  if (tokens < patch_off + 196 || patch_off < 0) return set_error(THEIA_ERR_ARG, "preprocess: bad token layout");
+  if (in_h < 1 || in_w < 1 || in_h > 8192 || in_w > 8192) return set_error(THEIA_ERR_ARG, "preprocess: image %d x %d", in_h, in_w);
+  float sc[3], of[3];
+  for (int c = 0; c < 3; ++c) {
+    if (do_normalize) {
+      of[c] = do_rescale ? mean3[c] * 255.f : mean3[c];
+      sc[c] = 1.f / (do_rescale ? std3[c] * 255.f : std3[c]);
+    } else {
+      of[c] = 0.f;
+      sc[c] = do_rescale ? (1.f / 255.f) : 1.f;
+    }
+  }
+  const long long total = static_cast<long long>(B) * tokens * 96;
+  preprocess_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, S(stream)>>>(
+      images, static_cast<bf16*>(patches), tokens, patch_off, B, channels_first, in_h, in_w, sc[0], sc[1], sc[2], of[0], of[1],
+      of[2]);
+  THEIA_CHECK_LAUNCH("preprocess_f32");
   return THEIA_OK;
 }
 

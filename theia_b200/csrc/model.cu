@@ -119,6 +119,7 @@ struct theia_model {
   long long pack_blocks = 0, unpack_blocks = 0;
   int last_B = 0;
   int in_h = 224, in_w = 224;  // extent of the images theia_model_forward receives (theia_model_set_input_size)
+  int in_f32 = 0;              // pixel type of those images: 0 = uint8, 1 = fp32 (theia_model_set_input_dtype)
 };
 
 namespace {
@@ -587,6 +588,12 @@ extern "C" int theia_model_set_input_size(theia_model* m, int height, int width)
   return THEIA_OK;
 }
 
+extern "C" int theia_model_set_input_dtype(theia_model* m, int is_f32) {
+  if (!m) return set_error(THEIA_ERR_ARG, "theia_model_set_input_dtype: null model");
+  m->in_f32 = is_f32 ? 1 : 0;
+  return THEIA_OK;
+}
+
 extern "C" int theia_model_pack_table(theia_model* m, const int** table, void** packbf) {
   if (!m->master || !m->ws) return set_error(THEIA_ERR_ARG, "model not bound");
   *table = reinterpret_cast<const int*>(m->ws + m->o_table);
@@ -887,8 +894,14 @@ extern "C" int theia_model_forward(theia_model* m, const uint8_t* images, int B,
   const int NT = m->N;
   const int M = B * NT, P = B * 256;
   m->last_B = B;
-  TRY(theia_preprocess_hw(images, m->in_h, m->in_w, c.AB(m->patches), B, channels_first, do_resize, do_rescale, do_normalize,
-                          mean3, std3, NT, m->p0, c.s));
+  if (m->in_f32) {
+    if (do_resize) return set_error(THEIA_ERR_UNSUPPORTED, "float images are not resized on this path (pass do_resize = 0)");
+    TRY(theia_preprocess_f32(reinterpret_cast<const float*>(images), m->in_h, m->in_w, c.AB(m->patches), B, channels_first,
+                             do_rescale, do_normalize, mean3, std3, NT, m->p0, c.s));
+  } else {
+    TRY(theia_preprocess_hw(images, m->in_h, m->in_w, c.AB(m->patches), B, channels_first, do_resize, do_rescale, do_normalize,
+                            mean3, std3, NT, m->p0, c.s));
+  }
   {  // patch embedding + CLS + position embeddings (hf:modeling_vit.py:100-128,153-168)
     theia_gemm_desc d = gemm_base(M, D, 768);
     d.A = c.AB(m->patches), d.lda = 768, d.B = c.PB(m->wpe), d.ldb = 768;

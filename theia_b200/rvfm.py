@@ -197,6 +197,7 @@ class RobotVisionFM(nn.Module):
         self._max_batch = int(kwargs.pop("max_batch", 0))
         self._handle = None
         self._input_hw = (224, 224)
+        self._input_f32 = False
         self._handle_batch = 0
         self._workspace = None
         self._gbufs = [None, None]
@@ -312,6 +313,7 @@ class RobotVisionFM(nn.Module):
             L.lib().theia_model_destroy(self._handle)
         self._handle = None
         self._input_hw = (224, 224)  # a new context starts at the default extent
+        self._input_f32 = False      # ... and at uint8 pixels
         self._workspace = None
         self._gbufs = [None, None]
         self._pack_table = (0, 0)
@@ -415,7 +417,14 @@ class RobotVisionFM(nn.Module):
         if x.dim() == 3:
             x = x[None]
         if x.dtype != torch.uint8:
-            raise NotImplementedError("theia_b200 takes uint8 images in [0,255] (the reference's training input)")
+            # float images (values in [0, 255], or [0, 1] with do_rescale=False): same fused rescale / normalise; the
+            # bicubic resize of float tensors is not restated on this path
+            if not x.dtype.is_floating_point:
+                raise NotImplementedError(f"theia_b200 takes uint8 or floating-point images, not {x.dtype}")
+            if do_resize:
+                raise NotImplementedError("float images are not resized on this path: pass do_resize=False "
+                                          "(uint8 images of any extent are resized like the reference does)")
+            x = x.to(torch.float32)
         chw = 1 if (x.shape[1] in (1, 3) and x.shape[-1] not in (1, 3)) else 0
         if x.shape[1 if chw else 3] != 3:
             raise NotImplementedError("theia_b200 takes 3-channel images")
@@ -450,6 +459,10 @@ class RobotVisionFM(nn.Module):
         if (H, W) != self._input_hw:
             L.check(L.lib().theia_model_set_input_size(self._handle, H, W), "theia_model_set_input_size")
             self._input_hw = (H, W)
+        is_f32 = images.dtype == torch.float32
+        if is_f32 != self._input_f32:
+            L.check(L.lib().theia_model_set_input_dtype(self._handle, int(is_f32)), "theia_model_set_input_dtype")
+            self._input_f32 = is_f32
         L.check(L.lib().theia_model_forward(
             self._handle, images.data_ptr(), B, chw, (2 if on_cpu else 1) if do_resize else 0, int(kw.get("do_rescale", True)),
             int(kw.get("do_normalize", True)), mean, std, int(run_heads), ptrs,
