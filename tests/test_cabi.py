@@ -133,3 +133,34 @@ def test_teacher_descriptor_host_logic(lib):
         assert rc == 3, (field, rc)  # THEIA_ERR_UNSUPPORTED
         assert msg in lib.theia_last_error()
         setattr(d, field, old)
+
+
+def test_image_input_host_logic():
+    """what `RobotVisionFM._prep_images` accepts (backbones.py:337-339 hands the same things to the HF processor):
+    uint8 / float tensors, numpy arrays and PIL lists, HWC or CHW, any extent; host logic only, nothing is computed"""
+    import numpy as np
+    import torch
+    from theia_b200 import RobotVisionFM
+    m = RobotVisionFM(backbone="facebook/deit-tiny-patch16-224",
+                      target_feature_sizes={"facebook/dinov2-large": (1024, 16, 16)})
+    x, chw = m._prep_images(torch.zeros((2, 224, 224, 3), dtype=torch.uint8), True)
+    assert tuple(x.shape) == (2, 224, 224, 3) and chw == 0 and x.dtype == torch.uint8
+    x, chw = m._prep_images(torch.zeros((2, 3, 300, 240), dtype=torch.uint8), True)
+    assert chw == 1 and x.is_contiguous()
+    x, chw = m._prep_images(np.zeros((160, 200, 3), np.uint8), False)  # a single image gets a batch axis
+    assert tuple(x.shape) == (1, 160, 200, 3) and chw == 0
+    try:
+        from PIL import Image
+        imgs = [Image.fromarray(np.full((64, 48, 3), 7, np.uint8)) for _ in range(3)]
+        x, chw = m._prep_images(imgs, True)
+        assert tuple(x.shape) == (3, 64, 48, 3) and chw == 0
+    except ImportError:
+        pass
+    x, chw = m._prep_images(torch.rand(2, 224, 224, 3, dtype=torch.float64), False)  # floats: fp32, no resize
+    assert x.dtype == torch.float32
+    with pytest.raises(NotImplementedError):
+        m._prep_images(torch.rand(2, 224, 224, 3), True)
+    with pytest.raises(NotImplementedError):
+        m._prep_images(torch.zeros((2, 224, 224, 3), dtype=torch.int32), False)
+    with pytest.raises(NotImplementedError):
+        m._prep_images(torch.zeros((2, 224, 224, 4), dtype=torch.uint8), False)
